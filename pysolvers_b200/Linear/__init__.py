@@ -1,0 +1,8 @@
+"""``PySolvers.Linear`` surface (PySolvers/Linear/__init__.py:1-12)."""
+from .base import (IterativeLinearSolver, IterativeLinearSolverType,  # noqa: F401
+                   LinearSolver, LinearSolverType, mvmult)
+from .precond import (Preconditioner, GenericPreconditioner,  # noqa: F401
+                      LeftPreconditioner, RightPreconditioner,
+                      IdentityPreconditioner, PreconditionerType,
+                      IdentityPreconditionerType)
+from .krylov import PCG, PCGSolver  # noqa: F401

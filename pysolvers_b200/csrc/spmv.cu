@@ -1,0 +1,445 @@
+// CSR SpMV for sm_100a: y = A x (+ fused epilogues), fp64 values / int32 indices.
+//
+// Replaces scipy's sequential csr_matvec behind `A*x`
+// (PySolvers/Linear/IterativeLinearSolver.py:104 and every call site listed in
+// SURVEY.md section 2.1).  Two kernels, picked once per matrix from row-length
+// statistics gathered at psb_csr_create:
+//
+//  STREAM (short rows: stencils, FE matrices, AMG operators)
+//    A persistent grid of CTAs walks tiles of 256 (or 512) consecutive rows.  The
+//    tile's nonzeros are one CONTIGUOUS slice of vals/colind, so the CTA streams it
+//    with coalesced 128-bit loads, multiplies by the gathered x[col] (L1/L2 hits for
+//    banded matrices) and parks the products in shared memory.  Then one thread per
+//    row adds its products IN STORED ORDER starting from +0 -- the same sequence of
+//    roundings as scipy's csr_matvec, so y is bit-identical to the reference.
+//    HBM traffic = 12 B/nnz + 4 B/row (rowptr) + x once + y once.
+//
+//  VECTOR (long or very uneven rows)
+//    2..32 lanes per row, strided accumulate, shuffle reduction.
+//
+// The fused x.y (p'Ap of PCG, PCGSolver.py:113) is reduced deterministically:
+// fixed tree inside the CTA, one partial per CTA, and the CTA that draws the last
+// ticket adds the partials in index order.
+#include "spmv.cuh"
+
+#include <algorithm>
+#include <new>
+
+namespace psb {
+
+// ---------------------------------------------------------------------------
+// row statistics (one pass over rowptr)
+// ---------------------------------------------------------------------------
+__global__ void csr_stats_kernel(const int* __restrict__ rowptr, int64_t n_rows,
+                                 int* __restrict__ stats) {
+  int m_row = 0, m_t256 = 0, m_t512 = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_rows;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int a = rowptr[i];
+    m_row = max(m_row, rowptr[i + 1] - a);
+    if ((i & 255) == 0) {
+      int64_t e = min(i + 256, n_rows);
+      m_t256 = max(m_t256, rowptr[e] - a);
+    }
+    if ((i & 511) == 0) {
+      int64_t e = min(i + 512, n_rows);
+      m_t512 = max(m_t512, rowptr[e] - a);
+    }
+  }
+  atomicMax(&stats[0], m_row);
+  atomicMax(&stats[1], m_t256);
+  atomicMax(&stats[2], m_t512);
+}
+
+// ---------------------------------------------------------------------------
+// epilogue shared by both kernels
+// ---------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void epilogue(int64_t row, double sum, const double* __restrict__ x,
+                                         double* __restrict__ y, const EpiArgs& ea,
+                                         double& acc) {
+  if (EPI == EPI_STORE) {
+    y[row] = sum;
+  } else if (EPI == EPI_DOT) {
+    y[row] = sum;
+    acc += __ldg(x + row) * sum;
+  } else if (EPI == EPI_RESID) {
+    y[row] = ea.f[row] - sum;
+  } else if (EPI == EPI_ADD) {
+    y[row] = y[row] + sum;
+  } else if (EPI == EPI_JACOBI) {
+    double r = ea.f[row] - sum;
+    double d = ea.dinv[row] * r;
+    if (ea.omega != 1.0) d = ea.omega * d;
+    y[row] = __ldg(x + row) + d;
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void finish_dot(double acc, const psb_csr A, const EpiArgs& ea,
+                                           double* scratch) {
+  if (EPI != EPI_DOT) return;
+  double t = block_sum(acc, scratch);
+  if (threadIdx.x == 0) A.partials[blockIdx.x] = t;
+  if (last_block(A.ticket)) {
+    double total = sum_partials(A.partials, gridDim.x, scratch);
+    if (threadIdx.x == 0) *ea.dot = total;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// STREAM kernel
+// ---------------------------------------------------------------------------
+template <int EPI, int RPT, bool VEC>
+__global__ void __launch_bounds__(kBlock)
+spmv_stream_kernel(const psb_csr A, const double* __restrict__ x, double* __restrict__ y,
+                   const EpiArgs ea, const int* __restrict__ d_skip, int prod_cap) {
+  constexpr int R = kBlock * RPT;
+  extern __shared__ double smem[];
+  double* prod = smem;                                   // [prod_cap]
+  int*    rp   = reinterpret_cast<int*>(smem + prod_cap); // [R + 1]
+  __shared__ double scratch[kWarps];
+
+  if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
+
+  const int tid = threadIdx.x;
+  const int64_t n_tiles = (A.n_rows + R - 1) / R;
+  double acc = 0.0;
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * R;
+    const int nr = (int)min((int64_t)R, A.n_rows - row0);
+    for (int i = tid; i <= nr; i += kBlock) rp[i] = ld_stream_i(A.rowptr + row0 + i);
+    __syncthreads();
+    const int s = rp[0];
+    const int len = rp[nr] - s;
+
+    // ---- phase 1: stream the tile's nonzeros, products -> shared memory ----
+    if (VEC) {
+      const int base0 = s & ~3;                       // 16-byte aligned start
+      const int nquads = (s - base0 + len + 3) >> 2;
+      for (int q = tid; q < nquads; q += kBlock) {
+        const int g = base0 + (q << 2);
+        int c[4];
+        double v[4];
+        if ((int64_t)g + 4 <= A.nnz) {
+          int4 ci = ld_stream_i4(A.colind + g);
+          double2 v01 = ld_stream2(A.vals + g);
+          double2 v23 = ld_stream2(A.vals + g + 2);
+          c[0] = ci.x; c[1] = ci.y; c[2] = ci.z; c[3] = ci.w;
+          v[0] = v01.x; v[1] = v01.y; v[2] = v23.x; v[3] = v23.y;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            bool ok = (int64_t)g + j < A.nnz;
+            c[j] = ok ? ld_stream_i(A.colind + g + j) : 0;
+            v[j] = ok ? ld_stream(A.vals + g + j) : 0.0;
+          }
+        }
+        double xv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = g + j - s;
+          xv[j] = (k >= 0 && k < len) ? __ldg(x + c[j]) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = g + j - s;
+          if (k >= 0 && k < len) prod[k] = v[j] * xv[j];
+        }
+      }
+    } else {
+      for (int i0 = tid; i0 < len; i0 += 4 * kBlock) {
+        int c[4];
+        double v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i0 + j * kBlock;
+          const bool ok = i < len;
+          c[j] = ok ? ld_stream_i(A.colind + s + i) : 0;
+          v[j] = ok ? ld_stream(A.vals + s + i) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i0 + j * kBlock;
+          if (i < len) prod[i] = v[j] * __ldg(x + c[j]);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 2: one thread per row, sequential sum in stored order --------
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int lr = tid + j * kBlock;
+      if (lr < nr) {
+        const int a = rp[lr] - s, b = rp[lr + 1] - s;
+        double sum = 0.0;
+        for (int k = a; k < b; ++k) sum += prod[k];
+        epilogue<EPI>(row0 + lr, sum, x, y, ea, acc);
+      }
+    }
+    __syncthreads();
+  }
+  finish_dot<EPI>(acc, A, ea, scratch);
+}
+
+// ---------------------------------------------------------------------------
+// VECTOR kernel: W lanes per row
+// ---------------------------------------------------------------------------
+template <int EPI, int W>
+__global__ void __launch_bounds__(kBlock)
+spmv_vector_kernel(const psb_csr A, const double* __restrict__ x, double* __restrict__ y,
+                   const EpiArgs ea, const int* __restrict__ d_skip) {
+  __shared__ double scratch[kWarps];
+  if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
+  constexpr int ROWS = kBlock / W;
+  const int lane = threadIdx.x % W;
+  const int sub  = threadIdx.x / W;
+  double acc = 0.0;
+  const int64_t n_groups = (A.n_rows + ROWS - 1) / ROWS;
+  for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int64_t row = grp * ROWS + sub;
+    double sum = 0.0;
+    if (row < A.n_rows) {
+      const int a = A.rowptr[row], b = A.rowptr[row + 1];
+      for (int k = a + lane; k < b; k += W)
+        sum += ld_stream(A.vals + k) * __ldg(x + ld_stream_i(A.colind + k));
+    }
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o, W);
+    if (row < A.n_rows && lane == 0) epilogue<EPI>(row, sum, x, y, ea, acc);
+  }
+  finish_dot<EPI>(acc, A, ea, scratch);
+}
+
+// ---------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------
+struct LaunchCfg { int grid; size_t smem; };
+
+template <typename K>
+static int occupancy_grid(K kernel, size_t smem, int64_t work_items, int max_grid, int* grid_out) {
+  if (smem > 48 * 1024)
+    PSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem));
+  if (per_sm < 1) per_sm = 1;
+  int64_t g = (int64_t)per_sm * sm_count();
+  g = std::min<int64_t>(g, work_items);
+  g = std::min<int64_t>(g, max_grid);
+  *grid_out = (int)std::max<int64_t>(g, 1);
+  return PSB_OK;
+}
+
+template <int EPI, int RPT, bool VEC>
+static int launch_stream(const psb_csr* A, const double* x, double* y, const EpiArgs& ea,
+                         const int* d_skip, cudaStream_t st) {
+  constexpr int R = kBlock * RPT;
+  const int cap = (A->max_tile_nnz[RPT - 1] + 1) & ~1;   // keep rp[] 8-byte aligned
+  const size_t smem = (size_t)cap * sizeof(double) + (size_t)(R + 1) * sizeof(int);
+  static thread_local int cached_grid = 0;
+  static thread_local size_t cached_smem = 0;
+  static thread_local int64_t cached_tiles = -1;
+  const int64_t tiles = (A->n_rows + R - 1) / R;
+  if (cached_grid == 0 || cached_smem != smem || cached_tiles != tiles) {
+    int g = 0;
+    int rc = occupancy_grid(spmv_stream_kernel<EPI, RPT, VEC>, smem, tiles, A->max_grid, &g);
+    if (rc != PSB_OK) return rc;
+    cached_grid = g; cached_smem = smem; cached_tiles = tiles;
+  }
+  spmv_stream_kernel<EPI, RPT, VEC><<<cached_grid, kBlock, smem, st>>>(*A, x, y, ea, d_skip, cap);
+  PSB_LAUNCH_CHECK();
+  return PSB_OK;
+}
+
+template <int EPI, int W>
+static int launch_vector(const psb_csr* A, const double* x, double* y, const EpiArgs& ea,
+                         const int* d_skip, cudaStream_t st) {
+  constexpr int ROWS = kBlock / W;
+  static thread_local int cached_grid = 0;
+  static thread_local int64_t cached_groups = -1;
+  const int64_t groups = (A->n_rows + ROWS - 1) / ROWS;
+  if (cached_grid == 0 || cached_groups != groups) {
+    int g = 0;
+    int rc = occupancy_grid(spmv_vector_kernel<EPI, W>, 0, groups, A->max_grid, &g);
+    if (rc != PSB_OK) return rc;
+    cached_grid = g; cached_groups = groups;
+  }
+  spmv_vector_kernel<EPI, W><<<cached_grid, kBlock, 0, st>>>(*A, x, y, ea, d_skip);
+  PSB_LAUNCH_CHECK();
+  return PSB_OK;
+}
+
+template <int EPI>
+static int launch_epi(const psb_csr* A, const double* x, double* y, const EpiArgs& ea,
+                      const int* d_skip, cudaStream_t st) {
+  if (A->n_rows == 0) return PSB_OK;
+  if (A->kind == PSB_SPMV_STREAM) {
+    if (A->rpt == 2)
+      return A->vec_loads ? launch_stream<EPI, 2, true>(A, x, y, ea, d_skip, st)
+                          : launch_stream<EPI, 2, false>(A, x, y, ea, d_skip, st);
+    return A->vec_loads ? launch_stream<EPI, 1, true>(A, x, y, ea, d_skip, st)
+                        : launch_stream<EPI, 1, false>(A, x, y, ea, d_skip, st);
+  }
+  switch (A->vec_width) {
+    case 2:  return launch_vector<EPI, 2>(A, x, y, ea, d_skip, st);
+    case 4:  return launch_vector<EPI, 4>(A, x, y, ea, d_skip, st);
+    case 8:  return launch_vector<EPI, 8>(A, x, y, ea, d_skip, st);
+    case 16: return launch_vector<EPI, 16>(A, x, y, ea, d_skip, st);
+    default: return launch_vector<EPI, 32>(A, x, y, ea, d_skip, st);
+  }
+}
+
+int spmv_launch(const psb_csr* A, Epi epi, const double* x, double* y, const EpiArgs& ea,
+                const int* d_skip, cudaStream_t st) {
+  switch (epi) {
+    case EPI_STORE:  return launch_epi<EPI_STORE>(A, x, y, ea, d_skip, st);
+    case EPI_DOT:    return launch_epi<EPI_DOT>(A, x, y, ea, d_skip, st);
+    case EPI_RESID:  return launch_epi<EPI_RESID>(A, x, y, ea, d_skip, st);
+    case EPI_ADD:    return launch_epi<EPI_ADD>(A, x, y, ea, d_skip, st);
+    case EPI_JACOBI: return launch_epi<EPI_JACOBI>(A, x, y, ea, d_skip, st);
+    default: break;
+  }
+  set_error("spmv_launch: unknown epilogue %d", (int)epi);
+  return PSB_ERR_ARG;
+}
+
+// shared memory the STREAM kernel may use and still keep >= 4 CTAs per SM
+static constexpr int kStreamSmemBudget = 48 * 1024;
+
+static void choose_kernel(psb_csr* A) {
+  const double mean = A->n_rows ? (double)A->nnz / (double)A->n_rows : 0.0;
+  int w = 2;
+  while (w < 32 && w < mean) w <<= 1;
+  A->vec_width = w;
+  auto fits = [&](int rpt) {
+    size_t smem = (size_t)((A->max_tile_nnz[rpt - 1] + 1) & ~1) * 8 + (size_t)(kBlock * rpt + 1) * 4;
+    return smem <= (size_t)kStreamSmemBudget;
+  };
+  if (mean <= 32.0 && fits(2)) { A->kind = PSB_SPMV_STREAM; A->rpt = 2; }
+  else if (mean <= 32.0 && fits(1)) { A->kind = PSB_SPMV_STREAM; A->rpt = 1; }
+  else { A->kind = PSB_SPMV_VECTOR; A->rpt = 1; }
+}
+
+}  // namespace psb
+
+using namespace psb;
+
+extern "C" int psb_csr_create(int64_t n_rows, int64_t n_cols, int64_t nnz,
+                              const int32_t* d_rowptr, const int32_t* d_colind,
+                              const double* d_vals, void* stream, psb_csr_t* out) {
+  PSB_REQUIRE(out != nullptr, PSB_ERR_ARG, "psb_csr_create: out is NULL");
+  PSB_REQUIRE(n_rows >= 0 && n_cols >= 0 && nnz >= 0, PSB_ERR_ARG, "psb_csr_create: negative size");
+  PSB_REQUIRE(nnz < (int64_t)INT32_MAX && n_rows < (int64_t)INT32_MAX && n_cols < (int64_t)INT32_MAX,
+              PSB_ERR_UNSUPP, "psb_csr_create: int32 index range exceeded");
+  PSB_REQUIRE(d_rowptr != nullptr, PSB_ERR_ARG, "psb_csr_create: rowptr is NULL");
+  PSB_REQUIRE(nnz == 0 || (d_colind != nullptr && d_vals != nullptr), PSB_ERR_ARG,
+              "psb_csr_create: colind/vals NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  psb_csr* A = new (std::nothrow) psb_csr();
+  PSB_REQUIRE(A != nullptr, PSB_ERR_ARG, "psb_csr_create: out of host memory");
+  A->n_rows = n_rows; A->n_cols = n_cols; A->nnz = nnz;
+  A->rowptr = d_rowptr; A->colind = d_colind; A->vals = d_vals;
+  A->vec_loads = aligned16(d_colind) && aligned16(d_vals);
+  A->max_grid = sm_count() * 16;
+  A->partials = nullptr; A->ticket = nullptr;
+  int h_stats[3] = {0, 0, 0};
+  int* d_stats = nullptr;
+  cudaError_t e = cudaMalloc(&A->partials, sizeof(double) * A->max_grid);
+  if (e == cudaSuccess) e = cudaMalloc(&A->ticket, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemsetAsync(A->ticket, 0, sizeof(unsigned int), st);
+  if (e == cudaSuccess) e = cudaMalloc(&d_stats, sizeof(h_stats));
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_stats, 0, sizeof(h_stats), st);
+  if (e == cudaSuccess && n_rows > 0) {
+    int grid = (int)std::min<int64_t>((n_rows + kBlock - 1) / kBlock, (int64_t)sm_count() * 8);
+    csr_stats_kernel<<<grid, kBlock, 0, st>>>(d_rowptr, n_rows, d_stats);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaPeekAtLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (d_stats) cudaFree(d_stats);
+  if (e != cudaSuccess) {
+    set_error("psb_csr_create: %s", cudaGetErrorString(e));
+    if (A->partials) cudaFree(A->partials);
+    if (A->ticket) cudaFree(A->ticket);
+    delete A;
+    return PSB_ERR_CUDA;
+  }
+  A->max_row = h_stats[0];
+  A->max_tile_nnz[0] = h_stats[1];
+  A->max_tile_nnz[1] = h_stats[2];
+  choose_kernel(A);
+  *out = A;
+  return PSB_OK;
+}
+
+extern "C" int psb_csr_destroy(psb_csr_t A) {
+  if (A == nullptr) return PSB_OK;
+  if (A->partials) cudaFree(A->partials);
+  if (A->ticket) cudaFree(A->ticket);
+  delete A;
+  return PSB_OK;
+}
+
+extern "C" int psb_csr_info(psb_csr_t A, int64_t info[8]) {
+  PSB_REQUIRE(A != nullptr && info != nullptr, PSB_ERR_ARG, "psb_csr_info: NULL argument");
+  info[0] = A->kind;
+  info[1] = A->max_row;
+  info[2] = A->max_tile_nnz[0];
+  info[3] = (int64_t)kBlock * A->rpt;
+  info[4] = A->vec_width;
+  info[5] = A->max_grid;
+  info[6] = A->vec_loads ? 1 : 0;
+  info[7] = A->max_tile_nnz[1];
+  return PSB_OK;
+}
+
+extern "C" int psb_csr_set_kind(psb_csr_t A, int kind) {
+  PSB_REQUIRE(A != nullptr, PSB_ERR_ARG, "psb_csr_set_kind: NULL handle");
+  if (kind == PSB_SPMV_VECTOR) { A->kind = kind; return PSB_OK; }
+  if (kind == PSB_SPMV_STREAM || kind == PSB_SPMV_STREAM + 16) {
+    const int rpt = (kind == PSB_SPMV_STREAM) ? 2 : 1;   // +16 selects 256-row tiles
+    size_t smem = (size_t)((A->max_tile_nnz[rpt - 1] + 1) & ~1) * 8 + (size_t)(kBlock * rpt + 1) * 4;
+    PSB_REQUIRE(smem <= (size_t)max_optin_smem(), PSB_ERR_UNSUPP,
+                "psb_csr_set_kind: tile does not fit in shared memory");
+    A->kind = PSB_SPMV_STREAM; A->rpt = rpt;
+    return PSB_OK;
+  }
+  set_error("psb_csr_set_kind: unknown kind %d", kind);
+  return PSB_ERR_ARG;
+}
+
+extern "C" int psb_spmv(psb_csr_t A, const double* d_x, double* d_y, void* stream) {
+  PSB_REQUIRE(A && d_x && d_y, PSB_ERR_ARG, "psb_spmv: NULL argument");
+  return spmv_launch(A, EPI_STORE, d_x, d_y, EpiArgs(), nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int psb_spmv_dot(psb_csr_t A, const double* d_x, double* d_y, double* d_dot, void* stream) {
+  PSB_REQUIRE(A && d_x && d_y && d_dot, PSB_ERR_ARG, "psb_spmv_dot: NULL argument");
+  PSB_REQUIRE(A->n_rows == A->n_cols, PSB_ERR_ARG, "psb_spmv_dot: matrix must be square");
+  EpiArgs ea; ea.dot = d_dot;
+  return spmv_launch(A, EPI_DOT, d_x, d_y, ea, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int psb_spmv_residual(psb_csr_t A, const double* d_x, const double* d_f, double* d_y,
+                                 void* stream) {
+  PSB_REQUIRE(A && d_x && d_y && d_f, PSB_ERR_ARG, "psb_spmv_residual: NULL argument");
+  EpiArgs ea; ea.f = d_f;
+  return spmv_launch(A, EPI_RESID, d_x, d_y, ea, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int psb_spmv_add(psb_csr_t A, const double* d_x, double* d_y, void* stream) {
+  PSB_REQUIRE(A && d_x && d_y, PSB_ERR_ARG, "psb_spmv_add: NULL argument");
+  return spmv_launch(A, EPI_ADD, d_x, d_y, EpiArgs(), nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int psb_jacobi_sweep(psb_csr_t A, const double* d_dinv, double omega, const double* d_f,
+                                const double* d_x, double* d_xnew, void* stream) {
+  PSB_REQUIRE(A && d_dinv && d_f && d_x && d_xnew, PSB_ERR_ARG, "psb_jacobi_sweep: NULL argument");
+  PSB_REQUIRE(d_x != d_xnew, PSB_ERR_ARG, "psb_jacobi_sweep: x_new must not alias x");
+  PSB_REQUIRE(A->n_rows == A->n_cols, PSB_ERR_ARG, "psb_jacobi_sweep: matrix must be square");
+  EpiArgs ea; ea.f = d_f; ea.dinv = d_dinv; ea.omega = omega;
+  return spmv_launch(A, EPI_JACOBI, d_x, d_xnew, ea, nullptr, (cudaStream_t)stream);
+}

@@ -1,0 +1,44 @@
+// Internal interface of the CSR SpMV family (spmv.cu) used by the solvers.
+#pragma once
+#include "common.cuh"
+
+struct psb_csr {
+  int64_t n_rows, n_cols, nnz;
+  const int*    rowptr;
+  const int*    colind;
+  const double* vals;
+  int  kind;            // PSB_SPMV_STREAM | PSB_SPMV_VECTOR
+  int  max_row;         // longest row
+  int  max_tile_nnz[2]; // most nnz in a tile of 256 / 512 consecutive rows
+  int  rpt;             // STREAM: rows per thread (1 -> 256-row tiles, 2 -> 512)
+  int  vec_width;       // VECTOR: lanes per row
+  bool vec_loads;       // arrays 16-byte aligned -> 128-bit loads of vals/colind
+  double*       partials;   // per-CTA partial sums of the fused dot
+  unsigned int* ticket;     // last-CTA ticket
+  int  max_grid;        // CTAs the partial buffer can hold
+};
+
+namespace psb {
+
+enum Epi : int {
+  EPI_STORE = 0,   // y = A x
+  EPI_DOT   = 1,   // y = A x ; dot = x . y
+  EPI_RESID = 2,   // y = f - A x
+  EPI_ADD   = 3,   // y += A x
+  EPI_JACOBI = 4,  // y = x + omega * dinv .* (f - A x)
+  EPI_COUNT
+};
+
+struct EpiArgs {
+  const double* f     = nullptr;   // RESID, JACOBI
+  const double* dinv  = nullptr;   // JACOBI
+  double        omega = 1.0;       // JACOBI
+  double*       dot   = nullptr;   // DOT: where the last CTA writes x . y
+};
+
+// Enqueue one SpMV-shaped kernel.  `d_skip` (nullable): the kernel is a no-op
+// when *d_skip != 0 (solver loops keep launching after convergence).
+int spmv_launch(const psb_csr* A, Epi epi, const double* x, double* y,
+                const EpiArgs& ea, const int* d_skip, cudaStream_t stream);
+
+}  // namespace psb

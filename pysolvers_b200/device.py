@@ -1,0 +1,127 @@
+"""Device-side objects of the host layer: torch tensors own the HBM, the C ABI
+holds raw pointers into them.
+
+``DeviceCSR`` is the uploaded form of the scipy CSR operand the reference hands
+to ``mvmult`` (PySolvers/Linear/IterativeLinearSolver.py:94-106): int32
+``indptr``/``indices`` and fp64 ``data`` exactly as scipy stores them -- the
+stored (possibly unsorted) column order is kept, because the STREAM SpMV sums
+each row in that order to stay bit-identical to scipy's csr_matvec.
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _native as nat
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise nat.NativeError(
+            'pysolvers_b200 needs a CUDA device: the solve path has no CPU '
+            'fallback.')
+
+
+def current_stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None) as c_void_p."""
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def to_device(a, dtype=torch.float64):
+    """Upload a numpy array (or pass through a CUDA tensor) as a contiguous
+    1-D tensor of ``dtype``."""
+    if isinstance(a, torch.Tensor):
+        t = a
+        if not t.is_cuda:
+            t = t.cuda(non_blocking=True)
+        return t.to(dtype).contiguous()
+    arr = np.ascontiguousarray(a)
+    want = {torch.float64: np.float64, torch.int32: np.int32}[dtype]
+    if arr.dtype != want:
+        arr = arr.astype(want)
+    if not arr.flags.writeable:
+        arr = arr.copy()
+    return torch.from_numpy(arr).cuda(non_blocking=True)
+
+
+def as_csr(A):
+    """Accept what the reference accepts as a matrix operand: a scipy sparse
+    matrix (converted to CSR if needed) or a dense 2-D ndarray.  A dense matrix
+    is converted to CSR -- the GPU path is sparse-only."""
+    if isinstance(A, DeviceCSR):
+        return A
+    if sp.issparse(A):
+        return A if sp.isspmatrix_csr(A) or isinstance(A, sp.csr_array) else A.tocsr()
+    if isinstance(A, np.ndarray) and A.ndim == 2:
+        return sp.csr_matrix(A)
+    raise TypeError('matrix operand must be a scipy sparse matrix or a 2-D '
+                    'numpy array, got %r' % type(A))
+
+
+class DeviceCSR:
+    """CSR matrix resident in HBM plus its psb_csr_t handle."""
+
+    def __init__(self, A=None, indptr=None, indices=None, data=None, shape=None):
+        require_cuda()
+        if A is not None:
+            A = as_csr(A)
+            if isinstance(A, DeviceCSR):
+                raise TypeError('already a DeviceCSR')
+            shape = A.shape
+            indptr, indices, data = A.indptr, A.indices, A.data
+        if len(data) >= 2**31 - 1 or max(shape) >= 2**31 - 1:
+            raise nat.NativeError('matrices that need int64 indices (nnz or n '
+                                  '>= 2^31) are not supported by the GPU path')
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.indptr = to_device(indptr, torch.int32)
+        self.indices = to_device(indices, torch.int32)
+        self.data = to_device(data, torch.float64)
+        self.nnz = int(self.data.numel())
+        if self.indptr.numel() != self.shape[0] + 1:
+            raise ValueError('indptr has the wrong length')
+        self._h = C.c_void_p()
+        nat.check(nat.lib().psb_csr_create(
+            self.shape[0], self.shape[1], self.nnz, ptr(self.indptr),
+            ptr(self.indices), ptr(self.data), current_stream_ptr(),
+            C.byref(self._h)), 'psb_csr_create')
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self):
+        buf = (C.c_int64 * 8)()
+        nat.check(nat.lib().psb_csr_info(self._h, buf), 'psb_csr_info')
+        return dict(kind=int(buf[0]), max_row=int(buf[1]), max_tile_nnz=int(buf[2]),
+                    rows_per_tile=int(buf[3]), vec_width=int(buf[4]),
+                    max_grid=int(buf[5]), vec_loads=bool(buf[6]),
+                    max_tile_nnz_512=int(buf[7]))
+
+    def set_kind(self, kind):
+        nat.check(nat.lib().psb_csr_set_kind(self._h, kind), 'psb_csr_set_kind')
+
+    def matvec(self, x, out=None):
+        """y = A x on the device; x, y are CUDA fp64 tensors."""
+        if out is None:
+            out = torch.empty(self.shape[0], dtype=torch.float64, device=x.device)
+        nat.check(nat.lib().psb_spmv(self._h, ptr(x), ptr(out),
+                                     current_stream_ptr()), 'psb_spmv')
+        return out
+
+    def algorithmic_bytes(self):
+        """HBM bytes one SpMV must move."""
+        n, m = self.shape
+        return 12 * self.nnz + 4 * (n + 1) + 8 * m + 8 * n
+
+    def __del__(self):
+        try:
+            if self._h:
+                nat.lib().psb_csr_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass

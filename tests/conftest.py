@@ -1,0 +1,70 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden', 'reference_golden.npz')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+@pytest.fixture(scope='session')
+def golden():
+    """Fixtures produced by running the reference itself
+    (tests/golden/make_golden.py)."""
+    z = np.load(GOLDEN)
+    return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope='session')
+def cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from pysolvers_b200.csrc.build import build_native
+    build_native()
+    return torch.device('cuda:0')
+
+
+@pytest.fixture(scope='session', autouse=True)
+def _single_thread_blas():
+    """The fixtures were generated with one OpenBLAS thread (ddot's summation
+    order depends on the thread count); pin the same here."""
+    try:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=1, user_api='blas'):
+            yield
+    except ImportError:
+        yield
+
+
+def assert_same_history(got, want, what=''):
+    """Bit-equal when the same BLAS kernels run (the build container); on a
+    host whose OpenBLAS picks other ddot kernels the last bits may move, so
+    fall back to 1e-9 relative."""
+    got = np.asarray(got)
+    want = np.asarray(want)
+    assert got.shape == want.shape, what
+    if not np.array_equal(got, want):
+        assert rel_err(got, want) < 1e-9, what
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = np.maximum(np.abs(b), np.finfo(np.float64).tiny)
+    return np.max(np.abs(a - b) / den) if a.size else 0.0
+
+
+def golden_csr(g, prefix):
+    import scipy.sparse as sp
+    shape = tuple(int(v) for v in g[prefix + '/shape'])
+    return sp.csr_matrix((g[prefix + '/data'], g[prefix + '/indices'],
+                          g[prefix + '/indptr']), shape=shape)

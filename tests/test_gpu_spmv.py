@@ -1,0 +1,123 @@
+"""SpMV parity on the B200: CUDA kernels (through the C ABI) vs scipy's
+csr_matvec, the routine the reference executes behind ``A*x``
+(PySolvers/Linear/IterativeLinearSolver.py:104)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+def _mats():
+    from pysolvers_b200.problems import fd_laplacian_2d, fd_laplacian_3d, load_dh_matrix
+    rng = np.random.default_rng(5)
+    out = {
+        'lap2d_m7': -fd_laplacian_2d(0.0, 1.0, 7),
+        'lap2d_m64': -fd_laplacian_2d(0.0, 1.0, 64),
+        'lap2d_m300': -fd_laplacian_2d(0.0, 1.0, 300),
+        'lap3d_m20': fd_laplacian_3d(0.0, 1.0, 20),
+        'dh12': load_dh_matrix(12),
+        'rect': sp.random(1000, 377, density=0.02, random_state=rng, format='csr'),
+        'empty_rows': sp.csr_matrix(sp.random(513, 513, density=0.002, random_state=rng)),
+        'one_row': sp.csr_matrix(np.arange(1.0, 6.0).reshape(1, 5)),
+        'dense_rows': sp.random(300, 300, density=0.5, random_state=rng, format='csr'),
+    }
+    # a few very long rows among short ones (skewed histogram)
+    skew = sp.lil_matrix((2000, 2000))
+    skew.setdiag(2.0)
+    skew[7, :] = rng.random(2000)
+    skew[1500, ::2] = 1.5
+    out['skewed'] = skew.tocsr()
+    return out
+
+
+@pytest.mark.parametrize('name', ['lap2d_m7', 'lap2d_m64', 'lap2d_m300', 'lap3d_m20', 'dh12',
+                                  'rect', 'empty_rows', 'one_row', 'dense_rows', 'skewed'])
+def test_spmv_matches_scipy(cuda, name):
+    import torch
+    from pysolvers_b200 import _native as nat
+    from pysolvers_b200.device import DeviceCSR, to_device
+    A = _mats()[name]
+    x = np.random.default_rng(1).standard_normal(A.shape[1])
+    want = A @ x
+    dA = DeviceCSR(A)
+    xd = to_device(x)
+    kinds = [dA.info()['kind']]
+    for kind in (nat.SPMV_STREAM, nat.SPMV_STREAM + 16, nat.SPMV_VECTOR):
+        try:
+            dA.set_kind(kind)
+        except nat.NativeError:
+            continue
+        got = dA.matvec(xd).cpu().numpy()
+        if kind != nat.SPMV_VECTOR:
+            # STREAM sums each row in stored order from +0, no FMA: bit-identical
+            assert np.array_equal(got, want), (name, kind)
+        else:
+            scale = np.abs(A) @ np.abs(x) + 1e-300
+            assert np.max(np.abs(got - want) / scale) < 1e-14, (name, kind)
+
+
+def test_spmv_epilogues(cuda):
+    import torch
+    from pysolvers_b200 import _native as nat
+    from pysolvers_b200.device import DeviceCSR, to_device, ptr, current_stream_ptr
+    from pysolvers_b200.problems import fd_laplacian_2d
+    A = -fd_laplacian_2d(0.0, 1.0, 50)
+    n = A.shape[0]
+    rng = np.random.default_rng(2)
+    x, f, y0 = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
+    dA = DeviceCSR(A)
+    lib = nat.lib()
+    xd, fd = to_device(x), to_device(f)
+    st = current_stream_ptr()
+    # y = A x and dot = x.y
+    yd = torch.empty(n, dtype=torch.float64, device='cuda')
+    dd = torch.zeros(1, dtype=torch.float64, device='cuda')
+    nat.check(lib.psb_spmv_dot(dA.handle, ptr(xd), ptr(yd), ptr(dd), st))
+    Ax = A @ x
+    assert np.array_equal(yd.cpu().numpy(), Ax)
+    assert abs(dd.item() - np.dot(x, Ax)) <= 1e-13 * np.dot(np.abs(x), np.abs(Ax))
+    # deterministic: same bits on a second run
+    dd2 = torch.zeros(1, dtype=torch.float64, device='cuda')
+    nat.check(lib.psb_spmv_dot(dA.handle, ptr(xd), ptr(yd), ptr(dd2), st))
+    assert dd.item() == dd2.item()
+    # residual
+    nat.check(lib.psb_spmv_residual(dA.handle, ptr(xd), ptr(fd), ptr(yd), st))
+    assert np.array_equal(yd.cpu().numpy(), f - Ax)
+    # y += A x
+    yd = to_device(y0)
+    nat.check(lib.psb_spmv_add(dA.handle, ptr(xd), ptr(yd), st))
+    assert np.array_equal(yd.cpu().numpy(), y0 + Ax)
+    # Jacobi sweeps (ClassicSmoothers.py:12-14), omega = 1 and 2/3
+    dinv = np.reciprocal(A.diagonal())
+    dinv_d = to_device(dinv)
+    out = torch.empty(n, dtype=torch.float64, device='cuda')
+    nat.check(lib.psb_jacobi_sweep(dA.handle, ptr(dinv_d), 1.0, ptr(fd), ptr(xd), ptr(out), st))
+    assert np.array_equal(out.cpu().numpy(), x + np.multiply(dinv, f - Ax))
+    om = 2.0 / 3.0
+    nat.check(lib.psb_jacobi_sweep(dA.handle, ptr(dinv_d), om, ptr(fd), ptr(xd), ptr(out), st))
+    assert np.array_equal(out.cpu().numpy(), x + om * np.multiply(dinv, f - Ax))
+
+
+def test_dot_matches_numpy(cuda):
+    import torch
+    from pysolvers_b200 import _native as nat
+    from pysolvers_b200.device import to_device, ptr, current_stream_ptr
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 255, 256, 257, 100001, 1 << 20):
+        a, b = rng.standard_normal(n), rng.standard_normal(n)
+        out = torch.zeros(1, dtype=torch.float64, device='cuda')
+        nat.check(nat.lib().psb_dot(n, ptr(to_device(a)), ptr(to_device(b)), ptr(out),
+                                    current_stream_ptr()))
+        ref = np.dot(a, b)
+        assert abs(out.item() - ref) <= 1e-13 * np.dot(np.abs(a), np.abs(b)), n
+
+
+def test_mvmult_drop_in(cuda):
+    from pysolvers_b200.Linear import mvmult
+    from pysolvers_b200.problems import load_dh_matrix
+    A = load_dh_matrix(9)
+    x = np.random.default_rng(4).random(A.shape[0])
+    assert np.array_equal(mvmult(A, x), A * x)

@@ -1,0 +1,59 @@
+"""CPU-side checks of the C-ABI boundary: the library builds for sm_100a,
+loads, and exports every symbol include/pysolv_b200.h declares; the ctypes
+table in pysolvers_b200/_native.py covers the header one to one."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, 'include', 'pysolv_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(psb_[a-z0-9_]+)\s*\(', text)))
+
+
+@pytest.fixture(scope='module')
+def libpath():
+    from pysolvers_b200.csrc.build import build_native
+    return build_native()
+
+
+def test_header_declares_functions():
+    fns = _header_functions()
+    assert 'psb_pcg_solve' in fns and 'psb_spmv' in fns and len(fns) >= 10
+
+
+def test_library_exports_every_declared_symbol(libpath):
+    lib = ctypes.CDLL(libpath)
+    missing = [f for f in _header_functions() if not hasattr(lib, f)]
+    assert not missing, 'declared in the header but not exported: %s' % missing
+
+
+def test_ctypes_table_matches_header():
+    from pysolvers_b200 import _native
+    assert sorted(_native.SIGNATURES) == _header_functions()
+
+
+def test_version_and_error_text(libpath):
+    from pysolvers_b200 import _native
+    lib = _native.lib()
+    assert lib.psb_version() >= 100
+    # argument validation happens before any CUDA call: NULL handle -> PSB_ERR_ARG
+    rc = lib.psb_spmv(None, None, None, None)
+    assert rc == -2
+    assert b'NULL' in lib.psb_last_error()
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure; nothing under pysolvers_b200/ may
+    import it."""
+    pkg = os.path.join(ROOT, 'pysolvers_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
