@@ -295,7 +295,7 @@ def run_single_gpu(args):
                 'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * e2e_s / args.steps},
         'gpu_launches': int(launches),
         'clocks': clocks,
-        'roofline': {'bound': 'hbm', 'kernel': 'spmv_stream_kernel<EPI_DOT> (A p and p.Ap)',
+        'roofline': {'bound': 'hbm', 'kernel': 'spmv_bulk_kernel<EPI_DOT> (A p fused with p.Ap)',
                      'achieved': spmv_gbs, 'peak': peak_gbs, 'unit': 'GB/s',
                      'frac': spmv_gbs / peak_gbs, 'traffic': None,
                      'bytes_per_launch': spmv_bytes, 'ms_per_launch': spmv_ms,

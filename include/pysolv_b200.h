@@ -46,10 +46,15 @@ long long   psb_launch_count(void);
 
 /* ------------------------------------------------------------------- CSR -- */
 /* SpMV kernel kinds chosen from the row-length histogram at create time. */
-#define PSB_SPMV_STREAM  1  /* CTA streams a contiguous nnz chunk through smem;
-                               one thread per row sums in STORED order (bit-equal
-                               to scipy csr_matvec)                              */
-#define PSB_SPMV_VECTOR  2  /* sub-warp per row, shuffle reduction              */
+#define PSB_SPMV_STREAM      1  /* tiles of consecutive rows staged into shared memory
+                                  by bulk async copies (TMA engine), double-buffered;
+                                  one thread per row sums in STORED order (bit-equal to
+                                  scipy csr_matvec)                                  */
+#define PSB_SPMV_VECTOR      2  /* sub-warp per row, shuffle reduction               */
+#define PSB_SPMV_STREAM_LSU  3  /* first-generation STREAM: coalesced LDG.128 of the
+                                  tile, products parked in shared memory            */
+#define PSB_SPMV_TILE512    16  /* OR-ed into a STREAM kind for psb_csr_set_kind:
+                                  512-row tiles instead of 256                       */
 
 /* Wraps caller-owned device arrays (no copy).  Synchronises `stream` once to
  * read back the row-length statistics that pick the kernel.
@@ -60,7 +65,8 @@ int psb_csr_create(int64_t n_rows, int64_t n_cols, int64_t nnz,
                    const double* d_vals, void* stream, psb_csr_t* out);
 int psb_csr_destroy(psb_csr_t A);
 /* info[0]=kernel kind, [1]=max row length, [2]=max nnz per 256-row tile,
- * [3]=rows per tile, [4]=vector width (VECTOR kind), [5]=grid size. */
+ * [3]=rows per tile, [4]=vector width (VECTOR kind), [5]=max grid size,
+ * [6]=arrays 16-byte aligned, [7]=max nnz per 512-row tile. */
 int psb_csr_info(psb_csr_t A, int64_t info[8]);
 /* Force a kernel kind (testing / A-B timing); PSB_ERR_UNSUPP if impossible. */
 int psb_csr_set_kind(psb_csr_t A, int kind);
@@ -87,6 +93,43 @@ int psb_jacobi_sweep(psb_csr_t A, const double* d_dinv, double omega,
  * PCGSolver.py:86,102,125,134) */
 int psb_dot(int64_t n, const double* d_x, const double* d_y, double* d_out,
             void* stream);
+
+/* ---------------------------------------------- sparse triangular solves -- */
+/* Level analysis + repacking of a triangular CSR factor given in HOST memory (the
+ * factors come from the reference's SuperLU setup on the CPU): rows are sorted
+ * level-major, the strictly triangular part is stored SELL-32 in that order, the
+ * diagonal is split out, everything is uploaded once.  `lower` != 0: entries with
+ * col < row are the dependencies (col > row ignored); otherwise the reverse.
+ * `unit_diag` != 0: the diagonal is taken as 1 (stored diagonal entries ignored).
+ * Synchronises `stream`.  Replaces the factor objects of
+ * PySolvers/Linear/ICPreconditioner.py:45-56 / ILUTPreconditioner.py:51-53. */
+int psb_trsv_create(int64_t n, const int32_t* h_rowptr, const int32_t* h_colind,
+                    const double* h_vals, int lower, int unit_diag, void* stream,
+                    psb_trsv_t* out);
+int psb_trsv_destroy(psb_trsv_t T);
+/* info[0]=n, [1]=levels, [2]=off-diagonal nnz, [3]=packed (padded) nnz,
+ * [4]=lower, [5]=unit_diag, [6]=32-row groups. */
+int psb_trsv_info(psb_trsv_t T, int64_t info[8]);
+/* Copies out the level sets (host arrays of levels+1 and n int32): level of a row
+ * = 1 + max level of its dependencies; rows level-major, ascending in a level. */
+int psb_trsv_get_levels(psb_trsv_t T, int32_t* h_level_ptr, int32_t* h_level_rows);
+/* x = T^-1 b in one persistent launch (x must not alias b).  Replaces
+ * scipy spsolve_triangular, ICPreconditioner.py:61,63. */
+int psb_trsv_solve(psb_trsv_t T, const double* d_b, double* d_x, void* stream);
+/* *h_flag != 0 if a solve gave up waiting for a dependency (synchronises). */
+int psb_trsv_error(psb_trsv_t T, int32_t* h_flag);
+
+/* ------------------------------------------------------ preconditioners -- */
+/* z = L^-T (L^-1 r)   (ICRightPreconditioner.applyRight, ICPreconditioner.py:58-63).
+ * The factors stay owned by the caller and must outlive the preconditioner. */
+int psb_ic_create(psb_trsv_t L, psb_trsv_t Lt, psb_prec_t* out);
+/* z = Pc U^-1 L^-1 Pr r with Pr[perm_r[i], i] = 1, Pc[i, perm_c[i]] = 1 and unit
+ * lower L -- SuperLU.solve (ILUTPreconditioner.py:67,78).  perm arrays: HOST int32. */
+int psb_ilu_create(psb_trsv_t L, psb_trsv_t U, const int32_t* h_perm_r,
+                   const int32_t* h_perm_c, void* stream, psb_prec_t* out);
+/* z = M^-1 r (z must not alias r).  Preconditioner.applyRight / applyLeft. */
+int psb_prec_apply(psb_prec_t P, const double* d_r, double* d_z, void* stream);
+int psb_prec_destroy(psb_prec_t P);
 
 /* ------------------------------------------------------------------ PCG -- */
 /* status codes written to psb_solve_result.status */
@@ -120,6 +163,25 @@ int psb_pcg_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, double* d_x,
                   void* d_work, int64_t work_bytes, int32_t maxiter, double tau,
                   int32_t fail_on_maxiter, double* d_hist,
                   psb_solve_result* result, void* stream);
+
+/* ---------------------------------------------------------------- GMRES -- */
+#define PSB_ORTH_CGS2  1  /* classical Gram-Schmidt twice, batched dots (default)   */
+#define PSB_ORTH_MGS   2  /* modified Gram-Schmidt in the reference's order
+                             (GMRESSolver.py:110-112); for un-preconditioned parity */
+
+int64_t psb_gmres_workspace_bytes(int64_t n, int32_t maxiter);
+
+/* Whole right-preconditioned, un-restarted GMRES solve on the device
+ * (PySolvers/Linear/GMRESSolver.py:75-174): Arnoldi + Givens loop, then
+ * x = M^-1 (Q y) and the true residual check.  d_hist receives |g_{k+1}| per
+ * iteration.  result->norm_r is the TRUE residual norm, norm_r_rec the recursive
+ * one; status PSB_GMRES_FALSE_CONV when only the latter met tau.  At maxiter the
+ * reference raises NameError (:180); here x_k of the last iteration is returned
+ * with status PSB_MAXITER.  Synchronises `stream`. */
+int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, double* d_x,
+                    void* d_work, int64_t work_bytes, int32_t maxiter, double tau,
+                    int32_t fail_on_maxiter, int32_t orth, double* d_hist,
+                    psb_solve_result* result, void* stream);
 
 #ifdef __cplusplus
 }

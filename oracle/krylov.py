@@ -27,8 +27,19 @@ def _result(success, iters, soln, resid, hist, msg=None):
                 msg=msg, hist=np.asarray(hist, dtype=np.float64))
 
 
-def pcg(A, b, prec=None, maxiter=100, tau=1.0e-8, fail_on_maxiter=True):
+def pairwise_dot(a, b):
+    """Same dot product, different (pairwise) summation order.  Running the
+    oracle with this instead of ``np.dot`` measures how far a residual history
+    moves when ONLY the rounding of the reductions changes -- the noise floor
+    any re-implementation with its own reduction tree lives on."""
+    return np.sum(a * b)
+
+
+def pcg(A, b, prec=None, maxiter=100, tau=1.0e-8, fail_on_maxiter=True,
+        dot=np.dot):
     """Preconditioned CG.  ``prec`` is a callable r -> M^{-1} r or None.
+    ``dot`` is np.dot as in the reference; tests pass ``pairwise_dot`` to
+    measure rounding sensitivity.
 
     With ``prec=None`` the identity returns its argument, so u aliases r exactly
     as in the reference (Preconditioner.py:58-68).
@@ -38,7 +49,8 @@ def pcg(A, b, prec=None, maxiter=100, tau=1.0e-8, fail_on_maxiter=True):
     assert n == nc and n == len(b)
     hist = []
 
-    norm_b = npla.norm(b)                                   # PCGSolver.py:86
+    norm = npla.norm if dot is np.dot else (lambda v: np.sqrt(dot(v, v)))
+    norm_b = norm(b)                                        # PCGSolver.py:86
     if norm_b == 0.0:                                       # :87-88
         return _result(True, 1, np.zeros_like(b), 0, hist)
 
@@ -46,7 +58,7 @@ def pcg(A, b, prec=None, maxiter=100, tau=1.0e-8, fail_on_maxiter=True):
     p = apply_prec(r)                                       # :98
     u = np.copy(p)                                          # :99
     x = np.zeros_like(b)                                    # :100
-    u_dot_r = np.dot(u, r)                                  # :102
+    u_dot_r = dot(u, r)                                     # :102
     if u_dot_r == 0.0:                                      # :104-105
         return _result(False, 0, None, None, hist, 'breakdown dot(u,r)==0')
 
@@ -54,7 +66,7 @@ def pcg(A, b, prec=None, maxiter=100, tau=1.0e-8, fail_on_maxiter=True):
     norm_r = None
     for k in range(maxiter):                                # :109
         Ap = _matvec(A, p)                                  # :111
-        pAp = np.dot(p, Ap)                                 # :113
+        pAp = dot(p, Ap)                                    # :113
         if pAp == 0.0:                                      # :114-115
             return _result(False, k, None, None, hist,
                            'breakdown dot(p, Ap)==0')
@@ -62,12 +74,12 @@ def pcg(A, b, prec=None, maxiter=100, tau=1.0e-8, fail_on_maxiter=True):
         x = x + alpha * p                                   # :121
         r = r - alpha * Ap                                  # :122
         u = apply_prec(r)                                   # :123
-        norm_r = npla.norm(r)                               # :125
+        norm_r = norm(r)                                    # :125
         hist.append(norm_r)                                 # :126 reportIter
         if (norm_r <= tau * norm_b) or ((not fail_on_maxiter)
                                         and k == maxiter - 1):   # :129-131
             return _result(True, k + 1, x, norm_r, hist)
-        new_u_dot_r = np.dot(u, r)                          # :134
+        new_u_dot_r = dot(u, r)                             # :134
         beta = new_u_dot_r / u_dot_r                        # :135
         u_dot_r = new_u_dot_r                               # :136
         p = u + beta * p                                    # :138

@@ -5,4 +5,7 @@ from .precond import (Preconditioner, GenericPreconditioner,  # noqa: F401
                       LeftPreconditioner, RightPreconditioner,
                       IdentityPreconditioner, PreconditionerType,
                       IdentityPreconditionerType)
-from .krylov import PCG, PCGSolver  # noqa: F401
+from .krylov import PCG, PCGSolver, GMRES, GMRESSolver  # noqa: F401
+from .factorized import (RightIC, ICRightPreconditioner, LeftILUT, RightILUT,  # noqa: F401
+                         ILUTPreconditioner, LeftILUTPreconditioner,
+                         RightILUTPreconditioner)

@@ -106,3 +106,85 @@ class PCGSolver(IterativeLinearSolver):
         if st == nat.CONVERGED:
             return self.handleConvergence(res.k, x, res.norm_r, normB)
         return self.handleMaxiter(res.k, x, res.norm_r, normB)
+
+
+class GMRES(IterativeLinearSolverType):
+    """Factory for GMRESSolver (GMRESSolver.py:27-40).  ``orth`` is an added,
+    optional knob: 'cgs2' (default, batched) or 'mgs' (the reference's
+    orthogonalisation order)."""
+
+    def __init__(self, control=CommonSolverArgs(),
+                 precond=IdentityPreconditionerType(), name='GMRES', orth='cgs2'):
+        super().__init__(control=control, precond=precond, name=name)
+        self.orth = orth
+
+    def makeSolver(self, name=None):
+        return GMRESSolver(self.control(), precond=self.precond(),
+                           name=self.name() if name is None else name,
+                           orth=self.orth)
+
+
+class GMRESSolver(IterativeLinearSolver):
+    """Right-preconditioned GMRES without restart: the Krylov dimension is
+    ``maxiter`` (GMRESSolver.py:75-83).
+
+    Reference quirks kept: the preconditioner is rebuilt on EVERY solve --
+    ``freezePrec`` has no effect, because the reference assigns the formed
+    preconditioner to a local variable (GMRESSolver.py:71-72); a left
+    preconditioner is a no-op (only applyRight is used, :107,160).  Reference
+    bugs not kept: ``self.precond`` is initialised here (the reference raises
+    AttributeError without the harness workaround), and reaching maxiter
+    returns ``handleMaxiter`` with the last iterate instead of the NameError
+    of GMRESSolver.py:180.
+    """
+
+    def __init__(self, control=CommonSolverArgs(),
+                 precond=IdentityPreconditionerType(), name='GMRES', orth='cgs2'):
+        super().__init__(control=control, precond=precond, name=name)
+        self.precond = None
+        self.orth = orth
+        self.last_history = None
+
+    def solve(self, A, b):
+        n = self._check_system(A, b)
+        self._require_euclidean_norm()
+        require_cuda()
+        b = np.asarray(b)
+        b_d = to_device(b)
+        if n == 0 or _device_norm(b_d) == 0.0:
+            return self.handleConvergence(0, np.zeros_like(b), 0, 0)
+
+        precond = self.precondType().form(A)          # always rebuilt, see class doc
+        prec_h = right_handle_of(precond)
+        orth = {'cgs2': nat.ORTH_CGS2, 'mgs': nat.ORTH_MGS}[self.orth]
+
+        dA = _upload_matrix(A)
+        maxiter = int(self.maxiter())
+        lib = nat.lib()
+        wbytes = int(lib.psb_gmres_workspace_bytes(n, maxiter))
+        work = torch.empty(wbytes, dtype=torch.uint8, device=b_d.device)
+        x_d = torch.empty(n, dtype=torch.float64, device=b_d.device)
+        hist_d = torch.empty(max(maxiter, 1), dtype=torch.float64, device=b_d.device)
+        res = nat.SolveResult()
+        nat.check(lib.psb_gmres_solve(
+            dA.handle, prec_h, ptr(b_d), ptr(x_d), ptr(work), wbytes, maxiter,
+            float(self.tau()), 1 if self.failOnMaxiter() else 0, orth, ptr(hist_d),
+            C.byref(res), current_stream_ptr()), 'psb_gmres_solve')
+
+        hist = hist_d[:res.n_hist].cpu().numpy()
+        self.last_history = hist
+        normB = res.norm_b
+        for k in range(res.n_hist):
+            self.reportIter(k, hist[k], normB)
+        if res.status == nat.TRIVIAL:
+            return self.handleConvergence(0, np.zeros_like(b), 0, 0)
+        x = self._to_host(x_d, b)
+        if res.status == nat.CONVERGED:
+            return self.handleConvergence(res.k, x, res.norm_r, normB)
+        if res.status == nat.GMRES_FALSE_CONV:
+            return SolveStatus(
+                success=False, iters=res.k + 1, soln=x, resid=res.norm_r,
+                msg='GMRES failure: true residual %12.5g did not meet tolerance '
+                    'tau=%12.5g. Recursive residual was %12.5g.' % (
+                        res.norm_r, self.tau(), res.norm_r_rec))
+        return self.handleMaxiter(res.k, x, res.norm_r_rec, normB)

@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, 'libpysolv_b200.so')
 PSB_OK = 0
 # status codes of psb_solve_result.status (include/pysolv_b200.h)
 CONVERGED, MAXITER, BREAKDOWN_UR, BREAKDOWN_PAP, TRIVIAL, GMRES_FALSE_CONV = range(6)
-SPMV_STREAM, SPMV_VECTOR = 1, 2
+ORTH_CGS2, ORTH_MGS = 1, 2
+SPMV_STREAM, SPMV_VECTOR, SPMV_STREAM_LSU, SPMV_TILE512 = 1, 2, 3, 16
 
 
 class NativeError(RuntimeError):
@@ -47,9 +48,22 @@ SIGNATURES = {
     'psb_spmv_add': (C.c_int, [_vp, _vp, _vp, _vp]),
     'psb_jacobi_sweep': (C.c_int, [_vp, _vp, _dbl, _vp, _vp, _vp, _vp]),
     'psb_dot': (C.c_int, [_i64, _vp, _vp, _vp, _vp]),
+    'psb_trsv_create': (C.c_int, [_i64, _vp, _vp, _vp, C.c_int, C.c_int, _vp, C.POINTER(_vp)]),
+    'psb_trsv_destroy': (C.c_int, [_vp]),
+    'psb_trsv_info': (C.c_int, [_vp, C.POINTER(_i64)]),
+    'psb_trsv_get_levels': (C.c_int, [_vp, _vp, _vp]),
+    'psb_trsv_solve': (C.c_int, [_vp, _vp, _vp, _vp]),
+    'psb_trsv_error': (C.c_int, [_vp, C.POINTER(_i32)]),
+    'psb_ic_create': (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    'psb_ilu_create': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    'psb_prec_apply': (C.c_int, [_vp, _vp, _vp, _vp]),
+    'psb_prec_destroy': (C.c_int, [_vp]),
     'psb_pcg_workspace_bytes': (_i64, [_i64, C.c_int]),
     'psb_pcg_solve': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _dbl, _i32, _vp,
                                 C.POINTER(SolveResult), _vp]),
+    'psb_gmres_workspace_bytes': (_i64, [_i64, _i32]),
+    'psb_gmres_solve': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _dbl, _i32, _i32, _vp,
+                                  C.POINTER(SolveResult), _vp]),
 }
 
 _lib = None

@@ -50,8 +50,31 @@ def _compile(src, force, hdr_mtime):
     return obj, p.stderr, True
 
 
+def _source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    files = [os.path.join(HERE, f) for f in sorted(os.listdir(HERE))
+             if f.endswith(('.cu', '.cuh'))]
+    files += [os.path.join(ROOT, 'include', 'pysolv_b200.h'), os.path.abspath(__file__)]
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, 'rb').read())
+    return h.hexdigest()
+
+
 def build_native(force=False, verbose=False):
-    """Compile (if stale) and return the path of the shared library."""
+    """Compile (if stale) and return the path of the shared library.
+
+    Staleness is decided by a content hash of the sources stored beside the
+    library (file times do not survive the snapshot to the GPU box), so a
+    prebuilt .so that matches the sources is used as is."""
+    stamp = LIB + '.srchash'
+    digest = _source_hash()
+    if (not force and os.path.exists(LIB) and os.path.exists(stamp)
+            and open(stamp).read().strip() == digest):
+        if verbose:
+            print('up to date', LIB)
+        return LIB
     os.makedirs(OBJ_DIR, exist_ok=True)
     srcs = _sources()
     hdr = _headers_mtime()
@@ -70,8 +93,10 @@ def build_native(force=False, verbose=False):
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError('link failed:\n%s\n%s' % (p.stdout, p.stderr))
+    with open(stamp, 'w') as f:
+        f.write(digest + '\n')
     if verbose:
-        print('built' if rebuilt else 'up to date', LIB)
+        print('built' if rebuilt else 'relinked', LIB)
     return LIB
 
 

@@ -398,6 +398,11 @@ extern "C" int psb_pcg_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, do
     set_error("psb_pcg_solve: device loop ended without a terminal state (k=%d)", hs.k);
     return PSB_ERR_CUDA;
   }
+  if (has_prec && prec->check_error() != 0) {
+    set_error("psb_pcg_solve: the %s preconditioner reported a device-side failure "
+              "(a triangular-solve dependency never became ready)", prec->kind());
+    return PSB_ERR_CUDA;
+  }
   result->status = hs.status;
   result->k = hs.k_final;
   result->n_hist = hs.n_hist;

@@ -9,6 +9,8 @@ struct psb_prec {
   virtual ~psb_prec() {}
   virtual int apply(const double* d_r, double* d_z, const int* d_skip, cudaStream_t st) = 0;
   virtual const char* kind() const = 0;
+  // non-zero when a device-side failure was recorded (synchronises)
+  virtual int check_error() { return 0; }
 };
 
 namespace psb {

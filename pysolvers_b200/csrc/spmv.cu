@@ -5,14 +5,22 @@
 // SURVEY.md section 2.1).  Two kernels, picked once per matrix from row-length
 // statistics gathered at psb_csr_create:
 //
-//  STREAM (short rows: stencils, FE matrices, AMG operators)
+//  STREAM (short rows: stencils, FE matrices, AMG operators) -- the default
 //    A persistent grid of CTAs walks tiles of 256 (or 512) consecutive rows.  The
-//    tile's nonzeros are one CONTIGUOUS slice of vals/colind, so the CTA streams it
-//    with coalesced 128-bit loads, multiplies by the gathered x[col] (L1/L2 hits for
-//    banded matrices) and parks the products in shared memory.  Then one thread per
-//    row adds its products IN STORED ORDER starting from +0 -- the same sequence of
-//    roundings as scipy's csr_matvec, so y is bit-identical to the reference.
-//    HBM traffic = 12 B/nnz + 4 B/row (rowptr) + x once + y once.
+//    tile's nonzeros are one CONTIGUOUS slice of vals/colind, so one elected thread
+//    stages rowptr/colind/vals of the NEXT tile into shared memory with three bulk
+//    async copies (cp.async.bulk + mbarrier complete_tx, the TMA engine: SASS UBLKCP)
+//    while all threads work on the current one: double-buffered, no LSU wavefronts
+//    and no registers spent on the streaming part, L2 evict-first for the matrix so
+//    x stays cached.  Then one thread per row reads its (col, val) pairs from shared
+//    memory, gathers x[col] (adjacent rows of a banded matrix hit adjacent x: the
+//    gathers coalesce) and accumulates IN STORED ORDER starting from +0 -- the same
+//    sequence of roundings as scipy's csr_matvec, so y is bit-identical to the
+//    reference.  HBM traffic = 12 B/nnz + 4 B/row (rowptr) + x once + y once.
+//
+//  STREAM_LSU: the first-generation variant (coalesced 128-bit LDG of the tile,
+//    products parked in shared memory); kept for arrays that are not 16-byte aligned
+//    and for A/B timing.  ncu showed it L1-wavefront bound (profiles/round1_notes.md).
 //
 //  VECTOR (long or very uneven rows)
 //    2..32 lanes per row, strided accumulate, shuffle reduction.
@@ -185,6 +193,174 @@ spmv_stream_kernel(const psb_csr A, const double* __restrict__ x, double* __rest
 }
 
 // ---------------------------------------------------------------------------
+// STREAM kernel, bulk-async staged (default)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// global -> shared bulk copy (TMA engine), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                         uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+               "[%0], [%1], %2, [%3], %4;"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
+// Layout of one stage in dynamic shared memory (all offsets 16-byte aligned):
+//   vals[cap_v] doubles | cols[cap_c] ints | rp[R + 4] ints
+template <int EPI, int RPT>
+__global__ void __launch_bounds__(kBlock)
+spmv_bulk_kernel(const psb_csr A, const double* __restrict__ x, double* __restrict__ y,
+                 const EpiArgs ea, const int* __restrict__ d_skip, int cap_v, int cap_c) {
+  constexpr int R = kBlock * RPT;
+  constexpr int STAGES = 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double scratch[kWarps];
+  __shared__ __align__(8) uint64_t full[STAGES];
+
+  if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
+
+  const int tid = threadIdx.x;
+  const size_t stage_bytes = (size_t)cap_v * 8 + (size_t)cap_c * 4 + (size_t)(R + 4) * 4;
+  const int64_t n_tiles = (A.n_rows + R - 1) / R;
+  const int nnz_v_lim = (int)(A.nnz & ~(int64_t)1);          // bulk copies stop at the last
+  const int nnz_c_lim = (int)(A.nnz & ~(int64_t)3);          // whole 16-byte chunk of each array
+  const int rp_lim = (int)((A.n_rows + 1) & ~(int64_t)3);
+
+  auto stage_vals = [&](int st) { return reinterpret_cast<double*>(smem_raw + st * stage_bytes); };
+  auto stage_cols = [&](int st) { return reinterpret_cast<int*>(smem_raw + st * stage_bytes + (size_t)cap_v * 8); };
+  auto stage_rp = [&](int st) {
+    return reinterpret_cast<int*>(smem_raw + st * stage_bytes + (size_t)cap_v * 8 + (size_t)cap_c * 4);
+  };
+
+  uint64_t pol = 0;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    pol = policy_evict_first();
+  }
+  __syncthreads();
+
+  // producer (thread 0): stage tile `t` whose nonzero range is [s, e)
+  auto issue = [&](int64_t t, int st, int s, int e) {
+    const int64_t row0 = t * R;
+    const int nr = (int)min((int64_t)R, A.n_rows - row0);
+    const int v0 = s & ~1, c0 = s & ~3;
+    const int v1 = min((e + 1) & ~1, nnz_v_lim);
+    const int c1 = min((e + 3) & ~3, nnz_c_lim);
+    const int r1 = (int)min((int64_t)((nr + 1 + 3) & ~3), (int64_t)rp_lim - row0);
+    const uint32_t bv = v1 > v0 ? (uint32_t)(v1 - v0) * 8u : 0u;
+    const uint32_t bc = c1 > c0 ? (uint32_t)(c1 - c0) * 4u : 0u;
+    const uint32_t br = r1 > 0 ? (uint32_t)r1 * 4u : 0u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&full[st], bv + bc + br);
+    if (bv) bulk_g2s(stage_vals(st), A.vals + v0, bv, &full[st], pol);
+    if (bc) bulk_g2s(stage_cols(st), A.colind + c0, bc, &full[st], pol);
+    if (br) bulk_g2s(stage_rp(st), A.rowptr + row0, br, &full[st], pol);
+  };
+  auto tile_bounds = [&](int64_t t, int& s, int& e) {
+    const int64_t row0 = t * R;
+    s = ld_stream_i(A.rowptr + row0);
+    e = ld_stream_i(A.rowptr + min(row0 + R, A.n_rows));
+  };
+
+  int64_t tile = blockIdx.x;
+  int s_next = 0, e_next = 0;       // bounds of the tile to be staged next (thread 0 only)
+  if (tid == 0 && tile < n_tiles) {
+    int s, e;
+    tile_bounds(tile, s, e);
+    issue(tile, 0, s, e);
+    if (tile + gridDim.x < n_tiles) tile_bounds(tile + gridDim.x, s_next, e_next);
+  }
+
+  double acc = 0.0;
+  uint32_t phase_bits = 0u;
+  int st = 0;
+  for (; tile < n_tiles; tile += gridDim.x, st ^= 1) {
+    const int64_t nxt = tile + gridDim.x;
+    if (tid == 0 && nxt < n_tiles) {
+      issue(nxt, st ^ 1, s_next, e_next);              // stage st^1 was released by the
+      if (nxt + gridDim.x < n_tiles)                   // __syncthreads of the previous trip
+        tile_bounds(nxt + gridDim.x, s_next, e_next);
+    }
+    while (!mbar_try_wait(&full[st], (phase_bits >> st) & 1u)) {}
+    phase_bits ^= (1u << st);
+
+    const int64_t row0 = tile * R;
+    const int nr = (int)min((int64_t)R, A.n_rows - row0);
+    const double* sv = stage_vals(st);
+    const int*    sc = stage_cols(st);
+    int*          rp = stage_rp(st);
+
+    // Bulk copies stop at the last whole 16-byte chunk of each array; the few elements
+    // past it (they can only matter to the tiles at the very end of the matrix) are
+    // fetched with ordinary loads.  All conditions are uniform across the CTA.
+    if (row0 + nr + 1 > rp_lim) {
+      for (int64_t i = max(row0, (int64_t)rp_lim) + tid; i <= row0 + nr; i += kBlock)
+        rp[i - row0] = A.rowptr[i];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+    }
+    {
+      const int s0 = rp[0], e0 = rp[nr];
+      if (e0 > nnz_v_lim || e0 > nnz_c_lim) {
+        double* svw = stage_vals(st);
+        int*    scw = stage_cols(st);
+        for (int i = max(s0, nnz_v_lim) + tid; i < e0; i += kBlock) svw[i - (s0 & ~1)] = A.vals[i];
+        for (int i = max(s0, nnz_c_lim) + tid; i < e0; i += kBlock) scw[i - (s0 & ~3)] = A.colind[i];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+      }
+    }
+
+    const int s = rp[0];
+    const int offv = s & ~1, offc = s & ~3;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int lr = tid + j * kBlock;
+      if (lr < nr) {
+        const int a = rp[lr], b = rp[lr + 1];
+        double sum = 0.0;
+        int k = a;
+        for (; k + 4 <= b; k += 4) {                   // 4 independent gathers in flight
+          const int c0 = sc[k - offc], c1 = sc[k + 1 - offc], c2 = sc[k + 2 - offc], c3 = sc[k + 3 - offc];
+          const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+          sum += sv[k - offv] * x0;
+          sum += sv[k + 1 - offv] * x1;
+          sum += sv[k + 2 - offv] * x2;
+          sum += sv[k + 3 - offv] * x3;
+        }
+        for (; k < b; ++k) sum += sv[k - offv] * __ldg(x + sc[k - offc]);
+        epilogue<EPI>(row0 + lr, sum, x, y, ea, acc);
+      }
+    }
+    __syncthreads();                                   // stage st may be refilled now
+  }
+  finish_dot<EPI>(acc, A, ea, scratch);
+}
+
+// ---------------------------------------------------------------------------
 // VECTOR kernel: W lanes per row
 // ---------------------------------------------------------------------------
 template <int EPI, int W>
@@ -253,6 +429,36 @@ static int launch_stream(const psb_csr* A, const double* x, double* y, const Epi
   return PSB_OK;
 }
 
+static inline void bulk_caps(const psb_csr* A, int rpt, int* cap_v, int* cap_c, size_t* smem) {
+  const int mt = A->max_tile_nnz[rpt - 1];
+  *cap_v = (mt + 2 + 1) & ~1;                  // tile nnz + alignment slack, even
+  *cap_c = (mt + 6 + 3) & ~3;                  // multiple of 4 ints keeps rp[] 16-byte aligned
+  const size_t stage = (size_t)*cap_v * 8 + (size_t)*cap_c * 4 + (size_t)(kBlock * rpt + 4) * 4;
+  *smem = 2 * stage;
+}
+
+template <int EPI, int RPT>
+static int launch_bulk(const psb_csr* A, const double* x, double* y, const EpiArgs& ea,
+                       const int* d_skip, cudaStream_t st) {
+  constexpr int R = kBlock * RPT;
+  int cap_v, cap_c;
+  size_t smem;
+  bulk_caps(A, RPT, &cap_v, &cap_c, &smem);
+  static thread_local int cached_grid = 0;
+  static thread_local size_t cached_smem = 0;
+  static thread_local int64_t cached_tiles = -1;
+  const int64_t tiles = (A->n_rows + R - 1) / R;
+  if (cached_grid == 0 || cached_smem != smem || cached_tiles != tiles) {
+    int g = 0;
+    int rc = occupancy_grid(spmv_bulk_kernel<EPI, RPT>, smem, tiles, A->max_grid, &g);
+    if (rc != PSB_OK) return rc;
+    cached_grid = g; cached_smem = smem; cached_tiles = tiles;
+  }
+  spmv_bulk_kernel<EPI, RPT><<<cached_grid, kBlock, smem, st>>>(*A, x, y, ea, d_skip, cap_v, cap_c);
+  PSB_LAUNCH_CHECK();
+  return PSB_OK;
+}
+
 template <int EPI, int W>
 static int launch_vector(const psb_csr* A, const double* x, double* y, const EpiArgs& ea,
                          const int* d_skip, cudaStream_t st) {
@@ -276,6 +482,10 @@ static int launch_epi(const psb_csr* A, const double* x, double* y, const EpiArg
                       const int* d_skip, cudaStream_t st) {
   if (A->n_rows == 0) return PSB_OK;
   if (A->kind == PSB_SPMV_STREAM) {
+    return A->rpt == 2 ? launch_bulk<EPI, 2>(A, x, y, ea, d_skip, st)
+                       : launch_bulk<EPI, 1>(A, x, y, ea, d_skip, st);
+  }
+  if (A->kind == PSB_SPMV_STREAM_LSU) {
     if (A->rpt == 2)
       return A->vec_loads ? launch_stream<EPI, 2, true>(A, x, y, ea, d_skip, st)
                           : launch_stream<EPI, 2, false>(A, x, y, ea, d_skip, st);
@@ -305,21 +515,28 @@ int spmv_launch(const psb_csr* A, Epi epi, const double* x, double* y, const Epi
   return PSB_ERR_ARG;
 }
 
-// shared memory the STREAM kernel may use and still keep >= 4 CTAs per SM
-static constexpr int kStreamSmemBudget = 48 * 1024;
+// shared memory budgets that keep >= 3 CTAs per SM resident
+static constexpr size_t kBulkSmemBudget = 72 * 1024;
+static constexpr size_t kLsuSmemBudget = 48 * 1024;
+
+static size_t lsu_smem(const psb_csr* A, int rpt) {
+  return (size_t)((A->max_tile_nnz[rpt - 1] + 1) & ~1) * 8 + (size_t)(kBlock * rpt + 1) * 4;
+}
 
 static void choose_kernel(psb_csr* A) {
   const double mean = A->n_rows ? (double)A->nnz / (double)A->n_rows : 0.0;
   int w = 2;
   while (w < 32 && w < mean) w <<= 1;
   A->vec_width = w;
-  auto fits = [&](int rpt) {
-    size_t smem = (size_t)((A->max_tile_nnz[rpt - 1] + 1) & ~1) * 8 + (size_t)(kBlock * rpt + 1) * 4;
-    return smem <= (size_t)kStreamSmemBudget;
-  };
-  if (mean <= 32.0 && fits(2)) { A->kind = PSB_SPMV_STREAM; A->rpt = 2; }
-  else if (mean <= 32.0 && fits(1)) { A->kind = PSB_SPMV_STREAM; A->rpt = 1; }
-  else { A->kind = PSB_SPMV_VECTOR; A->rpt = 1; }
+  A->kind = PSB_SPMV_VECTOR; A->rpt = 1;
+  if (mean > 32.0) return;
+  if (A->vec_loads) {                                  // bulk copies need 16-byte alignment
+    int cv, cc; size_t smem;
+    bulk_caps(A, 1, &cv, &cc, &smem);
+    if (smem <= kBulkSmemBudget) { A->kind = PSB_SPMV_STREAM; A->rpt = 1; return; }
+  }
+  if (lsu_smem(A, 2) <= kLsuSmemBudget) { A->kind = PSB_SPMV_STREAM_LSU; A->rpt = 2; }
+  else if (lsu_smem(A, 1) <= kLsuSmemBudget) { A->kind = PSB_SPMV_STREAM_LSU; A->rpt = 1; }
 }
 
 }  // namespace psb
@@ -398,13 +615,22 @@ extern "C" int psb_csr_info(psb_csr_t A, int64_t info[8]) {
 
 extern "C" int psb_csr_set_kind(psb_csr_t A, int kind) {
   PSB_REQUIRE(A != nullptr, PSB_ERR_ARG, "psb_csr_set_kind: NULL handle");
-  if (kind == PSB_SPMV_VECTOR) { A->kind = kind; return PSB_OK; }
-  if (kind == PSB_SPMV_STREAM || kind == PSB_SPMV_STREAM + 16) {
-    const int rpt = (kind == PSB_SPMV_STREAM) ? 2 : 1;   // +16 selects 256-row tiles
-    size_t smem = (size_t)((A->max_tile_nnz[rpt - 1] + 1) & ~1) * 8 + (size_t)(kBlock * rpt + 1) * 4;
+  const int base = kind & 15;
+  const int rpt = (kind & PSB_SPMV_TILE512) ? 2 : 1;
+  if (base == PSB_SPMV_VECTOR) { A->kind = base; return PSB_OK; }
+  if (base == PSB_SPMV_STREAM) {
+    PSB_REQUIRE(A->vec_loads, PSB_ERR_UNSUPP, "psb_csr_set_kind: arrays are not 16-byte aligned");
+    int cv, cc; size_t smem;
+    bulk_caps(A, rpt, &cv, &cc, &smem);
     PSB_REQUIRE(smem <= (size_t)max_optin_smem(), PSB_ERR_UNSUPP,
                 "psb_csr_set_kind: tile does not fit in shared memory");
-    A->kind = PSB_SPMV_STREAM; A->rpt = rpt;
+    A->kind = base; A->rpt = rpt;
+    return PSB_OK;
+  }
+  if (base == PSB_SPMV_STREAM_LSU) {
+    PSB_REQUIRE(lsu_smem(A, rpt) <= (size_t)max_optin_smem(), PSB_ERR_UNSUPP,
+                "psb_csr_set_kind: tile does not fit in shared memory");
+    A->kind = base; A->rpt = rpt;
     return PSB_OK;
   }
   set_error("psb_csr_set_kind: unknown kind %d", kind);

@@ -1,0 +1,405 @@
+// Sparse triangular solves for the IC / ILUT preconditioners (and the AMG Gauss-Seidel
+// smoother and coarse solve): x = T^-1 b for a lower or upper triangular CSR factor.
+//
+// Replaces scipy.sparse.linalg.spsolve_triangular (PySolvers/Linear/ICPreconditioner.py:61-63)
+// and SuperLU.solve (PySolvers/Linear/ILUTPreconditioner.py:67,78), both SuperLU gstrs on
+// one CPU thread.  The factors come from the reference's own SuperLU setup on the host and
+// are uploaded once.
+//
+// The reference's IC factor of the 2-D Laplacian has ~11.8 m dependency levels with only
+// ~m/12 rows each: a kernel launch (or a grid barrier) per
+// level is hopeless, the solve is bound by the LATENCY of the dependency chain, not by HBM.
+// Design:
+//  * analysis (host, once): level(i) = 1 + max level of the rows it depends on; rows sorted
+//    level-major (ascending inside a level); the strictly triangular part is repacked in
+//    that order as SELL-32 (entry k of 32 consecutive items is contiguous) so every load of
+//    the solve is coalesced; the diagonal is split out.
+//  * solve: ONE persistent launch.  Warps claim 32 consecutive items with an atomic
+//    counter; each THREAD owns one row and accumulates b_i - sum L_ij x_j sequentially IN
+//    STORED COLUMN ORDER, dividing by the diagonal last (the reference's summation order,
+//    SURVEY.md section 7.3-2), so the dependency that arrives last -- the one nearest the
+//    diagonal -- is also the last operand and everything else is folded in beforehand.
+//    Readiness travels with the data: x is pre-filled with a NaN sentinel and a consumer
+//    polls x[j] (ld.volatile, L2) until it changes -- one L2 round trip per level on the
+//    critical path, no flags, no fences, no grid barrier.  The poll loop never blocks a
+//    lane on another (each trip is non-blocking), so dependencies inside a warp resolve.
+//    Items are claimed in dependency order, hence every awaited row is owned by a warp that
+//    is already running: no deadlock whatever the residency.  A bounded spin count turns a
+//    would-be hang into an error code.
+#include "sptrsv.cuh"
+#include "prec.cuh"
+
+#include <algorithm>
+#include <new>
+
+namespace psb {
+
+static constexpr unsigned long long kSentinelBits = 0xFFF8DEADBEEF0B20ull;   // a quiet NaN payload
+static constexpr int kSpinLimit = 1 << 22;   // polls per lane before giving up (>= 1 s)
+
+__device__ __forceinline__ double ld_volatile(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile(double* p, double v) {
+  asm volatile("st.volatile.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ bool is_ready(double v) {
+  return (unsigned long long)__double_as_longlong(v) != kSentinelBits;
+}
+
+__global__ void __launch_bounds__(kBlock)
+trsv_prepare_kernel(double* __restrict__ x, int64_t n, unsigned int* counter, const int* d_skip) {
+  if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
+  const double s = __longlong_as_double((long long)kSentinelBits);
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+    x[i] = s;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;
+}
+
+struct TrsvView {
+  int64_t n;
+  int n_groups;
+  const int32_t* order;
+  const int64_t* grp_ptr;
+  const int32_t* cols;
+  const double* vals;
+  const double* diag;
+  unsigned int* counter;
+  int* error;
+  int unit_diag;
+};
+
+__global__ void __launch_bounds__(kBlock)
+trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
+                  const int32_t* __restrict__ rhs_map, double* out2,
+                  const int32_t* __restrict__ out_map, const int* d_skip) {
+  if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned int g = 0;
+    if (lane == 0) g = atomicAdd(T.counter, 1u);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= (unsigned int)T.n_groups) return;
+    const int64_t q = (int64_t)g * 32 + lane;
+    const bool active = q < T.n;
+    int row = 0;
+    double acc = 0.0, d = 1.0;
+    const int64_t base = T.grp_ptr[g];
+    const int len = (int)((T.grp_ptr[g + 1] - base) >> 5);
+    if (active) {
+      row = T.order[q];
+      acc = rhs_map ? rhs[rhs_map[row]] : rhs[row];
+      d = T.diag[q];
+    }
+    int k = 0;
+    int spins = 0;
+    bool done = !active;
+    // prefetch the first entry
+    int c = -1;
+    double v = 0.0;
+    if (active && len > 0) { c = T.cols[base + lane]; v = T.vals[base + lane]; }
+    while (!__all_sync(0xffffffffu, done)) {
+      if (!done) {
+        if (k < len && c >= 0) {
+          const double xv = ld_volatile(x + c);
+          if (is_ready(xv)) {
+            acc = acc - v * xv;                       // stored order, product rounded first
+            ++k;
+            if (k < len) {
+              c = T.cols[base + (int64_t)k * 32 + lane];
+              v = T.vals[base + (int64_t)k * 32 + lane];
+            }
+          } else if (++spins > kSpinLimit) {
+            *T.error = 1;                             // dependency never arrived: give up loudly
+            k = len;
+          }
+        } else {
+          const double r = T.unit_diag ? acc : acc / d;   // divide by the diagonal last
+          st_volatile(x + row, r);
+          if (out2 != nullptr) out2[out_map[row]] = r;
+          done = true;
+        }
+      }
+    }
+  }
+}
+
+int trsv_solve(const psb_trsv* T, const double* rhs, double* x, const int32_t* rhs_map,
+               double* out2, const int32_t* out_map, const int* d_skip, cudaStream_t st) {
+  if (T->n == 0) return PSB_OK;
+  const int fill_grid = (int)std::min<int64_t>((T->n + kBlock * 4 - 1) / (kBlock * 4), (int64_t)sm_count() * 8);
+  trsv_prepare_kernel<<<std::max(fill_grid, 1), kBlock, 0, st>>>(x, T->n, T->d_counter, d_skip);
+  PSB_LAUNCH_CHECK();
+  static thread_local int per_sm = 0;
+  if (per_sm == 0) {
+    PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_solve_kernel, kBlock, 0));
+    if (per_sm < 1) per_sm = 1;
+  }
+  const int64_t warps_needed = T->n_groups;
+  int64_t grid = std::min<int64_t>((int64_t)per_sm * sm_count(), (warps_needed + kWarps - 1) / kWarps);
+  TrsvView V{T->n, T->n_groups, T->d_order, T->d_grp_ptr, T->d_cols, T->d_vals, T->d_diag,
+             T->d_counter, T->d_error, T->unit_diag};
+  trsv_solve_kernel<<<(int)std::max<int64_t>(grid, 1), kBlock, 0, st>>>(V, rhs, x, rhs_map, out2, out_map, d_skip);
+  PSB_LAUNCH_CHECK();
+  return PSB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host analysis
+// ---------------------------------------------------------------------------
+static void free_trsv(psb_trsv* T) {
+  if (!T) return;
+  cudaFree(T->d_order); cudaFree(T->d_grp_ptr); cudaFree(T->d_cols); cudaFree(T->d_vals);
+  cudaFree(T->d_diag); cudaFree(T->d_counter); cudaFree(T->d_error);
+  delete T;
+}
+
+template <typename T>
+static cudaError_t upload(T** dptr, const std::vector<T>& h, cudaStream_t st) {
+  cudaError_t e = cudaMalloc((void**)dptr, std::max<size_t>(h.size(), 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  if (!h.empty()) e = cudaMemcpyAsync(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+  return e;
+}
+
+// ---------------------------------------------------------------------------
+// preconditioner objects
+// ---------------------------------------------------------------------------
+struct IcPrec : psb_prec {
+  psb_trsv* L = nullptr;     // not owned
+  psb_trsv* Lt = nullptr;
+  double* tmp = nullptr;     // owned, n doubles
+  ~IcPrec() override { cudaFree(tmp); }
+  const char* kind() const override { return "ic"; }
+  int check_error() override {
+    int a = 0, b = 0;
+    cudaMemcpy(&a, L->d_error, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaMemcpy(&b, Lt->d_error, sizeof(int), cudaMemcpyDeviceToHost);
+    return a | b;
+  }
+  int apply(const double* r, double* z, const int* d_skip, cudaStream_t st) override {
+    int rc = trsv_solve(L, r, tmp, nullptr, nullptr, nullptr, d_skip, st);    // u = L^-1 r
+    if (rc != PSB_OK) return rc;
+    return trsv_solve(Lt, tmp, z, nullptr, nullptr, nullptr, d_skip, st);     // z = L^-T u
+  }
+};
+
+// x = Pc U^-1 L^-1 Pr v with Pr[perm_r[i], i] = 1 and Pc[i, perm_c[i]] = 1
+// (SuperLU.solve).
+struct IluPrec : psb_prec {
+  psb_trsv* L = nullptr;     // unit lower, not owned
+  psb_trsv* U = nullptr;
+  int32_t* iperm_r = nullptr;   // owned: row r of L takes v[iperm_r[r]]
+  int32_t* iperm_c = nullptr;   // owned: result[iperm_c[r]] = z[r]
+  double* tmp1 = nullptr;       // owned
+  double* tmp2 = nullptr;
+  ~IluPrec() override { cudaFree(iperm_r); cudaFree(iperm_c); cudaFree(tmp1); cudaFree(tmp2); }
+  const char* kind() const override { return "ilu"; }
+  int check_error() override {
+    int a = 0, b = 0;
+    cudaMemcpy(&a, L->d_error, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaMemcpy(&b, U->d_error, sizeof(int), cudaMemcpyDeviceToHost);
+    return a | b;
+  }
+  int apply(const double* r, double* z, const int* d_skip, cudaStream_t st) override {
+    int rc = trsv_solve(L, r, tmp1, iperm_r, nullptr, nullptr, d_skip, st);
+    if (rc != PSB_OK) return rc;
+    return trsv_solve(U, tmp1, tmp2, nullptr, z, iperm_c, d_skip, st);
+  }
+};
+
+}  // namespace psb
+
+using namespace psb;
+
+extern "C" int psb_trsv_create(int64_t n, const int32_t* h_rowptr, const int32_t* h_colind,
+                               const double* h_vals, int lower, int unit_diag, void* stream,
+                               psb_trsv_t* out) {
+  PSB_REQUIRE(out != nullptr && n >= 0, PSB_ERR_ARG, "psb_trsv_create: bad argument");
+  PSB_REQUIRE(n < (int64_t)INT32_MAX, PSB_ERR_UNSUPP, "psb_trsv_create: int32 row range exceeded");
+  PSB_REQUIRE(h_rowptr != nullptr, PSB_ERR_ARG, "psb_trsv_create: rowptr is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  psb_trsv* T = new (std::nothrow) psb_trsv();
+  PSB_REQUIRE(T != nullptr, PSB_ERR_ARG, "psb_trsv_create: out of host memory");
+  T->n = n; T->lower = lower ? 1 : 0; T->unit_diag = unit_diag ? 1 : 0;
+
+  // ---- levels: level(i) = 1 + max level over the rows i depends on ------------------
+  std::vector<int32_t> level((size_t)n, 0);
+  std::vector<double> diag_by_row((size_t)n, 1.0);
+  std::vector<int32_t> off_count((size_t)n, 0);
+  int32_t max_level = -1;
+  bool missing_diag = false;
+  auto visit = [&](int64_t i) {
+    int32_t lv = 0, cnt = 0;
+    bool have_d = false;
+    for (int32_t p = h_rowptr[i]; p < h_rowptr[i + 1]; ++p) {
+      const int32_t j = h_colind[p];
+      if (j == i) { diag_by_row[i] = h_vals[p]; have_d = true; continue; }
+      const bool dep = lower ? (j < i) : (j > i);
+      if (!dep) continue;                      // entries on the wrong side are ignored
+      ++cnt;
+      lv = std::max(lv, level[j] + 1);
+    }
+    if (!have_d && !unit_diag) missing_diag = true;
+    if (unit_diag) diag_by_row[i] = 1.0;
+    level[i] = lv; off_count[i] = cnt;
+    max_level = std::max(max_level, lv);
+  };
+  if (lower) for (int64_t i = 0; i < n; ++i) visit(i);
+  else       for (int64_t i = n - 1; i >= 0; --i) visit(i);
+  if (missing_diag) {
+    delete T;
+    set_error("psb_trsv_create: a row has no diagonal entry");
+    return PSB_ERR_ARG;
+  }
+  T->n_levels = (int)(max_level + 1);
+
+  // ---- level-major order (counting sort, ascending row id inside a level) -----------
+  T->h_level_ptr.assign((size_t)T->n_levels + 1, 0);
+  for (int64_t i = 0; i < n; ++i) T->h_level_ptr[level[i] + 1]++;
+  for (int l = 0; l < T->n_levels; ++l) T->h_level_ptr[l + 1] += T->h_level_ptr[l];
+  T->h_level_rows.assign((size_t)n, 0);
+  {
+    std::vector<int32_t> cursor(T->h_level_ptr.begin(), T->h_level_ptr.end() - (T->n_levels ? 1 : 0));
+    for (int64_t i = 0; i < n; ++i) T->h_level_rows[cursor[level[i]]++] = (int32_t)i;
+  }
+
+  // ---- SELL-32 packing in that order --------------------------------------------------
+  T->n_groups = (int)((n + 31) / 32);
+  std::vector<int64_t> grp_ptr((size_t)T->n_groups + 1, 0);
+  for (int g = 0; g < T->n_groups; ++g) {
+    int32_t w = 0;
+    for (int l = 0; l < 32; ++l) {
+      const int64_t q = (int64_t)g * 32 + l;
+      if (q < n) w = std::max(w, off_count[T->h_level_rows[q]]);
+    }
+    grp_ptr[g + 1] = grp_ptr[g] + (int64_t)w * 32;
+  }
+  T->nnz_packed = grp_ptr[T->n_groups];
+  std::vector<int32_t> cols((size_t)T->nnz_packed, -1);
+  std::vector<double> vals((size_t)T->nnz_packed, 0.0);
+  std::vector<double> diag((size_t)n, 1.0);
+  int64_t nnz_off = 0;
+  for (int64_t q = 0; q < n; ++q) {
+    const int32_t i = T->h_level_rows[q];
+    const int g = (int)(q >> 5), l = (int)(q & 31);
+    diag[q] = diag_by_row[i];
+    int k = 0;
+    for (int32_t p = h_rowptr[i]; p < h_rowptr[i + 1]; ++p) {
+      const int32_t j = h_colind[p];
+      if (j == i) continue;
+      const bool dep = lower ? (j < i) : (j > i);
+      if (!dep) continue;
+      cols[grp_ptr[g] + (int64_t)k * 32 + l] = j;
+      vals[grp_ptr[g] + (int64_t)k * 32 + l] = h_vals[p];
+      ++k; ++nnz_off;
+    }
+  }
+  T->nnz_off = nnz_off;
+
+  cudaError_t e = upload(&T->d_order, T->h_level_rows, st);
+  if (e == cudaSuccess) e = upload(&T->d_grp_ptr, grp_ptr, st);
+  if (e == cudaSuccess) e = upload(&T->d_cols, cols, st);
+  if (e == cudaSuccess) e = upload(&T->d_vals, vals, st);
+  if (e == cudaSuccess) e = upload(&T->d_diag, diag, st);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&T->d_counter, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&T->d_error, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemsetAsync(T->d_error, 0, sizeof(int), st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // host vectors die at return
+  if (e != cudaSuccess) {
+    set_error("psb_trsv_create: %s", cudaGetErrorString(e));
+    free_trsv(T);
+    return PSB_ERR_CUDA;
+  }
+  *out = T;
+  return PSB_OK;
+}
+
+extern "C" int psb_trsv_destroy(psb_trsv_t T) {
+  free_trsv(T);
+  return PSB_OK;
+}
+
+extern "C" int psb_trsv_info(psb_trsv_t T, int64_t info[8]) {
+  PSB_REQUIRE(T && info, PSB_ERR_ARG, "psb_trsv_info: NULL argument");
+  info[0] = T->n; info[1] = T->n_levels; info[2] = T->nnz_off; info[3] = T->nnz_packed;
+  info[4] = T->lower; info[5] = T->unit_diag; info[6] = T->n_groups; info[7] = 0;
+  return PSB_OK;
+}
+
+extern "C" int psb_trsv_get_levels(psb_trsv_t T, int32_t* h_level_ptr, int32_t* h_level_rows) {
+  PSB_REQUIRE(T && h_level_ptr && h_level_rows, PSB_ERR_ARG, "psb_trsv_get_levels: NULL argument");
+  std::copy(T->h_level_ptr.begin(), T->h_level_ptr.end(), h_level_ptr);
+  std::copy(T->h_level_rows.begin(), T->h_level_rows.end(), h_level_rows);
+  return PSB_OK;
+}
+
+extern "C" int psb_trsv_solve(psb_trsv_t T, const double* d_b, double* d_x, void* stream) {
+  PSB_REQUIRE(T && d_b && d_x, PSB_ERR_ARG, "psb_trsv_solve: NULL argument");
+  PSB_REQUIRE(d_b != d_x, PSB_ERR_ARG, "psb_trsv_solve: x must not alias b");
+  return trsv_solve(T, d_b, d_x, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int psb_trsv_error(psb_trsv_t T, int32_t* h_flag) {
+  PSB_REQUIRE(T && h_flag, PSB_ERR_ARG, "psb_trsv_error: NULL argument");
+  int v = 0;
+  PSB_CUDA(cudaMemcpy(&v, T->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+  *h_flag = v;
+  return PSB_OK;
+}
+
+extern "C" int psb_ic_create(psb_trsv_t L, psb_trsv_t Lt, psb_prec_t* out) {
+  PSB_REQUIRE(L && Lt && out, PSB_ERR_ARG, "psb_ic_create: NULL argument");
+  PSB_REQUIRE(L->n == Lt->n && L->lower && !Lt->lower, PSB_ERR_ARG,
+              "psb_ic_create: need a lower and an upper factor of the same size");
+  IcPrec* P = new (std::nothrow) IcPrec();
+  PSB_REQUIRE(P != nullptr, PSB_ERR_ARG, "psb_ic_create: out of host memory");
+  P->n = L->n; P->L = L; P->Lt = Lt;
+  cudaError_t e = cudaMalloc((void**)&P->tmp, std::max<int64_t>(L->n, 1) * sizeof(double));
+  if (e != cudaSuccess) { delete P; set_error("psb_ic_create: %s", cudaGetErrorString(e)); return PSB_ERR_CUDA; }
+  *out = P;
+  return PSB_OK;
+}
+
+extern "C" int psb_ilu_create(psb_trsv_t L, psb_trsv_t U, const int32_t* h_perm_r,
+                              const int32_t* h_perm_c, void* stream, psb_prec_t* out) {
+  PSB_REQUIRE(L && U && h_perm_r && h_perm_c && out, PSB_ERR_ARG, "psb_ilu_create: NULL argument");
+  PSB_REQUIRE(L->n == U->n && L->lower && !U->lower, PSB_ERR_ARG,
+              "psb_ilu_create: need a lower and an upper factor of the same size");
+  const int64_t n = L->n;
+  IluPrec* P = new (std::nothrow) IluPrec();
+  PSB_REQUIRE(P != nullptr, PSB_ERR_ARG, "psb_ilu_create: out of host memory");
+  P->n = n; P->L = L; P->U = U;
+  // (Pr v)[perm_r[i]] = v[i]  ->  row r of the L solve reads v[iperm_r[r]]
+  // (Pc z)[i] = z[perm_c[i]]  ->  row r of the U solve writes result[iperm_c[r]]
+  std::vector<int32_t> ipr((size_t)n), ipc((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    if (h_perm_r[i] < 0 || h_perm_r[i] >= n || h_perm_c[i] < 0 || h_perm_c[i] >= n) {
+      delete P; set_error("psb_ilu_create: permutation entry out of range"); return PSB_ERR_ARG;
+    }
+    ipr[h_perm_r[i]] = (int32_t)i;
+    ipc[h_perm_c[i]] = (int32_t)i;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = upload(&P->iperm_r, ipr, st);
+  if (e == cudaSuccess) e = upload(&P->iperm_c, ipc, st);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&P->tmp1, std::max<int64_t>(n, 1) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&P->tmp2, std::max<int64_t>(n, 1) * sizeof(double));
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { delete P; set_error("psb_ilu_create: %s", cudaGetErrorString(e)); return PSB_ERR_CUDA; }
+  *out = P;
+  return PSB_OK;
+}
+
+extern "C" int psb_prec_apply(psb_prec_t P, const double* d_r, double* d_z, void* stream) {
+  PSB_REQUIRE(P && d_r && d_z, PSB_ERR_ARG, "psb_prec_apply: NULL argument");
+  PSB_REQUIRE(d_r != d_z, PSB_ERR_ARG, "psb_prec_apply: z must not alias r");
+  return P->apply(d_r, d_z, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int psb_prec_destroy(psb_prec_t P) {
+  delete P;
+  return PSB_OK;
+}

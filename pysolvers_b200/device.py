@@ -125,3 +125,105 @@ class DeviceCSR:
                 self._h = C.c_void_p()
         except Exception:
             pass
+
+
+def host_csr(A):
+    """scipy CSR (int32 indices, fp64 data, C-contiguous) of a host matrix."""
+    M = sp.csr_matrix(A)
+    return (np.ascontiguousarray(M.indptr, dtype=np.int32),
+            np.ascontiguousarray(M.indices, dtype=np.int32),
+            np.ascontiguousarray(M.data, dtype=np.float64), M.shape)
+
+
+class DeviceTrsv:
+    """A triangular factor analysed into level sets and resident in HBM
+    (psb_trsv_t).  ``T`` is a host scipy matrix in CSR stored order."""
+
+    def __init__(self, T, lower, unit_diag=False):
+        require_cuda()
+        indptr, indices, data, shape = host_csr(T)
+        assert shape[0] == shape[1]
+        self.n = int(shape[0])
+        self.lower, self.unit_diag = bool(lower), bool(unit_diag)
+        self._h = C.c_void_p()
+        nat.check(nat.lib().psb_trsv_create(
+            self.n, indptr.ctypes.data_as(C.c_void_p), indices.ctypes.data_as(C.c_void_p),
+            data.ctypes.data_as(C.c_void_p), 1 if lower else 0, 1 if unit_diag else 0,
+            current_stream_ptr(), C.byref(self._h)), 'psb_trsv_create')
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self):
+        buf = (C.c_int64 * 8)()
+        nat.check(nat.lib().psb_trsv_info(self._h, buf), 'psb_trsv_info')
+        return dict(n=int(buf[0]), levels=int(buf[1]), nnz_off=int(buf[2]),
+                    nnz_packed=int(buf[3]), lower=bool(buf[4]), unit_diag=bool(buf[5]),
+                    groups=int(buf[6]))
+
+    def levels(self):
+        """(level_ptr, level_rows) as int32 numpy arrays."""
+        nlev = self.info()['levels']
+        lptr = np.zeros(nlev + 1, dtype=np.int32)
+        rows = np.zeros(self.n, dtype=np.int32)
+        nat.check(nat.lib().psb_trsv_get_levels(
+            self._h, lptr.ctypes.data_as(C.c_void_p), rows.ctypes.data_as(C.c_void_p)),
+            'psb_trsv_get_levels')
+        return lptr, rows
+
+    def solve(self, b, out=None):
+        """x = T^-1 b; b, x CUDA fp64 tensors."""
+        if out is None:
+            out = torch.empty_like(b)
+        nat.check(nat.lib().psb_trsv_solve(self._h, ptr(b), ptr(out), current_stream_ptr()),
+                  'psb_trsv_solve')
+        return out
+
+    def check(self):
+        flag = C.c_int32(0)
+        nat.check(nat.lib().psb_trsv_error(self._h, C.byref(flag)), 'psb_trsv_error')
+        if flag.value:
+            raise nat.NativeError('triangular solve: a dependency never became ready')
+
+    def __del__(self):
+        try:
+            if self._h:
+                nat.lib().psb_trsv_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+
+class DevicePrec:
+    """Owner of a psb_prec_t plus whatever it references (kept alive here)."""
+
+    def __init__(self, handle, n, keep=()):
+        self._h = handle
+        self.n = n
+        self._keep = tuple(keep)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def apply(self, r, out=None):
+        if out is None:
+            out = torch.empty_like(r)
+        nat.check(nat.lib().psb_prec_apply(self._h, ptr(r), ptr(out), current_stream_ptr()),
+                  'psb_prec_apply')
+        return out
+
+    def apply_host(self, vec):
+        """numpy in, numpy out (upload, apply on the device, download)."""
+        v = np.asarray(vec, dtype=np.float64)
+        out = self.apply(to_device(v))
+        return out.cpu().numpy()
+
+    def __del__(self):
+        try:
+            if self._h:
+                nat.lib().psb_prec_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass

@@ -82,7 +82,17 @@ def test_pcg_vs_oracle_fresh_inputs(cuda, seed):
     assert st.success() == ref['success']
     assert abs(st.iters() - ref['iters']) <= 1
     k = min(len(hist), len(ref['hist']))
-    assert rel_err(hist[:k], ref['hist'][:k]) < HIST_RTOL
+    # Rounding noise floor of THIS input: the oracle against itself with only the
+    # summation order of its dot products changed.  CG amplifies 1-ulp changes of
+    # alpha/beta on ill-conditioned systems (DH-11 here), so 1e-10 is attainable only
+    # while that floor is below it; beyond that we require to stay within 10x the floor.
+    alt = krylov.pcg(A, b, maxiter=400, tau=1e-9, dot=krylov.pairwise_dot)
+    ka = min(k, len(alt['hist']))
+    floor = np.abs(alt['hist'][:ka] - ref['hist'][:ka]) / ref['hist'][:ka]
+    floor = np.maximum.accumulate(floor)
+    err = np.abs(hist[:ka] - ref['hist'][:ka]) / ref['hist'][:ka]
+    assert np.all(err <= np.maximum(HIST_RTOL, 10.0 * floor)), float(np.max(err / np.maximum(HIST_RTOL, floor)))
+    assert rel_err(hist[:20], ref['hist'][:20]) < HIST_RTOL
     assert np.linalg.norm(st.soln() - ref['soln']) <= SOLN_RTOL * np.linalg.norm(ref['soln'])
 
 

@@ -45,13 +45,14 @@ def test_spmv_matches_scipy(cuda, name):
     dA = DeviceCSR(A)
     xd = to_device(x)
     kinds = [dA.info()['kind']]
-    for kind in (nat.SPMV_STREAM, nat.SPMV_STREAM + 16, nat.SPMV_VECTOR):
+    for kind in (nat.SPMV_STREAM, nat.SPMV_STREAM | nat.SPMV_TILE512, nat.SPMV_STREAM_LSU,
+                 nat.SPMV_STREAM_LSU | nat.SPMV_TILE512, nat.SPMV_VECTOR):
         try:
             dA.set_kind(kind)
         except nat.NativeError:
             continue
         got = dA.matvec(xd).cpu().numpy()
-        if kind != nat.SPMV_VECTOR:
+        if (kind & 15) != nat.SPMV_VECTOR:
             # STREAM sums each row in stored order from +0, no FMA: bit-identical
             assert np.array_equal(got, want), (name, kind)
         else:
@@ -109,8 +110,8 @@ def test_dot_matches_numpy(cuda):
     for n in (1, 2, 3, 255, 256, 257, 100001, 1 << 20):
         a, b = rng.standard_normal(n), rng.standard_normal(n)
         out = torch.zeros(1, dtype=torch.float64, device='cuda')
-        nat.check(nat.lib().psb_dot(n, ptr(to_device(a)), ptr(to_device(b)), ptr(out),
-                                    current_stream_ptr()))
+        ad, bd = to_device(a), to_device(b)       # keep alive until the kernel has run
+        nat.check(nat.lib().psb_dot(n, ptr(ad), ptr(bd), ptr(out), current_stream_ptr()))
         ref = np.dot(a, b)
         assert abs(out.item() - ref) <= 1e-13 * np.dot(np.abs(a), np.abs(b)), n
 

@@ -1,0 +1,161 @@
+"""Sparse triangular solves and the IC / ILUT preconditioners on the B200.
+
+Level sets must match the numpy oracle bit-exactly (north_star); the solve
+follows the row-wise stored-order summation of oracle.precond.trsv_rowwise, so
+on small cases it is compared bit for bit with that restatement and to
+rounding with scipy's spsolve_triangular / SuperLU.solve (what the reference
+calls, ICPreconditioner.py:58-63, ILUTPreconditioner.py:66-78)."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from conftest import rel_err, golden_csr
+
+pytestmark = pytest.mark.gpu
+
+
+def _lap(m):
+    from pysolvers_b200.problems import fd_laplacian_2d
+    return -fd_laplacian_2d(0.0, 1.0, m)
+
+
+def _factors(m):
+    from oracle import precond
+    return precond.ic_factor(_lap(m))
+
+
+@pytest.mark.parametrize('m', [8, 24])
+def test_levels_bit_exact_and_solve_matches_rowwise(cuda, m):
+    from oracle import precond
+    from pysolvers_b200.device import DeviceTrsv, to_device
+    L, Lt = _factors(m)
+    v = np.random.default_rng(m).standard_normal(L.shape[0])
+    for T, lower in ((L, True), (Lt, False)):
+        dT = DeviceTrsv(T, lower=lower)
+        level, lptr, lrows = precond.level_sets(T, lower=lower)
+        got_ptr, got_rows = dT.levels()
+        assert np.array_equal(got_ptr, lptr)
+        assert np.array_equal(got_rows, lrows)
+        assert dT.info()['levels'] == len(lptr) - 1
+        x = dT.solve(to_device(v)).cpu().numpy()
+        dT.check()
+        assert np.array_equal(x, precond.trsv_rowwise(T, v, lower=lower))
+        ref = spla.spsolve_triangular(T, v, lower=lower)
+        assert np.linalg.norm(x - ref) <= 1e-13 * np.linalg.norm(ref)
+
+
+def test_trsv_edge_cases(cuda):
+    from pysolvers_b200.device import DeviceTrsv, to_device
+    rng = np.random.default_rng(0)
+    # diagonal only (one level), unit lower with explicit ones, single row, dense-ish random lower
+    cases = []
+    cases.append((sp.diags(rng.random(77) + 1.0).tocsr(), True, False))
+    Lr = sp.tril(sp.random(300, 300, density=0.05, random_state=rng), k=-1) + sp.identity(300)
+    cases.append((Lr.tocsr(), True, True))
+    cases.append((sp.csr_matrix(np.array([[2.5]])), True, False))
+    Ur = sp.triu(sp.random(257, 257, density=0.1, random_state=rng), k=1) + sp.diags(rng.random(257) + 2.0)
+    cases.append((Ur.tocsr(), False, False))
+    # long chain: bidiagonal -> n levels with one row each
+    n = 2000
+    chain = sp.diags([np.full(n - 1, -0.5), np.full(n, 1.5)], [-1, 0]).tocsr()
+    cases.append((chain, True, False))
+    for T, lower, unit in cases:
+        v = rng.standard_normal(T.shape[0])
+        dT = DeviceTrsv(T, lower=lower, unit_diag=unit)
+        x = dT.solve(to_device(v)).cpu().numpy()
+        dT.check()
+        ref = spla.spsolve_triangular(T.tocsr(), v, lower=lower, unit_diagonal=unit)
+        assert np.linalg.norm(x - ref) <= 1e-12 * np.linalg.norm(ref)
+    assert DeviceTrsv(chain, lower=True).info()['levels'] == n
+
+
+def test_ic_apply_vs_reference_golden(cuda, golden):
+    from pysolvers_b200.Linear import RightIC
+    A = _lap(32)
+    pre = RightIC().form(A)
+    gL = golden_csr(golden, 'ic/L_m32')
+    gLt = golden_csr(golden, 'ic/Lt_m32')
+    # the host setup is the reference's: same factors, same stored order, bit for bit
+    for mine, ref in ((pre._L, gL), (pre._Lt, gLt)):
+        assert np.array_equal(mine.indptr, ref.indptr)
+        assert np.array_equal(mine.indices, ref.indices)
+        assert np.array_equal(mine.data, ref.data)
+    v = golden['ic/apply_m32_in']
+    out = pre.applyRight(v)
+    assert rel_err(out, golden['ic/apply_m32_out']) < 1e-11
+    assert pre.applyLeft(v) is v
+
+
+def test_ilut_apply_vs_reference_golden(cuda, golden):
+    from pysolvers_b200.Linear import RightILUT, LeftILUT
+    from pysolvers_b200.problems import load_dh_matrix
+    A = load_dh_matrix(8)
+    v = golden['ilut/apply_dh8_in']
+    pre = RightILUT().form(A)
+    out = pre.applyRight(v)
+    g = golden['ilut/apply_dh8_out']
+    assert np.linalg.norm(out - g) <= 1e-12 * np.linalg.norm(g)
+    left = LeftILUT().form(A)
+    assert left.applyRight(v) is v                       # no-op from the right
+    assert left.right_device_handle() is None
+    assert np.linalg.norm(left.applyLeft(v) - g) <= 1e-12 * np.linalg.norm(g)
+
+
+def _run(solver, A, b):
+    hist = []
+    solver.reportIter = lambda k, nr, nb: hist.append(nr)
+    with contextlib.redirect_stdout(io.StringIO()):
+        st = solver.solve(A, b)
+    return st, np.asarray(hist)
+
+
+@pytest.mark.parametrize('m', [16, 32, 64])
+def test_icpcg_history_vs_reference_golden(cuda, golden, m):
+    from pysolvers_b200 import CommonSolverArgs
+    from pysolvers_b200.Linear import PCG, RightIC
+    A = _lap(m)
+    st, hist = _run(PCG(CommonSolverArgs(maxiter=500, tau=1e-8), precond=RightIC()).makeSolver(),
+                    A, np.ones(A.shape[0]))
+    key = 'icpcg/lap2d_m%d' % m
+    assert st.success() and abs(st.iters() - int(golden[key + '/iters'])) <= 1
+    k = min(len(hist), len(golden[key + '/hist']))
+    assert rel_err(hist[:k], golden[key + '/hist'][:k]) < 1e-10
+    gx = golden[key + '/x']
+    assert np.linalg.norm(st.soln() - gx) <= 1e-8 * np.linalg.norm(gx)
+
+
+def test_known_answer_dh10(cuda, golden):
+    """The assertions of the reference's own (stale) tests on the current API:
+    tests/TestPCG.py:28-40 and tests/TestGMRES.py:28-40 -- ||x - x_ex|| <= 1e-8."""
+    from pysolvers_b200 import CommonSolverArgs
+    from pysolvers_b200.Linear import PCG, RightIC, RightILUT
+    from pysolvers_b200.problems import load_dh_matrix
+    A = load_dh_matrix(10)
+    xex = np.random.default_rng(99).random(A.shape[0])
+    b = A @ xex
+    st, h = _run(PCG(CommonSolverArgs(maxiter=100, tau=1e-10), precond=RightIC()).makeSolver(), A, b)
+    assert st.success() and np.linalg.norm(st.soln() - xex) <= 1e-8
+    assert abs(st.iters() - int(golden['kat/pcg_ic_dh10/iters'])) <= 1
+    st, h = _run(PCG(CommonSolverArgs(maxiter=100, tau=1e-12), precond=RightILUT()).makeSolver(), A, b)
+    assert st.success() and np.linalg.norm(st.soln() - xex) <= 1e-8
+    assert abs(st.iters() - int(golden['kat/pcg_ilut_dh10/iters'])) <= 1
+
+
+def test_prec_frozen_reuse(cuda):
+    """PCG keeps the formed preconditioner while frozen (PCGSolver.py:92-94)."""
+    from pysolvers_b200 import CommonSolverArgs
+    from pysolvers_b200.Linear import PCG, RightIC
+    A = _lap(12)
+    s = PCG(CommonSolverArgs(maxiter=100, tau=1e-8), precond=RightIC()).makeSolver()
+    _run(s, A, np.ones(A.shape[0]))
+    first = s.precond
+    s.freezePrec()
+    _run(s, A, np.ones(A.shape[0]))
+    assert s.precond is first
+    s.unfreezePrec()
+    _run(s, A, np.ones(A.shape[0]))
+    assert s.precond is not first
