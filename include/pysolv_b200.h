@@ -36,7 +36,8 @@ extern "C" {
 typedef struct psb_csr*   psb_csr_t;    /* CSR matrix + chosen SpMV kernel      */
 typedef struct psb_trsv*  psb_trsv_t;   /* level-analysed triangular factor     */
 typedef struct psb_prec*  psb_prec_t;   /* preconditioner: z = M^-1 r on device */
-typedef struct psb_comm*  psb_comm_t;   /* NCCL communicator + halo plan        */
+typedef struct psb_comm*  psb_comm_t;   /* NCCL communicator + side stream      */
+typedef struct psb_dist*  psb_dist_t;   /* row-partitioned matrix + halo plan   */
 
 /* ------------------------------------------------------------------ misc -- */
 int         psb_version(void);
@@ -182,6 +183,37 @@ int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, double* d_x
                     void* d_work, int64_t work_bytes, int32_t maxiter, double tau,
                     int32_t fail_on_maxiter, int32_t orth, double* d_hist,
                     psb_solve_result* result, void* stream);
+
+/* ------------------------------------------------- multi-GPU (one rank per GPU) -- */
+/* The reference has no distributed code; contract: SURVEY.md section 8e.  NCCL is
+ * taken from the libnccl.so.2 already loaded in the process (torch's). */
+int psb_nccl_unique_id(void* h_id128);                 /* rank 0; 128-byte HOST buffer  */
+int psb_comm_create(const void* h_id128, int32_t rank, int32_t nranks, psb_comm_t* out);
+int psb_comm_destroy(psb_comm_t comm);
+int psb_comm_allreduce_sum(psb_comm_t comm, double* d_buf, int64_t count, void* stream);
+
+/* Plan for this rank's row block.  A_local: n_loc x (n_loc + n_halo) CSR with local column
+ * numbering (owned columns first, halo columns after, in sorted-global order).  Rows
+ * [r0, r1) reference no halo column (r0, r1 multiples of 4) and are multiplied while the
+ * halo is in flight.  Peer i: send `send_cnt[i]` entries to rank peer_rank[i] -- either
+ * the contiguous slice starting at local offset send_off[i] (d_send_idx == NULL or
+ * d_send_idx[i] == NULL) or gathered through the device index list d_send_idx[i] -- and
+ * receive recv_cnt[i] entries into halo positions [recv_off[i], recv_off[i]+recv_cnt[i]). */
+int psb_dist_create(psb_comm_t comm, psb_csr_t A_local, int64_t n_loc, int64_t n_halo,
+                    int64_t r0, int64_t r1, int32_t n_peers, const int32_t* h_peer_rank,
+                    const int64_t* h_send_off, const int64_t* h_send_cnt,
+                    const int32_t* const* d_send_idx, const int64_t* h_recv_off,
+                    const int64_t* h_recv_cnt, psb_dist_t* out);
+int psb_dist_destroy(psb_dist_t D);
+/* y_loc = A_loc [x_loc | halo]; d_x_ext has n_loc + n_halo entries, the halo part is
+ * filled by the exchange (NCCL send/recv on a side stream, overlapped with interior rows). */
+int psb_dist_spmv(psb_dist_t D, double* d_x_ext, double* d_y, void* stream);
+int64_t psb_dist_pcg_workspace_bytes(int64_t n_loc, int64_t n_halo);
+/* Un-preconditioned PCG on the row-partitioned system; same loop, result codes and history
+ * as psb_pcg_solve, with p.Ap and r.r all-reduced (2 NCCL all-reduces per iteration). */
+int psb_dist_pcg_solve(psb_dist_t D, const double* d_b_loc, double* d_x_loc, void* d_work,
+                       int64_t work_bytes, int32_t maxiter, double tau, int32_t fail_on_maxiter,
+                       double* d_hist, psb_solve_result* result, void* stream);
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,17 @@ SIGNATURES = {
     'psb_gmres_workspace_bytes': (_i64, [_i64, _i32]),
     'psb_gmres_solve': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _dbl, _i32, _i32, _vp,
                                   C.POINTER(SolveResult), _vp]),
+    'psb_nccl_unique_id': (C.c_int, [_vp]),
+    'psb_comm_create': (C.c_int, [_vp, _i32, _i32, C.POINTER(_vp)]),
+    'psb_comm_destroy': (C.c_int, [_vp]),
+    'psb_comm_allreduce_sum': (C.c_int, [_vp, _vp, _i64, _vp]),
+    'psb_dist_create': (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  C.POINTER(_vp)]),
+    'psb_dist_destroy': (C.c_int, [_vp]),
+    'psb_dist_spmv': (C.c_int, [_vp, _vp, _vp, _vp]),
+    'psb_dist_pcg_workspace_bytes': (_i64, [_i64, _i64]),
+    'psb_dist_pcg_solve': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _dbl, _i32, _vp,
+                                     C.POINTER(SolveResult), _vp]),
 }
 
 _lib = None

@@ -1,0 +1,488 @@
+// Row-partitioned PCG across the GPUs of one NVSwitch box: one process per GPU.
+//
+// The reference has no distributed code; this is the
+// multi-GPU contract of SURVEY.md section 8e.  Each rank owns a contiguous block of rows
+// (local CSR with columns renumbered: owned first, then halo columns in sorted-global
+// order) and the matching slices of x, r, p.  Per iteration the only traffic is
+//   * the SpMV halo: p's boundary entries to the neighbouring ranks (ncclSend/ncclRecv
+//     grouped, on a side stream), overlapped with the SpMV of the interior rows -- rows
+//     that touch halo columns run after the halo has landed;
+//   * two scalar all-reduces (p.Ap; r.r), issued on the compute stream between the
+//     kernels that produce and consume them.
+// Vector updates are local.  Every rank takes identical decisions (they all see the same
+// all-reduced scalars), and the host loops poll their state snapshots at the same logical
+// points, so all ranks enqueue the same sequence of collectives.
+//
+// NCCL is resolved at run time from the libnccl.so.2 torch has already loaded (dlopen), so
+// the single-GPU path has no NCCL dependency.
+#include "prec.cuh"
+#include "spmv.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+namespace psb {
+
+// ---------------------------------------------------------------------------
+// NCCL entry points, looked up once
+// ---------------------------------------------------------------------------
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.ok) return PSB_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { set_error("NCCL: cannot load libnccl.so.2 (%s)", dlerror()); return PSB_ERR_NCCL; }
+  g_nccl.handle = h;
+#define PSB_SYM(field, name)                                                      \
+  g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, name));        \
+  if (!g_nccl.field) { set_error("NCCL: missing symbol %s", name); return PSB_ERR_NCCL; }
+  PSB_SYM(GetUniqueId, "ncclGetUniqueId");
+  PSB_SYM(CommInitRank, "ncclCommInitRank");
+  PSB_SYM(CommDestroy, "ncclCommDestroy");
+  PSB_SYM(AllReduce, "ncclAllReduce");
+  PSB_SYM(Send, "ncclSend");
+  PSB_SYM(Recv, "ncclRecv");
+  PSB_SYM(GroupStart, "ncclGroupStart");
+  PSB_SYM(GroupEnd, "ncclGroupEnd");
+  PSB_SYM(GetErrorString, "ncclGetErrorString");
+#undef PSB_SYM
+  g_nccl.ok = true;
+  return PSB_OK;
+}
+
+#define PSB_NCCL(expr)                                                           \
+  do {                                                                           \
+    ncclResult_t _r = (expr);                                                    \
+    if (_r != ncclSuccess) {                                                     \
+      psb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,               \
+                     psb::g_nccl.GetErrorString(_r));                            \
+      return PSB_ERR_NCCL;                                                       \
+    }                                                                            \
+  } while (0)
+
+}  // namespace psb
+
+struct psb_comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_halo = nullptr;
+};
+
+struct psb_dist {
+  psb_comm* comm = nullptr;
+  psb_csr* A = nullptr;           // local block: n_loc rows, n_loc + n_halo columns
+  int64_t n_loc = 0, n_halo = 0;
+  int64_t r0 = 0, r1 = 0;         // rows [r0, r1) touch no halo column
+  struct Peer { int rank; int64_t send_off, send_cnt, recv_off, recv_cnt; int32_t* d_send_idx; double* d_send_buf; };
+  std::vector<Peer> peers;
+};
+
+namespace psb {
+
+struct DistState {
+  double udr[2];
+  double loc[4];       // this rank's partial sums: [0..2] p.Ap parts (low boundary, interior,
+                       // high boundary; an absent part stays 0), [3] r.r / b.b
+  double red[4];       // the same, summed over ranks
+  double norm_b, norm_r, tau;
+  int k, maxiter, done, status, k_final, fail_on_maxiter, n_hist, pad;
+};
+
+__device__ __forceinline__ double2 ld2d(const double* p) {
+  double2 v;
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+__global__ void __launch_bounds__(kBlock)
+dist_gather_kernel(const double* __restrict__ v, const int32_t* __restrict__ idx, int64_t cnt,
+                   double* __restrict__ out, const int* d_skip) {
+  if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * kBlock)
+    out[i] = v[idx[i]];
+}
+
+// r = b, x = 0, p = b (local slices), local b.b -> red[3]
+__global__ void __launch_bounds__(kBlock)
+dist_init_kernel(DistState* st, int64_t n, const double* __restrict__ b, double* __restrict__ x,
+                 double* __restrict__ r, double* __restrict__ p, ReduceBuf rb) {
+  __shared__ double scratch[kWarps];
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    const double v = b[i];
+    r[i] = v; x[i] = 0.0; p[i] = v;
+    acc += v * v;
+  }
+  double t = block_sum(acc, scratch);
+  if (threadIdx.x == 0) rb.partials[blockIdx.x] = t;
+  if (last_block(rb.ticket)) {
+    double s = sum_partials(rb.partials, gridDim.x, scratch);
+    if (threadIdx.x == 0) st->loc[3] = s;
+  }
+}
+
+// after the all-reduce of b.b
+__global__ void dist_init_finish_kernel(DistState* st) {
+  if (threadIdx.x != 0) return;
+  const double bb = st->red[3];
+  const double nb = sqrt(bb);
+  st->norm_b = nb;
+  st->udr[0] = bb;
+  if (nb == 0.0) { st->done = 1; st->status = PSB_TRIVIAL; st->k_final = 0; st->norm_r = 0.0; }
+}
+
+// K2: x += alpha p ; r -= alpha Ap ; local r.r -> red[3].  `it` is the iteration index.
+__global__ void __launch_bounds__(kBlock)
+dist_update_kernel(DistState* st, int64_t n, int it, double* __restrict__ x, const double* __restrict__ p,
+                   double* __restrict__ r, const double* __restrict__ Ap, ReduceBuf rb) {
+  __shared__ double scratch[kWarps];
+  if (ld_cg(&st->done) != 0) return;
+  const double pAp = (ld_cg(&st->red[0]) + ld_cg(&st->red[1])) + ld_cg(&st->red[2]);
+  if (pAp == 0.0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st->status = PSB_BREAKDOWN_PAP; st->k_final = it; st->done = 1; }
+    return;
+  }
+  const double alpha = ld_cg(&st->udr[it & 1]) / pAp;
+  double acc = 0.0;
+  const int64_t n2 = n >> 1;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n2; i += (int64_t)gridDim.x * kBlock) {
+    double2 x0 = ld2d(x + 2 * i), p0 = ld2d(p + 2 * i), r0 = ld2d(r + 2 * i), a0 = ld_stream2(Ap + 2 * i);
+    x0.x = x0.x + alpha * p0.x; x0.y = x0.y + alpha * p0.y;
+    r0.x = r0.x - alpha * a0.x; r0.y = r0.y - alpha * a0.y;
+    st_stream2(x + 2 * i, x0); st_stream2(r + 2 * i, r0);
+    acc += r0.x * r0.x; acc += r0.y * r0.y;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t e = n - 1;
+    const double xv = x[e] + alpha * p[e], rv = r[e] - alpha * Ap[e];
+    x[e] = xv; r[e] = rv;
+    acc += rv * rv;
+  }
+  double t = block_sum(acc, scratch);
+  if (threadIdx.x == 0) rb.partials[blockIdx.x] = t;
+  if (last_block(rb.ticket)) {
+    double s = sum_partials(rb.partials, gridDim.x, scratch);
+    if (threadIdx.x == 0) st->loc[3] = s;
+  }
+}
+
+// K3 (after the all-reduce of r.r): convergence test, beta, p = r + beta p.  Every CTA
+// takes the decision from the same scalars; CTA 0 records it.
+__global__ void __launch_bounds__(kBlock)
+dist_direction_kernel(DistState* st, int64_t n, int it, const double* __restrict__ r,
+                      double* __restrict__ p, double* __restrict__ hist) {
+  if (ld_cg(&st->done) != 0) return;
+  const double rr = ld_cg(&st->red[3]);
+  const double nr = sqrt(rr);
+  const double tau = st->tau, nb = st->norm_b;
+  const int maxiter = st->maxiter;
+  const bool conv = (nr <= tau * nb) || (!st->fail_on_maxiter && it == maxiter - 1);
+  const bool last = (it + 1 >= maxiter);
+  const double rr_old = ld_cg(&st->udr[it & 1]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st->norm_r = nr;
+    hist[it] = nr;
+    st->n_hist = it + 1;
+    if (conv) { st->status = PSB_CONVERGED; st->k_final = it; st->done = 1; }
+    else {
+      st->udr[(it + 1) & 1] = rr;
+      st->k = it + 1;
+      if (last) { st->status = PSB_MAXITER; st->k_final = it; st->done = 1; }
+    }
+  }
+  if (conv || last) return;
+  const double beta = rr / rr_old;
+  const int64_t n2 = n >> 1;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n2; i += (int64_t)gridDim.x * kBlock) {
+    double2 z0 = ld_stream2(r + 2 * i), p0 = ld2d(p + 2 * i);
+    p0.x = z0.x + beta * p0.x; p0.y = z0.y + beta * p0.y;
+    st_stream2(p + 2 * i, p0);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = r[n - 1] + beta * p[n - 1];
+}
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct DistPoll {
+  DistState* pinned = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int init() {
+    if (pinned) return PSB_OK;
+    PSB_CUDA(cudaHostAlloc((void**)&pinned, 2 * sizeof(DistState), cudaHostAllocDefault));
+    PSB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    PSB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    return PSB_OK;
+  }
+};
+static thread_local DistPoll t_dpoll;
+
+// halo exchange of vector v (length n_loc + n_halo) on the comm stream
+static int halo_exchange(psb_dist* D, double* v, const int* d_skip) {
+  psb_comm* c = D->comm;
+  for (auto& pr : D->peers) {
+    if (pr.d_send_idx != nullptr && pr.send_cnt > 0) {
+      int grid = (int)std::min<int64_t>((pr.send_cnt + kBlock - 1) / kBlock, (int64_t)sm_count() * 4);
+      dist_gather_kernel<<<std::max(grid, 1), kBlock, 0, c->comm_stream>>>(v, pr.d_send_idx, pr.send_cnt,
+                                                                          pr.d_send_buf, d_skip);
+      PSB_LAUNCH_CHECK();
+    }
+  }
+  PSB_NCCL(g_nccl.GroupStart());
+  for (auto& pr : D->peers) {
+    if (pr.send_cnt > 0) {
+      const double* src = pr.d_send_idx ? pr.d_send_buf : v + pr.send_off;
+      PSB_NCCL(g_nccl.Send(src, (size_t)pr.send_cnt, ncclDouble, pr.rank, c->comm, c->comm_stream));
+    }
+    if (pr.recv_cnt > 0)
+      PSB_NCCL(g_nccl.Recv(v + D->n_loc + pr.recv_off, (size_t)pr.recv_cnt, ncclDouble, pr.rank, c->comm,
+                           c->comm_stream));
+  }
+  PSB_NCCL(g_nccl.GroupEnd());
+  return PSB_OK;
+}
+
+}  // namespace psb
+
+using namespace psb;
+
+extern "C" int psb_nccl_unique_id(void* h_id128) {
+  PSB_REQUIRE(h_id128 != nullptr, PSB_ERR_ARG, "psb_nccl_unique_id: NULL buffer");
+  int rc = load_nccl();
+  if (rc != PSB_OK) return rc;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+  ncclUniqueId id;
+  PSB_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(h_id128, &id, sizeof(id));
+  return PSB_OK;
+}
+
+extern "C" int psb_comm_create(const void* h_id128, int32_t rank, int32_t nranks, psb_comm_t* out) {
+  PSB_REQUIRE(h_id128 && out && nranks >= 1 && rank >= 0 && rank < nranks, PSB_ERR_ARG,
+              "psb_comm_create: bad argument");
+  int rc = load_nccl();
+  if (rc != PSB_OK) return rc;
+  psb_comm* c = new (std::nothrow) psb_comm();
+  PSB_REQUIRE(c != nullptr, PSB_ERR_ARG, "psb_comm_create: out of host memory");
+  c->rank = rank; c->nranks = nranks;
+  ncclUniqueId id;
+  memcpy(&id, h_id128, sizeof(id));
+  ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+  if (r != ncclSuccess) {
+    set_error("psb_comm_create: ncclCommInitRank -> %s", g_nccl.GetErrorString(r));
+    delete c;
+    return PSB_ERR_NCCL;
+  }
+  PSB_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  PSB_CUDA(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+  PSB_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+  *out = c;
+  return PSB_OK;
+}
+
+extern "C" int psb_comm_destroy(psb_comm_t c) {
+  if (!c) return PSB_OK;
+  if (c->comm) g_nccl.CommDestroy(c->comm);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+  if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+  delete c;
+  return PSB_OK;
+}
+
+// Sum `count` doubles in place over all ranks (stream-ordered).
+extern "C" int psb_comm_allreduce_sum(psb_comm_t c, double* d_buf, int64_t count, void* stream) {
+  PSB_REQUIRE(c && d_buf && count >= 0, PSB_ERR_ARG, "psb_comm_allreduce_sum: bad argument");
+  PSB_NCCL(g_nccl.AllReduce(d_buf, d_buf, (size_t)count, ncclDouble, ncclSum, c->comm, (cudaStream_t)stream));
+  return PSB_OK;
+}
+
+extern "C" int psb_dist_create(psb_comm_t comm, psb_csr_t A_local, int64_t n_loc, int64_t n_halo,
+                               int64_t r0, int64_t r1, int32_t n_peers, const int32_t* h_peer_rank,
+                               const int64_t* h_send_off, const int64_t* h_send_cnt,
+                               const int32_t* const* d_send_idx, const int64_t* h_recv_off,
+                               const int64_t* h_recv_cnt, psb_dist_t* out) {
+  PSB_REQUIRE(comm && A_local && out && n_loc >= 0 && n_halo >= 0 && n_peers >= 0, PSB_ERR_ARG,
+              "psb_dist_create: bad argument");
+  PSB_REQUIRE(A_local->n_rows == n_loc && A_local->n_cols == n_loc + n_halo, PSB_ERR_ARG,
+              "psb_dist_create: local matrix must be n_loc x (n_loc + n_halo)");
+  PSB_REQUIRE(0 <= r0 && r0 <= r1 && r1 <= n_loc && (r0 % 4) == 0 && (r1 % 4 == 0 || r1 == n_loc),
+              PSB_ERR_ARG, "psb_dist_create: interior range must be 4-aligned and inside [0, n_loc]");
+  psb_dist* D = new (std::nothrow) psb_dist();
+  PSB_REQUIRE(D != nullptr, PSB_ERR_ARG, "psb_dist_create: out of host memory");
+  D->comm = comm; D->A = A_local; D->n_loc = n_loc; D->n_halo = n_halo; D->r0 = r0; D->r1 = r1;
+  for (int i = 0; i < n_peers; ++i) {
+    psb_dist::Peer p;
+    p.rank = h_peer_rank[i];
+    p.send_off = h_send_off[i]; p.send_cnt = h_send_cnt[i];
+    p.recv_off = h_recv_off[i]; p.recv_cnt = h_recv_cnt[i];
+    p.d_send_idx = nullptr; p.d_send_buf = nullptr;
+    if (d_send_idx != nullptr && d_send_idx[i] != nullptr && p.send_cnt > 0) {
+      p.d_send_idx = const_cast<int32_t*>(d_send_idx[i]);
+      cudaError_t e = cudaMalloc((void**)&p.d_send_buf, (size_t)p.send_cnt * sizeof(double));
+      if (e != cudaSuccess) { set_error("psb_dist_create: %s", cudaGetErrorString(e)); delete D; return PSB_ERR_CUDA; }
+    }
+    D->peers.push_back(p);
+  }
+  *out = D;
+  return PSB_OK;
+}
+
+extern "C" int psb_dist_destroy(psb_dist_t D) {
+  if (!D) return PSB_OK;
+  for (auto& p : D->peers) if (p.d_send_buf) cudaFree(p.d_send_buf);
+  delete D;
+  return PSB_OK;
+}
+
+// y_loc = A_loc [x_loc | halo(x)]: exchanges the halo of d_x_ext (length n_loc + n_halo) and
+// multiplies; interior rows overlap the exchange.  d_dot3 (nullable): three partial x.y sums.
+static int dist_spmv(psb_dist* D, double* d_x_ext, double* d_y, double* d_dot3, const int* d_skip,
+                     cudaStream_t st) {
+  psb_comm* c = D->comm;
+  const bool comm_needed = !D->peers.empty();
+  if (comm_needed) {
+    PSB_CUDA(cudaEventRecord(c->ev_ready, st));
+    PSB_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
+    int rc = halo_exchange(D, d_x_ext, d_skip);
+    if (rc != PSB_OK) return rc;
+    PSB_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
+  }
+  const Epi epi = d_dot3 ? EPI_DOT : EPI_STORE;
+  EpiArgs ea;
+  int rc;
+  if (D->r1 > D->r0) {                                   // interior rows: no halo column
+    psb_csr v = csr_row_view(D->A, D->r0, D->r1);
+    if (d_dot3) ea.dot = d_dot3 + 1;
+    rc = spmv_launch(&v, epi, d_x_ext, d_y, ea, d_skip, st);
+    if (rc != PSB_OK) return rc;
+  }
+  if (comm_needed) PSB_CUDA(cudaStreamWaitEvent(st, c->ev_halo, 0));
+  if (D->r0 > 0) {
+    psb_csr v = csr_row_view(D->A, 0, D->r0);
+    if (d_dot3) ea.dot = d_dot3 + 0;
+    rc = spmv_launch(&v, epi, d_x_ext, d_y, ea, d_skip, st);
+    if (rc != PSB_OK) return rc;
+  }
+  if (D->r1 < D->n_loc) {
+    psb_csr v = csr_row_view(D->A, D->r1, D->n_loc);
+    if (d_dot3) ea.dot = d_dot3 + 2;
+    rc = spmv_launch(&v, epi, d_x_ext, d_y, ea, d_skip, st);
+    if (rc != PSB_OK) return rc;
+  }
+  return PSB_OK;
+}
+
+extern "C" int psb_dist_spmv(psb_dist_t D, double* d_x_ext, double* d_y, void* stream) {
+  PSB_REQUIRE(D && d_x_ext && d_y, PSB_ERR_ARG, "psb_dist_spmv: NULL argument");
+  return dist_spmv(D, d_x_ext, d_y, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int64_t psb_dist_pcg_workspace_bytes(int64_t n_loc, int64_t n_halo) {
+  if (n_loc < 0 || n_halo < 0) return PSB_ERR_ARG;
+  const int64_t hdr = 4096 + align_up((int64_t)sm_count() * 16 * sizeof(double), 256);
+  return hdr + 2 * align_up(n_loc * 8, 256) + align_up((n_loc + n_halo) * 8, 256);
+}
+
+extern "C" int psb_dist_pcg_solve(psb_dist_t D, const double* d_b, double* d_x, void* d_work,
+                                  int64_t work_bytes, int32_t maxiter, double tau,
+                                  int32_t fail_on_maxiter, double* d_hist, psb_solve_result* result,
+                                  void* stream) {
+  PSB_REQUIRE(D && d_b && d_x && d_work && d_hist && result, PSB_ERR_ARG, "psb_dist_pcg_solve: NULL argument");
+  PSB_REQUIRE(maxiter >= 1, PSB_ERR_ARG, "psb_dist_pcg_solve: maxiter must be >= 1");
+  const int64_t n = D->n_loc;
+  PSB_REQUIRE(work_bytes >= psb_dist_pcg_workspace_bytes(n, D->n_halo), PSB_ERR_ARG,
+              "psb_dist_pcg_solve: workspace too small");
+  PSB_REQUIRE(aligned16(d_b) && aligned16(d_x) && ((uintptr_t)d_work & 255u) == 0, PSB_ERR_ARG,
+              "psb_dist_pcg_solve: b, x must be 16-byte and work 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  psb_comm* c = D->comm;
+  int rc = t_dpoll.init();
+  if (rc != PSB_OK) return rc;
+
+  char* base = (char*)d_work;
+  DistState* S = (DistState*)base;
+  ReduceBuf rb;
+  rb.ticket = (unsigned int*)(base + 1024);
+  rb.partials = (double*)(base + 4096);
+  rb.max_grid = sm_count() * 16;
+  char* v = base + 4096 + align_up((int64_t)sm_count() * 16 * sizeof(double), 256);
+  const int64_t vec = align_up(n * 8, 256);
+  double* r = (double*)v;
+  double* Ap = (double*)(v + vec);
+  double* p = (double*)(v + 2 * vec);          // n_loc + n_halo
+
+  PSB_CUDA(cudaMemsetAsync(d_work, 0, 4096, st));
+  DistState h0;
+  memset(&h0, 0, sizeof(h0));
+  h0.tau = tau; h0.maxiter = maxiter; h0.fail_on_maxiter = fail_on_maxiter;
+  PSB_CUDA(cudaMemcpyAsync(S, &h0, sizeof(h0), cudaMemcpyHostToDevice, st));
+  PSB_CUDA(cudaStreamSynchronize(st));
+
+  const int grid = stream_grid(std::max<int64_t>(n, 1), rb.max_grid);
+  dist_init_kernel<<<grid, kBlock, 0, st>>>(S, n, d_b, d_x, r, p, rb);
+  PSB_LAUNCH_CHECK();
+  PSB_NCCL(g_nccl.AllReduce(&S->loc[3], &S->red[3], 1, ncclDouble, ncclSum, c->comm, st));
+  dist_init_finish_kernel<<<1, 32, 0, st>>>(S);
+  PSB_LAUNCH_CHECK();
+
+  const int chunk = 16;
+  int enq = 0, slot = 0;
+  bool pending[2] = {false, false};
+  bool finished = false;
+  while (!finished) {
+    const int todo = std::min(chunk, maxiter - enq);
+    for (int i = 0; i < todo; ++i) {
+      const int it = enq + i;
+      rc = dist_spmv(D, p, Ap, &S->loc[0], &S->done, st);
+      if (rc != PSB_OK) return rc;
+      PSB_NCCL(g_nccl.AllReduce(&S->loc[0], &S->red[0], 3, ncclDouble, ncclSum, c->comm, st));
+      dist_update_kernel<<<grid, kBlock, 0, st>>>(S, n, it, d_x, p, r, Ap, rb);
+      PSB_LAUNCH_CHECK();
+      PSB_NCCL(g_nccl.AllReduce(&S->loc[3], &S->red[3], 1, ncclDouble, ncclSum, c->comm, st));
+      dist_direction_kernel<<<grid, kBlock, 0, st>>>(S, n, it, r, p, d_hist);
+      PSB_LAUNCH_CHECK();
+    }
+    enq += todo;
+    PSB_CUDA(cudaMemcpyAsync(&t_dpoll.pinned[slot], S, sizeof(DistState), cudaMemcpyDeviceToHost, st));
+    PSB_CUDA(cudaEventRecord(t_dpoll.ev[slot], st));
+    pending[slot] = true;
+    const int prev = slot ^ 1;
+    if (pending[prev]) {            // same logical point on every rank -> same decision
+      PSB_CUDA(cudaEventSynchronize(t_dpoll.ev[prev]));
+      pending[prev] = false;
+      if (t_dpoll.pinned[prev].done) finished = true;
+    }
+    if (enq >= maxiter) finished = true;
+    slot ^= 1;
+  }
+  PSB_CUDA(cudaStreamSynchronize(st));
+  PSB_CUDA(cudaStreamSynchronize(c->comm_stream));
+  DistState hs;
+  PSB_CUDA(cudaMemcpy(&hs, S, sizeof(hs), cudaMemcpyDeviceToHost));
+  if (!hs.done) {
+    set_error("psb_dist_pcg_solve: device loop ended without a terminal state (k=%d)", hs.k);
+    return PSB_ERR_CUDA;
+  }
+  result->status = hs.status; result->k = hs.k_final; result->n_hist = hs.n_hist; result->lucky = 0;
+  result->norm_r = hs.norm_r; result->norm_b = hs.norm_b; result->norm_r_rec = hs.norm_r;
+  return PSB_OK;
+}

@@ -184,7 +184,7 @@ spmv_stream_kernel(const psb_csr A, const double* __restrict__ x, double* __rest
         const int a = rp[lr] - s, b = rp[lr + 1] - s;
         double sum = 0.0;
         for (int k = a; k < b; ++k) sum += prod[k];
-        epilogue<EPI>(row0 + lr, sum, x, y, ea, acc);
+        epilogue<EPI>(A.row_off + row0 + lr, sum, x, y, ea, acc);
       }
     }
     __syncthreads();
@@ -352,7 +352,7 @@ spmv_bulk_kernel(const psb_csr A, const double* __restrict__ x, double* __restri
           sum += sv[k + 3 - offv] * x3;
         }
         for (; k < b; ++k) sum += sv[k - offv] * __ldg(x + sc[k - offc]);
-        epilogue<EPI>(row0 + lr, sum, x, y, ea, acc);
+        epilogue<EPI>(A.row_off + row0 + lr, sum, x, y, ea, acc);
       }
     }
     __syncthreads();                                   // stage st may be refilled now
@@ -384,7 +384,7 @@ spmv_vector_kernel(const psb_csr A, const double* __restrict__ x, double* __rest
     }
 #pragma unroll
     for (int o = W / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o, W);
-    if (row < A.n_rows && lane == 0) epilogue<EPI>(row, sum, x, y, ea, acc);
+    if (row < A.n_rows && lane == 0) epilogue<EPI>(A.row_off + row, sum, x, y, ea, acc);
   }
   finish_dot<EPI>(acc, A, ea, scratch);
 }
@@ -395,17 +395,20 @@ spmv_vector_kernel(const psb_csr A, const double* __restrict__ x, double* __rest
 struct LaunchCfg { int grid; size_t smem; };
 
 template <typename K>
-static int occupancy_grid(K kernel, size_t smem, int64_t work_items, int max_grid, int* grid_out) {
+static int occupancy_per_sm(K kernel, size_t smem, int* per_sm_out) {
   if (smem > 48 * 1024)
     PSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem));
-  if (per_sm < 1) per_sm = 1;
+  *per_sm_out = per_sm < 1 ? 1 : per_sm;
+  return PSB_OK;
+}
+
+static inline int grid_for(int per_sm, int64_t work_items, int max_grid) {
   int64_t g = (int64_t)per_sm * sm_count();
   g = std::min<int64_t>(g, work_items);
   g = std::min<int64_t>(g, max_grid);
-  *grid_out = (int)std::max<int64_t>(g, 1);
-  return PSB_OK;
+  return (int)std::max<int64_t>(g, 1);
 }
 
 template <int EPI, int RPT, bool VEC>
@@ -414,17 +417,16 @@ static int launch_stream(const psb_csr* A, const double* x, double* y, const Epi
   constexpr int R = kBlock * RPT;
   const int cap = (A->max_tile_nnz[RPT - 1] + 1) & ~1;   // keep rp[] 8-byte aligned
   const size_t smem = (size_t)cap * sizeof(double) + (size_t)(R + 1) * sizeof(int);
-  static thread_local int cached_grid = 0;
+  static thread_local int per_sm = 0;
   static thread_local size_t cached_smem = 0;
-  static thread_local int64_t cached_tiles = -1;
   const int64_t tiles = (A->n_rows + R - 1) / R;
-  if (cached_grid == 0 || cached_smem != smem || cached_tiles != tiles) {
-    int g = 0;
-    int rc = occupancy_grid(spmv_stream_kernel<EPI, RPT, VEC>, smem, tiles, A->max_grid, &g);
+  if (per_sm == 0 || cached_smem != smem) {
+    int rc = occupancy_per_sm(spmv_stream_kernel<EPI, RPT, VEC>, smem, &per_sm);
     if (rc != PSB_OK) return rc;
-    cached_grid = g; cached_smem = smem; cached_tiles = tiles;
+    cached_smem = smem;
   }
-  spmv_stream_kernel<EPI, RPT, VEC><<<cached_grid, kBlock, smem, st>>>(*A, x, y, ea, d_skip, cap);
+  spmv_stream_kernel<EPI, RPT, VEC><<<grid_for(per_sm, tiles, A->max_grid), kBlock, smem, st>>>(
+      *A, x, y, ea, d_skip, cap);
   PSB_LAUNCH_CHECK();
   return PSB_OK;
 }
@@ -444,17 +446,16 @@ static int launch_bulk(const psb_csr* A, const double* x, double* y, const EpiAr
   int cap_v, cap_c;
   size_t smem;
   bulk_caps(A, RPT, &cap_v, &cap_c, &smem);
-  static thread_local int cached_grid = 0;
+  static thread_local int per_sm = 0;
   static thread_local size_t cached_smem = 0;
-  static thread_local int64_t cached_tiles = -1;
   const int64_t tiles = (A->n_rows + R - 1) / R;
-  if (cached_grid == 0 || cached_smem != smem || cached_tiles != tiles) {
-    int g = 0;
-    int rc = occupancy_grid(spmv_bulk_kernel<EPI, RPT>, smem, tiles, A->max_grid, &g);
+  if (per_sm == 0 || cached_smem != smem) {
+    int rc = occupancy_per_sm(spmv_bulk_kernel<EPI, RPT>, smem, &per_sm);
     if (rc != PSB_OK) return rc;
-    cached_grid = g; cached_smem = smem; cached_tiles = tiles;
+    cached_smem = smem;
   }
-  spmv_bulk_kernel<EPI, RPT><<<cached_grid, kBlock, smem, st>>>(*A, x, y, ea, d_skip, cap_v, cap_c);
+  spmv_bulk_kernel<EPI, RPT><<<grid_for(per_sm, tiles, A->max_grid), kBlock, smem, st>>>(
+      *A, x, y, ea, d_skip, cap_v, cap_c);
   PSB_LAUNCH_CHECK();
   return PSB_OK;
 }
@@ -463,16 +464,13 @@ template <int EPI, int W>
 static int launch_vector(const psb_csr* A, const double* x, double* y, const EpiArgs& ea,
                          const int* d_skip, cudaStream_t st) {
   constexpr int ROWS = kBlock / W;
-  static thread_local int cached_grid = 0;
-  static thread_local int64_t cached_groups = -1;
+  static thread_local int per_sm = 0;
   const int64_t groups = (A->n_rows + ROWS - 1) / ROWS;
-  if (cached_grid == 0 || cached_groups != groups) {
-    int g = 0;
-    int rc = occupancy_grid(spmv_vector_kernel<EPI, W>, 0, groups, A->max_grid, &g);
+  if (per_sm == 0) {
+    int rc = occupancy_per_sm(spmv_vector_kernel<EPI, W>, 0, &per_sm);
     if (rc != PSB_OK) return rc;
-    cached_grid = g; cached_groups = groups;
   }
-  spmv_vector_kernel<EPI, W><<<cached_grid, kBlock, 0, st>>>(*A, x, y, ea, d_skip);
+  spmv_vector_kernel<EPI, W><<<grid_for(per_sm, groups, A->max_grid), kBlock, 0, st>>>(*A, x, y, ea, d_skip);
   PSB_LAUNCH_CHECK();
   return PSB_OK;
 }
@@ -499,6 +497,14 @@ static int launch_epi(const psb_csr* A, const double* x, double* y, const EpiArg
     case 16: return launch_vector<EPI, 16>(A, x, y, ea, d_skip, st);
     default: return launch_vector<EPI, 32>(A, x, y, ea, d_skip, st);
   }
+}
+
+psb_csr csr_row_view(const psb_csr* A, int64_t r0, int64_t r1) {
+  psb_csr v = *A;
+  v.rowptr = A->rowptr + r0;
+  v.n_rows = r1 - r0;
+  v.row_off = A->row_off + r0;
+  return v;
 }
 
 int spmv_launch(const psb_csr* A, Epi epi, const double* x, double* y, const EpiArgs& ea,
@@ -556,7 +562,7 @@ extern "C" int psb_csr_create(int64_t n_rows, int64_t n_cols, int64_t nnz,
   cudaStream_t st = (cudaStream_t)stream;
   psb_csr* A = new (std::nothrow) psb_csr();
   PSB_REQUIRE(A != nullptr, PSB_ERR_ARG, "psb_csr_create: out of host memory");
-  A->n_rows = n_rows; A->n_cols = n_cols; A->nnz = nnz;
+  A->n_rows = n_rows; A->n_cols = n_cols; A->nnz = nnz; A->row_off = 0;
   A->rowptr = d_rowptr; A->colind = d_colind; A->vals = d_vals;
   A->vec_loads = aligned16(d_colind) && aligned16(d_vals);
   A->max_grid = sm_count() * 16;

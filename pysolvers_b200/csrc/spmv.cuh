@@ -4,6 +4,7 @@
 
 struct psb_csr {
   int64_t n_rows, n_cols, nnz;
+  int64_t row_off;      // row-range views: vectors are indexed at row_off + row (rowptr is pre-offset)
   const int*    rowptr;
   const int*    colind;
   const double* vals;
@@ -40,5 +41,10 @@ struct EpiArgs {
 // when *d_skip != 0 (solver loops keep launching after convergence).
 int spmv_launch(const psb_csr* A, Epi epi, const double* x, double* y,
                 const EpiArgs& ea, const int* d_skip, cudaStream_t stream);
+
+// View of rows [r0, r1) of A (r0 a multiple of 4 keeps the bulk copies aligned).  Shares
+// the parent's arrays and reduction scratch; y, f, dinv and x[row] stay indexed by the
+// parent's row numbers.
+psb_csr csr_row_view(const psb_csr* A, int64_t r0, int64_t r1);
 
 }  // namespace psb

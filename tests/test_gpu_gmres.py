@@ -62,7 +62,10 @@ def test_gmres_unpreconditioned_mgs_and_left_noop(cuda, golden, lev):
     k = min(len(hist), len(g))
     # un-preconditioned MGS amplifies rounding (CGS2 vs MGS differ by 1e-6
     # on DH-8): same order as the reference -> 1e-8; CGS2 is held to iteration count only
-    assert rel_err(hist[:k], g[:k]) < 1e-8
+    # the last step of a small system exhausts the Krylov space: its residual
+    # (~1e-11 ||b||) is rounding noise in the reference too -- compare above 1e-10 ||b||
+    sel = g[:k] > 1e-10 * np.linalg.norm(b)
+    assert rel_err(hist[:k][sel], g[:k][sel]) < 1e-8
     st2, hist2 = _run(GMRES(CommonSolverArgs(maxiter=100, tau=1e-8), orth='cgs2').makeSolver(), A, b)
     assert st2.success() and abs(st2.iters() - st.iters()) <= 1
     gx = golden['gmres/dh%d/x' % lev]
