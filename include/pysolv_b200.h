@@ -184,6 +184,28 @@ int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, double* d_x
                     int32_t fail_on_maxiter, int32_t orth, double* d_hist,
                     psb_solve_result* result, void* stream);
 
+/* -------------------------------------------------------- AMG V-cycle -- */
+#define PSB_SMOOTH_JACOBI 0   /* x += omega D^-1 (f - A x), ClassicSmoothers.py:10-16 (omega=1) */
+#define PSB_SMOOTH_GS     1   /* x += triu(A)^-1 (f - A x), ClassicSmoothers.py:28-36          */
+
+/* Solve phase of the smoothed-aggregation V-cycle on a hierarchy built on the host
+ * (reference setup) and already uploaded: A[l] level matrices (0 = coarsest), P[l]
+ * level l -> l+1, R[l] level l+1 -> l (whatever MLHierarchy.update/downdate return).
+ * d_dinv[l] (Jacobi) / gsU[l] (Gauss-Seidel: psb_trsv of triu(A[l])) for l >= 1.
+ * `coarse`: exact LU of A[0] as a psb_ilu preconditioner (factored once on the host).
+ * The handle is a preconditioner: psb_prec_apply runs n_iters V-cycles from x0 = b with
+ * the early exit ||r|| < tau ||b|| (AMGPreconditioner.py:39-51, VCycleSolver.py:68-91).
+ * All handles passed in stay owned by the caller. */
+int psb_amg_create(int32_t n_levels, const psb_csr_t* A, const psb_csr_t* P,
+                   const psb_csr_t* R, const double* const* d_dinv,
+                   const psb_trsv_t* gsU, psb_prec_t coarse, int32_t smoother,
+                   double omega, int32_t nu_pre, int32_t nu_post, int32_t n_iters,
+                   double tau, psb_prec_t* out);
+/* AMGVCycleSolver.solve (VCycleSolver.py:52-95): up to maxiter cycles, d_hist[k] =
+ * ||b - A x_k||; status PSB_CONVERGED / PSB_MAXITER / PSB_TRIVIAL.  Synchronises. */
+int psb_amg_solve(psb_prec_t amg, const double* d_b, double* d_x, int32_t maxiter,
+                  double tau, double* d_hist, psb_solve_result* result, void* stream);
+
 /* ------------------------------------------------- multi-GPU (one rank per GPU) -- */
 /* The reference has no distributed code; contract: SURVEY.md section 8e.  NCCL is
  * taken from the libnccl.so.2 already loaded in the process (torch's). */

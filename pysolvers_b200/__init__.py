@@ -7,3 +7,4 @@ hand-written sm_100a CUDA kernels behind the C ABI of include/pysolv_b200.h.
 """
 from .core import CommonSolverArgs, SolveStatus  # noqa: F401
 from . import Linear  # noqa: F401
+from . import Nonlinear  # noqa: F401

@@ -15,6 +15,7 @@ PSB_OK = 0
 # status codes of psb_solve_result.status (include/pysolv_b200.h)
 CONVERGED, MAXITER, BREAKDOWN_UR, BREAKDOWN_PAP, TRIVIAL, GMRES_FALSE_CONV = range(6)
 ORTH_CGS2, ORTH_MGS = 1, 2
+SMOOTH_JACOBI, SMOOTH_GS = 0, 1
 SPMV_STREAM, SPMV_VECTOR, SPMV_STREAM_LSU, SPMV_TILE512 = 1, 2, 3, 16
 
 
@@ -58,6 +59,9 @@ SIGNATURES = {
     'psb_ilu_create': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     'psb_prec_apply': (C.c_int, [_vp, _vp, _vp, _vp]),
     'psb_prec_destroy': (C.c_int, [_vp]),
+    'psb_amg_create': (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dbl, _i32, _i32, _i32, _dbl,
+                                 C.POINTER(_vp)]),
+    'psb_amg_solve': (C.c_int, [_vp, _vp, _vp, _i32, _dbl, _vp, C.POINTER(SolveResult), _vp]),
     'psb_pcg_workspace_bytes': (_i64, [_i64, C.c_int]),
     'psb_pcg_solve': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _dbl, _i32, _vp,
                                 C.POINTER(SolveResult), _vp]),

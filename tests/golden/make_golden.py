@@ -204,6 +204,28 @@ def main():
             put('%s/pcg_amg_%s' % (tag, sm_name), st, h)
             print('%s pcg+amg(%s): iters=%d' % (tag, sm_name, st.iters()))
 
+    # hierarchies of irregular FE matrices (weak connections -> filtered-matrix lumping,
+    # phase-2 tie breaking) and of a Bratu Jacobian
+    extra = [('amg/dh7_L2', sp.coo_matrix(mmread(os.path.join(REF, 'TestMatrices', 'DH-Matrix-7.mtx'))).tocsr(), 2),
+             ('amg/dh9_L3', sp.coo_matrix(mmread(os.path.join(REF, 'TestMatrices', 'DH-Matrix-9.mtx'))).tocsr(), 3)]
+    fb = quiet(FDBratu2D, m=20)
+    extra.append(('amg/bratuJ_m20_L2', fb.evalJ(np.linspace(0.5, 2.0, 400)), 2))
+    rng = np.random.default_rng(5)
+    W = sp.random(300, 300, density=0.02, random_state=rng)
+    W = (W + W.T).tocsr()
+    W.data = -np.abs(W.data) * rng.choice([1.0, 0.01], size=W.nnz)   # strong and weak couplings
+    Wd = sp.diags(np.asarray(np.abs(W).sum(axis=1)).ravel() + 0.1)
+    extra.append(('amg/rand300_L2', (W + Wd).tocsr(), 2))
+    for tag, A, nlev in extra:
+        mlh = quiet(SmoothedAggregationMLHierarchy, A, numLevels=nlev)
+        csr_put(tag + '/Afine', A)
+        for k in range(nlev):
+            csr_put('%s/A%d' % (tag, k), mlh.matrix(k))
+        for k in range(nlev - 1):
+            csr_put('%s/P%d' % (tag, k), mlh.update(k))
+            csr_put('%s/R%d' % (tag, k), mlh.downdate(k))
+        print(tag, [mlh.matrix(k).shape[0] for k in range(nlev)])
+
     # ---------------- config 5 (small): Newton + PCG + AMG on Bratu -------------
     for m in (16, 32):
         for sm_name, sm in (('gs', GaussSeidelSmoother), ('djac', DampedJacobi)):

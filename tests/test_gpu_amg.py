@@ -1,0 +1,129 @@
+"""AMG V-cycle solve phase on the B200 against what the reference itself
+produced (tests/golden): V-cycle residual histories for the Gauss-Seidel,
+undamped-Jacobi and damped-Jacobi smoothers, preconditioner applications,
+PCG + AMG histories, and the Newton / Bratu driver (configuration 5, small)."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(solver, A, b):
+    hist = []
+    solver.reportIter = lambda k, nr, nb: hist.append(nr)
+    with contextlib.redirect_stdout(io.StringIO()):
+        st = solver.solve(A, b)
+    return st, np.asarray(hist)
+
+
+def _lap(m):
+    from pysolvers_b200.problems import fd_laplacian_2d
+    return -fd_laplacian_2d(0.0, 1.0, m)
+
+
+def _smoother(name):
+    from pysolvers_b200.Linear import GaussSeidelSmoother, JacobiSmoother, DampedJacobiSmoother
+    return {'gs': GaussSeidelSmoother, 'jac': JacobiSmoother, 'djac': DampedJacobiSmoother}[name]
+
+
+@pytest.mark.parametrize('m,nlev', [(16, 2), (32, 2), (32, 3)])
+@pytest.mark.parametrize('sm', ['gs', 'jac', 'djac'])
+def test_vcycle_history_and_apply_vs_reference_golden(cuda, golden, m, nlev, sm):
+    from pysolvers_b200 import CommonSolverArgs
+    from pysolvers_b200.Linear import AMGVCycle, AMG
+    A = _lap(m)
+    tag = 'amg/m%d_L%d' % (m, nlev)
+    s = AMGVCycle(CommonSolverArgs(maxiter=12, tau=1e-8, failOnMaxiter=False), numLevels=nlev,
+                  smoother=_smoother(sm)).makeSolver()
+    st, hist = _run(s, A, np.ones(A.shape[0]))
+    key = '%s/vcycle_%s' % (tag, sm)
+    g = golden[key + '/hist']
+    assert st.success() == bool(golden[key + '/success'])
+    assert st.iters() == int(golden[key + '/iters'])
+    assert len(hist) == len(g)
+    # undamped Jacobi diverges on this problem: growth amplifies rounding,
+    # so the diverging history is held to 1e-8; the convergent ones to 1e-10
+    tol = 1e-8 if sm == 'jac' else 1e-10
+    sel = g > 1e-13 * np.sqrt(A.shape[0])
+    assert rel_err(hist[sel], g[sel]) < tol
+    gx = golden[key + '/x']
+    assert np.linalg.norm(st.soln() - gx) <= 1e-8 * np.linalg.norm(gx)
+    with contextlib.redirect_stdout(io.StringIO()):
+        pre = AMG(numIters=5, numLevels=nlev, smoother=_smoother(sm)).form(A)
+        out = pre.apply(golden['%s/apply_%s_in' % (tag, sm)])
+    go = golden['%s/apply_%s_out' % (tag, sm)]
+    assert np.linalg.norm(out - go) <= (1e-7 if sm == 'jac' else 1e-10) * np.linalg.norm(go)
+
+
+@pytest.mark.parametrize('m,nlev', [(16, 2), (32, 2), (32, 3)])
+@pytest.mark.parametrize('sm', ['gs', 'djac'])
+def test_pcg_amg_history_vs_reference_golden(cuda, golden, m, nlev, sm):
+    from pysolvers_b200 import CommonSolverArgs
+    from pysolvers_b200.Linear import PCG, AMG
+    A = _lap(m)
+    key = 'amg/m%d_L%d/pcg_amg_%s' % (m, nlev, sm)
+    g = golden[key + '/hist']
+    s = PCG(CommonSolverArgs(maxiter=100, tau=1e-8),
+            precond=AMG(numIters=5, numLevels=nlev, smoother=_smoother(sm))).makeSolver()
+    st, hist = _run(s, A, np.ones(A.shape[0]))
+    assert st.success() == bool(golden[key + '/success'])
+    if st.success():
+        assert abs(st.iters() - int(golden[key + '/iters'])) <= 1
+        k = min(len(hist), len(g))
+        assert rel_err(hist[:k], g[:k]) < 1e-9
+        gx = golden[key + '/x']
+        assert np.linalg.norm(st.soln() - gx) <= 1e-8 * np.linalg.norm(gx)
+    else:
+        # the reference fails to converge here too (non-symmetric preconditioner: x0 = b);
+        # a stagnating history is chaotic in the last digits -- compare the first iterations
+        assert rel_err(hist[:5], g[:5]) < 1e-8
+
+
+def test_smoother_objects_plug_in_protocol(cuda):
+    """cls(A), .apply(f, x, nu) -> x  (ClassicSmoothers.py:6,10)."""
+    from oracle import multigrid as omg
+    from pysolvers_b200.Linear import GaussSeidelSmoother, JacobiSmoother, DampedJacobiSmoother
+    A = _lap(20)
+    rng = np.random.default_rng(0)
+    f, x = rng.random(A.shape[0]), rng.random(A.shape[0])
+    assert np.array_equal(JacobiSmoother(A).apply(f, x, 3), omg.Jacobi(A).apply(f, x, 3))
+    assert np.array_equal(DampedJacobiSmoother(A).apply(f, x, 2), omg.Jacobi(A, omega=2.0 / 3.0).apply(f, x, 2))
+    got, ref = GaussSeidelSmoother(A).apply(f, x, 2), omg.GaussSeidel(A).apply(f, x, 2)
+    assert np.linalg.norm(got - ref) <= 1e-13 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize('m', [16, 32])
+@pytest.mark.parametrize('sm', ['gs', 'djac'])
+def test_newton_bratu_vs_reference_golden(cuda, golden, m, sm):
+    """examples/FDBratu2D.py:36-48 with the hierarchy frozen after the first Jacobian."""
+    from pysolvers_b200 import CommonSolverArgs
+    from pysolvers_b200.Linear import PCG, AMG
+    from pysolvers_b200.Nonlinear import NewtonSolver
+    from pysolvers_b200.problems import FDBratu2D
+    func = FDBratu2D(m=m)
+    lin_iters = []
+    newton = NewtonSolver(control=CommonSolverArgs(tau=1.0e-12, maxiter=10),
+                          solver=PCG(control=CommonSolverArgs(), precond=AMG(numIters=5, smoother=_smoother(sm))),
+                          fixLinTol=False, minLinTol=1.0e-6, freezePrec=True)
+    inner = newton.solver
+    orig = inner.solve
+
+    def spy(J, rhs):
+        r = orig(J, rhs)
+        lin_iters.append(r.iters())
+        return r
+    inner.solve = spy
+    st, hist = _run(newton, func, func.initialU())
+    key = 'newton/bratu_m%d_%s' % (m, sm)
+    assert st.success() and st.iters() == int(golden[key + '/iters'])
+    assert lin_iters == golden[key + '/lin_iters'].tolist()
+    g = golden[key + '/hist']
+    sel = g > 1e-9 * g[0]          # below that the Newton residual is the linear solver's noise
+    assert rel_err(hist[sel], g[sel]) < 1e-6
+    gx = golden[key + '/x']
+    assert np.linalg.norm(st.soln() - gx) <= 1e-8 * np.linalg.norm(gx)
