@@ -103,7 +103,8 @@ def givens_apply(v, c, s, i):
     v[i + 1] = -s * a + c * bb
 
 
-def gmres(A, b, prec=None, maxiter=100, tau=1.0e-8, fail_on_maxiter=True):
+def gmres(A, b, prec=None, maxiter=100, tau=1.0e-8, fail_on_maxiter=True,
+          dot=np.dot):
     """Right-preconditioned, un-restarted MGS GMRES (GMRESSolver.py:55-180).
 
     The reference's exit at maxiter raises NameError (``norm_k`` undefined,
@@ -115,14 +116,15 @@ def gmres(A, b, prec=None, maxiter=100, tau=1.0e-8, fail_on_maxiter=True):
     assert n == nc and n == len(b)
     hist = []
 
-    norm_b = npla.norm(b)                                   # :66
+    norm = npla.norm if dot is np.dot else (lambda v: np.sqrt(dot(v, v)))
+    norm_b = norm(b)                                        # :66
     if norm_b == 0.0:
         return _result(True, 1, np.zeros_like(b), 0, hist)
 
     Q = np.zeros([n, maxiter + 1])                          # :77
     H = np.zeros([maxiter + 1, maxiter])                    # :80
     CS = np.zeros([maxiter, 2])                             # :83
-    beta = npla.norm(b)                                     # :90
+    beta = norm(b)                                          # :90
     Q[:, 0] = b / beta                                      # :91
     g = np.zeros(maxiter + 1)
     g[0] = 1.0
@@ -133,9 +135,9 @@ def gmres(A, b, prec=None, maxiter=100, tau=1.0e-8, fail_on_maxiter=True):
     for k in range(maxiter):                                # :104
         u = _matvec(A, apply_prec(Q[:, k]))                 # :107
         for j in range(k + 1):                              # :110-112 (MGS)
-            H[j, k] = np.dot(Q[:, j], u)
+            H[j, k] = dot(Q[:, j], u)
             u -= H[j, k] * Q[:, j]
-        H[k + 1, k] = npla.norm(u)                          # :115
+        H[k + 1, k] = norm(u)                               # :115
         col_norm = npla.norm(H[0:k + 1, k])                 # :121
         if abs(H[k + 1, k]) <= 1.0e-16 * col_norm:          # :122-123
             breakdown = True

@@ -68,3 +68,18 @@ def golden_csr(g, prefix):
     shape = tuple(int(v) for v in g[prefix + '/shape'])
     return sp.csr_matrix((g[prefix + '/data'], g[prefix + '/indices'],
                           g[prefix + '/indptr']), shape=shape)
+
+
+def assert_history_close(hist, want, A, x, rtol=1e-10, what=''):
+    """Residual norms agree to ``rtol`` relative down to the cancellation floor
+    of evaluating b - A x in fp64: an absolute 8 eps ||A||_inf ||x|| (below it
+    the reference's own digits are rounding noise)."""
+    import scipy.sparse as sp
+    hist, want = np.asarray(hist), np.asarray(want)
+    assert hist.shape == want.shape, (what, hist.shape, want.shape)
+    # NB: abs() of a scipy matrix sorts ITS indices in place (sum_duplicates) -- work on a
+    # copy: the stored column order is part of the reference's arithmetic
+    norm_a = float(abs(sp.csr_matrix(A, copy=True)).sum(axis=1).max())
+    floor = 8.0 * np.finfo(np.float64).eps * norm_a * float(np.linalg.norm(x))
+    bad = np.abs(hist - want) > rtol * np.abs(want) + floor
+    assert not bad.any(), (what, hist[bad], want[bad], floor)

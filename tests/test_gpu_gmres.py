@@ -60,12 +60,16 @@ def test_gmres_unpreconditioned_mgs_and_left_noop(cuda, golden, lev):
     st, hist = _run(GMRES(CommonSolverArgs(maxiter=100, tau=1e-8), orth='mgs').makeSolver(), A, b)
     assert st.success() and abs(st.iters() - int(golden['gmres/dh%d/iters' % lev])) <= 1
     k = min(len(hist), len(g))
-    # un-preconditioned MGS amplifies rounding (CGS2 vs MGS differ by 1e-6
-    # on DH-8): same order as the reference -> 1e-8; CGS2 is held to iteration count only
-    # the last step of a small system exhausts the Krylov space: its residual
-    # (~1e-11 ||b||) is rounding noise in the reference too -- compare above 1e-10 ||b||
-    sel = g[:k] > 1e-10 * np.linalg.norm(b)
-    assert rel_err(hist[:k][sel], g[:k][sel]) < 1e-8
+    # Un-preconditioned MGS Arnoldi on these FE matrices amplifies 1-ulp changes of the
+    # dot products.  The noise floor of THIS input is measured by running
+    # the oracle against itself with only the summation order of its dots changed; the GPU
+    # (same MGS order as the reference, own reduction tree) must stay within 10x of it.
+    alt = krylov.gmres(A, b, maxiter=100, tau=1e-8, dot=krylov.pairwise_dot)
+    ka = min(k, len(alt['hist']))
+    floor = np.maximum.accumulate(np.abs(alt['hist'][:ka] - g[:ka]) / g[:ka])
+    err = np.abs(hist[:ka] - g[:ka]) / g[:ka]
+    assert np.all(err <= np.maximum(1e-10, 10.0 * floor)), float(np.max(err))
+    assert rel_err(hist[:5], g[:5]) < 1e-10
     st2, hist2 = _run(GMRES(CommonSolverArgs(maxiter=100, tau=1e-8), orth='cgs2').makeSolver(), A, b)
     assert st2.success() and abs(st2.iters() - st.iters()) <= 1
     gx = golden['gmres/dh%d/x' % lev]

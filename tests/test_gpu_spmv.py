@@ -56,7 +56,7 @@ def test_spmv_matches_scipy(cuda, name):
             # STREAM sums each row in stored order from +0, no FMA: bit-identical
             assert np.array_equal(got, want), (name, kind)
         else:
-            scale = np.abs(A) @ np.abs(x) + 1e-300
+            scale = np.abs(A.copy()) @ np.abs(x) + 1e-300
             assert np.max(np.abs(got - want) / scale) < 1e-14, (name, kind)
 
 
