@@ -90,6 +90,51 @@ __device__ __forceinline__ int ld_stream_i(const int* p) {
 __device__ __forceinline__ double ld_cg(const double* p) { return __ldcg(p); }
 __device__ __forceinline__ int    ld_cg(const int* p)    { return __ldcg(p); }
 
+// L1-cached load on the coherent path (not .nc): for vectors a peer GPU or an earlier phase of
+// the same kernel may have written before this CTA first touches them
+__device__ __forceinline__ double ld_ca(const double* p) {
+  double v;
+  asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_vol(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_vol(double* p, double v) {
+  asm volatile("st.volatile.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_vol_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+constexpr int kPeerSpinLimit = 1 << 26;
+
+// Scalar exchange between GPUs over NVLink peer memory, NCCL-LL style: a double travels as two
+// 8-byte words, each carrying 32 data bits and the 32-bit epoch of the reduction it belongs
+// to.  8-byte stores are atomic, so a reader that sees the expected epoch in both words has the
+// whole value; epochs only grow, so slots never need to be reset.
+__device__ __forceinline__ void peer_push(unsigned long long* slot, double v, unsigned int epoch) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long tag = (unsigned long long)epoch << 32;
+  asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(slot), "l"(tag | (bits & 0xffffffffull)) : "memory");
+  asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(slot + 1), "l"(tag | (bits >> 32)) : "memory");
+}
+// returns false on time-out
+__device__ __forceinline__ bool peer_wait(const unsigned long long* slot, unsigned int epoch, double* out) {
+  int spins = 0;
+  for (;;) {
+    const unsigned long long w0 = ld_vol_u64(slot), w1 = ld_vol_u64(slot + 1);
+    if ((unsigned int)(w0 >> 32) == epoch && (unsigned int)(w1 >> 32) == epoch) {
+      *out = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+      return true;
+    }
+    if (++spins > kPeerSpinLimit) { *out = 0.0; return false; }
+  }
+}
+
 __device__ __forceinline__ void st_stream2(double* p, double2 v) {
   asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};"
                :: "l"(p), "d"(v.x), "d"(v.y) : "memory");

@@ -94,6 +94,18 @@ struct psb_dist {
   int64_t r0 = 0, r1 = 0;         // rows [r0, r1) touch no halo column
   struct Peer { int rank; int64_t send_off, send_cnt, recv_off, recv_cnt; int32_t* d_send_idx; double* d_send_buf; };
   std::vector<Peer> peers;
+  // ---- NVLink peer-memory mode (psb_dist_p2p_*) ------------------------------------------
+  bool p2p = false;
+  char* shm = nullptr;                 // this rank's exported region (cudaMalloc + IPC handle)
+  size_t shm_bytes = 0;
+  int64_t pbuf_off[2] = {0, 0};        // byte offsets of the two p buffers (n_loc + n_halo each)
+  std::vector<char*> peer_shm;         // [nranks] mapped base pointers (self = shm)
+  unsigned long long** d_slot_ptrs = nullptr;   // device [kRing][nranks]: my slot in rank q, ring e
+  int* d_error = nullptr;
+  unsigned int red_epoch = 1;          // next reduction epoch (host-assigned, same on all ranks)
+  unsigned long long halo_epoch = 1;   // epoch of the next p vector
+  struct Push { int64_t send_off, cnt; double* remote[2]; unsigned long long* remote_flag; };
+  std::vector<Push> pushes;            // contiguous halo pushes (one per receiving peer)
 };
 
 namespace psb {
@@ -218,6 +230,177 @@ dist_direction_kernel(DistState* st, int64_t n, int it, const double* __restrict
     st_stream2(p + 2 * i, p0);
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = r[n - 1] + beta * p[n - 1];
+}
+
+// ---------------------------------------------------------------------------------------
+// NVLink peer-memory mode: the collectives are fused into the compute kernels.
+//   * scalar all-reduce: the last CTA of the producing kernel stores its partial, epoch-tagged,
+//     into its slot in EVERY rank's memory (peer stores); the consuming kernel polls its local
+//     slots and adds them in rank order -- same bits on every rank, no collective launch;
+//   * halo: the kernel that writes p also stores the boundary slices straight into the
+//     neighbours' halo (ping-pong p buffers), then raises their flag; the boundary-row SpMV of
+//     the neighbour waits on that flag (spmv.cu wait_for_halo), interior rows never wait.
+// Layout of the exported region: [slots: kRing x 32 ranks x 2 words][flags: 32 x u64]
+// [p buffer 0][p buffer 1].
+// ---------------------------------------------------------------------------------------
+constexpr int kRing = 4;
+constexpr int kMaxRanks = 32;
+constexpr int kMaxPush = 4;
+constexpr int64_t kSlotsBytes = 4096;    // kRing * kMaxRanks * 16 B = 2048
+constexpr int64_t kFlagsBytes = 4096;
+
+struct P2PView {
+  const unsigned long long* my_slots;          // local: slot(e, q) at ((e % kRing) * kMaxRanks + q) * 2
+  unsigned long long* const* slot_ptrs;        // device [kRing * nranks]: my slot in rank q's memory
+  int nranks, my_rank;
+  int n_push;
+  int64_t push_off[kMaxPush], push_cnt[kMaxPush];
+  double* push_remote[kMaxPush];
+  unsigned long long* push_flag[kMaxPush];
+  int* error;
+};
+
+// all threads call; returns sum over ranks of the value pushed for `epoch`
+__device__ __forceinline__ double p2p_reduce(const P2PView& c, unsigned int epoch) {
+  __shared__ double s_sum;
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int q = 0; q < c.nranks; ++q) {
+      double v;
+      if (!peer_wait(c.my_slots + ((size_t)(epoch % kRing) * kMaxRanks + q) * 2, epoch, &v)) *c.error = 1;
+      s += v;
+    }
+    s_sum = s;
+  }
+  __syncthreads();
+  return s_sum;
+}
+
+__device__ __forceinline__ void p2p_push_scalar(const P2PView& c, unsigned int epoch, double v) {
+  for (int q = 0; q < c.nranks; ++q)
+    peer_push(c.slot_ptrs[(size_t)(epoch % kRing) * c.nranks + q], v, epoch);
+}
+
+// store p[i] into the halo of every neighbour whose slice contains i
+__device__ __forceinline__ void p2p_push_halo(const P2PView& c, int64_t i, double v) {
+#pragma unroll
+  for (int k = 0; k < kMaxPush; ++k)
+    if (k < c.n_push && i >= c.push_off[k] && i < c.push_off[k] + c.push_cnt[k])
+      c.push_remote[k][i - c.push_off[k]] = v;
+}
+
+// after every CTA has issued its halo stores: the last CTA raises the neighbours' flags
+__device__ __forceinline__ void p2p_raise_flags(const P2PView& c, unsigned int* ticket,
+                                                unsigned long long halo_epoch) {
+  __threadfence_system();
+  if (last_block(ticket)) {
+    if (threadIdx.x < c.n_push) {
+      __threadfence_system();
+      asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(c.push_flag[threadIdx.x]), "l"(halo_epoch) : "memory");
+    }
+  }
+}
+
+// r = b, x = 0, p = b (+ halo push), local b.b pushed for all-reduce
+__global__ void __launch_bounds__(kBlock)
+p2p_init_kernel(DistState* st, int64_t n, const double* __restrict__ b, double* __restrict__ x,
+                double* __restrict__ r, double* __restrict__ p, ReduceBuf rb, P2PView c,
+                unsigned int epoch, unsigned long long halo_epoch, unsigned int* ticket2) {
+  __shared__ double scratch[kWarps];
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    const double v = b[i];
+    r[i] = v; x[i] = 0.0; p[i] = v;
+    p2p_push_halo(c, i, v);
+    acc += v * v;
+  }
+  double t = block_sum(acc, scratch);
+  if (threadIdx.x == 0) rb.partials[blockIdx.x] = t;
+  if (last_block(rb.ticket)) {
+    double s = sum_partials(rb.partials, gridDim.x, scratch);
+    if (threadIdx.x == 0) { st->loc[3] = s; p2p_push_scalar(c, epoch, s); }
+  }
+  p2p_raise_flags(c, ticket2, halo_epoch);
+}
+
+__global__ void p2p_init_finish_kernel(DistState* st, P2PView c, unsigned int epoch) {
+  const double bb = p2p_reduce(c, epoch);
+  if (threadIdx.x != 0) return;
+  const double nb = sqrt(bb);
+  st->norm_b = nb;
+  st->udr[0] = bb;
+  if (nb == 0.0) { st->done = 1; st->status = PSB_TRIVIAL; st->k_final = 0; st->norm_r = 0.0; }
+}
+
+// K2: waits for the all-reduced p.Ap (epoch e_pap), updates x and r, pushes local r.r (e_rr)
+__global__ void __launch_bounds__(kBlock)
+p2p_update_kernel(DistState* st, int64_t n, int it, double* __restrict__ x, const double* __restrict__ p,
+                  double* __restrict__ r, const double* __restrict__ Ap, ReduceBuf rb, P2PView c,
+                  unsigned int e_pap, unsigned int e_rr) {
+  __shared__ double scratch[kWarps];
+  if (ld_cg(&st->done) != 0) return;
+  const double pAp = p2p_reduce(c, e_pap);
+  if (pAp == 0.0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st->status = PSB_BREAKDOWN_PAP; st->k_final = it; st->done = 1; }
+    return;
+  }
+  const double alpha = ld_cg(&st->udr[it & 1]) / pAp;
+  double acc = 0.0;
+  const int64_t n2 = n >> 1;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n2; i += (int64_t)gridDim.x * kBlock) {
+    double2 x0 = ld2d(x + 2 * i), p0 = ld2d(p + 2 * i), r0 = ld2d(r + 2 * i), a0 = ld_stream2(Ap + 2 * i);
+    x0.x = x0.x + alpha * p0.x; x0.y = x0.y + alpha * p0.y;
+    r0.x = r0.x - alpha * a0.x; r0.y = r0.y - alpha * a0.y;
+    st_stream2(x + 2 * i, x0); st_stream2(r + 2 * i, r0);
+    acc += r0.x * r0.x; acc += r0.y * r0.y;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t e = n - 1;
+    const double xv = x[e] + alpha * p[e], rv = r[e] - alpha * Ap[e];
+    x[e] = xv; r[e] = rv;
+    acc += rv * rv;
+  }
+  double t = block_sum(acc, scratch);
+  if (threadIdx.x == 0) rb.partials[blockIdx.x] = t;
+  if (last_block(rb.ticket)) {
+    double s = sum_partials(rb.partials, gridDim.x, scratch);
+    if (threadIdx.x == 0) { st->loc[3] = s; p2p_push_scalar(c, e_rr, s); }
+  }
+}
+
+// K3: waits for the all-reduced r.r, convergence test, p_new = r + beta p_old written to the
+// other p buffer AND to the neighbours' halos, then raises their flags.
+__global__ void __launch_bounds__(kBlock)
+p2p_direction_kernel(DistState* st, int64_t n, int it, const double* __restrict__ r,
+                     const double* __restrict__ p_old, double* __restrict__ p_new,
+                     double* __restrict__ hist, P2PView c, unsigned int e_rr,
+                     unsigned long long halo_epoch, unsigned int* ticket2) {
+  if (ld_cg(&st->done) != 0) return;
+  const double rr = p2p_reduce(c, e_rr);
+  const double nr = sqrt(rr);
+  const int maxiter = st->maxiter;
+  const bool conv = (nr <= st->tau * st->norm_b) || (!st->fail_on_maxiter && it == maxiter - 1);
+  const bool last = (it + 1 >= maxiter);
+  const double rr_old = ld_cg(&st->udr[it & 1]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st->norm_r = nr;
+    hist[it] = nr;
+    st->n_hist = it + 1;
+    if (conv) { st->status = PSB_CONVERGED; st->k_final = it; st->done = 1; }
+    else {
+      st->udr[(it + 1) & 1] = rr;
+      st->k = it + 1;
+      if (last) { st->status = PSB_MAXITER; st->k_final = it; st->done = 1; }
+    }
+  }
+  if (conv || last) return;
+  const double beta = rr / rr_old;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    const double v = r[i] + beta * p_old[i];
+    p_new[i] = v;
+    p2p_push_halo(c, i, v);
+  }
+  p2p_raise_flags(c, ticket2, halo_epoch);
 }
 
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
@@ -349,7 +532,72 @@ extern "C" int psb_dist_create(psb_comm_t comm, psb_csr_t A_local, int64_t n_loc
 extern "C" int psb_dist_destroy(psb_dist_t D) {
   if (!D) return PSB_OK;
   for (auto& p : D->peers) if (p.d_send_buf) cudaFree(p.d_send_buf);
+  for (size_t q = 0; q < D->peer_shm.size(); ++q)
+    if (D->peer_shm[q] && D->peer_shm[q] != D->shm) cudaIpcCloseMemHandle(D->peer_shm[q]);
+  if (D->shm) cudaFree(D->shm);
+  if (D->d_slot_ptrs) cudaFree(D->d_slot_ptrs);
+  if (D->d_error) cudaFree(D->d_error);
   delete D;
+  return PSB_OK;
+}
+
+// ---- NVLink peer-memory mode: export / map the shared regions ---------------------------------
+extern "C" int psb_dist_p2p_alloc(psb_dist_t D, void* h_handle64, int64_t layout[4]) {
+  PSB_REQUIRE(D && h_handle64 && layout, PSB_ERR_ARG, "psb_dist_p2p_alloc: NULL argument");
+  PSB_REQUIRE(D->comm->nranks <= kMaxRanks, PSB_ERR_UNSUPP, "psb_dist_p2p_alloc: too many ranks");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+  const int64_t vec = align_up((D->n_loc + D->n_halo) * 8, 256);
+  D->pbuf_off[0] = kSlotsBytes + kFlagsBytes;
+  D->pbuf_off[1] = D->pbuf_off[0] + vec;
+  D->shm_bytes = (size_t)(D->pbuf_off[1] + vec);
+  PSB_CUDA(cudaMalloc((void**)&D->shm, D->shm_bytes));
+  PSB_CUDA(cudaMemset(D->shm, 0, D->shm_bytes));
+  PSB_CUDA(cudaMalloc((void**)&D->d_error, sizeof(int)));
+  PSB_CUDA(cudaMemset(D->d_error, 0, sizeof(int)));
+  cudaIpcMemHandle_t h;
+  PSB_CUDA(cudaIpcGetMemHandle(&h, D->shm));
+  memcpy(h_handle64, &h, sizeof(h));
+  layout[0] = D->pbuf_off[0]; layout[1] = D->pbuf_off[1]; layout[2] = D->n_loc; layout[3] = D->n_halo;
+  return PSB_OK;
+}
+
+extern "C" int psb_dist_p2p_open(psb_dist_t D, const void* h_handles, int32_t n_push,
+                                 const int32_t* h_push_rank, const int64_t* h_send_off,
+                                 const int64_t* h_send_cnt, const int64_t* h_remote_off0,
+                                 const int64_t* h_remote_off1, const int32_t* h_remote_flag_index) {
+  PSB_REQUIRE(D && h_handles && D->shm, PSB_ERR_ARG, "psb_dist_p2p_open: call psb_dist_p2p_alloc first");
+  PSB_REQUIRE(n_push >= 0 && n_push <= kMaxPush, PSB_ERR_UNSUPP, "psb_dist_p2p_open: too many halo targets");
+  PSB_REQUIRE(D->A->kind == PSB_SPMV_STREAM, PSB_ERR_UNSUPP,
+              "psb_dist_p2p_open: the peer-memory mode needs the STREAM SpMV kernel");
+  const int nr = D->comm->nranks, me = D->comm->rank;
+  D->peer_shm.assign(nr, nullptr);
+  for (int q = 0; q < nr; ++q) {
+    if (q == me) { D->peer_shm[q] = D->shm; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)h_handles + (size_t)q * sizeof(h), sizeof(h));
+    void* ptr = nullptr;
+    PSB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    D->peer_shm[q] = (char*)ptr;
+  }
+  // my slot (ring e) in rank q's memory
+  std::vector<unsigned long long*> sp((size_t)kRing * nr);
+  for (int e = 0; e < kRing; ++e)
+    for (int q = 0; q < nr; ++q)
+      sp[(size_t)e * nr + q] = (unsigned long long*)D->peer_shm[q] + ((size_t)e * kMaxRanks + me) * 2;
+  PSB_CUDA(cudaMalloc((void**)&D->d_slot_ptrs, sp.size() * sizeof(void*)));
+  PSB_CUDA(cudaMemcpy(D->d_slot_ptrs, sp.data(), sp.size() * sizeof(void*), cudaMemcpyHostToDevice));
+  D->pushes.clear();
+  for (int i = 0; i < n_push; ++i) {
+    psb_dist::Push P;
+    const int q = h_push_rank[i];
+    PSB_REQUIRE(q >= 0 && q < nr && q != me, PSB_ERR_ARG, "psb_dist_p2p_open: bad push rank");
+    P.send_off = h_send_off[i]; P.cnt = h_send_cnt[i];
+    P.remote[0] = (double*)(D->peer_shm[q] + h_remote_off0[i]);
+    P.remote[1] = (double*)(D->peer_shm[q] + h_remote_off1[i]);
+    P.remote_flag = (unsigned long long*)(D->peer_shm[q] + kSlotsBytes) + h_remote_flag_index[i];
+    D->pushes.push_back(P);
+  }
+  D->p2p = true;
   return PSB_OK;
 }
 
@@ -402,11 +650,24 @@ extern "C" int64_t psb_dist_pcg_workspace_bytes(int64_t n_loc, int64_t n_halo) {
   return hdr + 2 * align_up(n_loc * 8, 256) + align_up((n_loc + n_halo) * 8, 256);
 }
 
+static int dist_pcg_p2p(psb_dist_t D, const double* d_b, double* d_x, void* d_work, int32_t maxiter,
+                        double tau, int32_t fail_on_maxiter, double* d_hist, psb_solve_result* result,
+                        cudaStream_t st);
+
 extern "C" int psb_dist_pcg_solve(psb_dist_t D, const double* d_b, double* d_x, void* d_work,
                                   int64_t work_bytes, int32_t maxiter, double tau,
                                   int32_t fail_on_maxiter, double* d_hist, psb_solve_result* result,
                                   void* stream) {
   PSB_REQUIRE(D && d_b && d_x && d_work && d_hist && result, PSB_ERR_ARG, "psb_dist_pcg_solve: NULL argument");
+  if (D->p2p) {
+    PSB_REQUIRE(maxiter >= 1, PSB_ERR_ARG, "psb_dist_pcg_solve: maxiter must be >= 1");
+    PSB_REQUIRE(work_bytes >= psb_dist_pcg_workspace_bytes(D->n_loc, D->n_halo), PSB_ERR_ARG,
+                "psb_dist_pcg_solve: workspace too small");
+    PSB_REQUIRE(aligned16(d_b) && aligned16(d_x) && ((uintptr_t)d_work & 255u) == 0, PSB_ERR_ARG,
+                "psb_dist_pcg_solve: b, x must be 16-byte and work 256-byte aligned");
+    return dist_pcg_p2p(D, d_b, d_x, d_work, maxiter, tau, fail_on_maxiter, d_hist, result,
+                        (cudaStream_t)stream);
+  }
   PSB_REQUIRE(maxiter >= 1, PSB_ERR_ARG, "psb_dist_pcg_solve: maxiter must be >= 1");
   const int64_t n = D->n_loc;
   PSB_REQUIRE(work_bytes >= psb_dist_pcg_workspace_bytes(n, D->n_halo), PSB_ERR_ARG,
@@ -478,6 +739,141 @@ extern "C" int psb_dist_pcg_solve(psb_dist_t D, const double* d_b, double* d_x, 
   PSB_CUDA(cudaStreamSynchronize(c->comm_stream));
   DistState hs;
   PSB_CUDA(cudaMemcpy(&hs, S, sizeof(hs), cudaMemcpyDeviceToHost));
+  if (!hs.done) {
+    set_error("psb_dist_pcg_solve: device loop ended without a terminal state (k=%d)", hs.k);
+    return PSB_ERR_CUDA;
+  }
+  result->status = hs.status; result->k = hs.k_final; result->n_hist = hs.n_hist; result->lucky = 0;
+  result->norm_r = hs.norm_r; result->norm_b = hs.norm_b; result->norm_r_rec = hs.norm_r;
+  return PSB_OK;
+}
+
+
+static int dist_pcg_p2p(psb_dist_t D, const double* d_b, double* d_x, void* d_work, int32_t maxiter,
+                        double tau, int32_t fail_on_maxiter, double* d_hist, psb_solve_result* result,
+                        cudaStream_t st) {
+  const int64_t n = D->n_loc;
+  int rc = t_dpoll.init();
+  if (rc != PSB_OK) return rc;
+  char* base = (char*)d_work;
+  DistState* S = (DistState*)base;
+  ReduceBuf rb;
+  rb.ticket = (unsigned int*)(base + 1024);
+  unsigned int* ticket2 = (unsigned int*)(base + 1024 + 64);
+  rb.partials = (double*)(base + 4096);
+  rb.max_grid = sm_count() * 16;
+  char* v = base + 4096 + align_up((int64_t)sm_count() * 16 * sizeof(double), 256);
+  const int64_t vec = align_up(n * 8, 256);
+  double* r = (double*)v;
+  double* Ap = (double*)(v + vec);
+  double* pbuf[2] = {(double*)(D->shm + D->pbuf_off[0]), (double*)(D->shm + D->pbuf_off[1])};
+
+  PSB_CUDA(cudaMemsetAsync(d_work, 0, 4096, st));
+  DistState h0;
+  memset(&h0, 0, sizeof(h0));
+  h0.tau = tau; h0.maxiter = maxiter; h0.fail_on_maxiter = fail_on_maxiter;
+  PSB_CUDA(cudaMemcpyAsync(S, &h0, sizeof(h0), cudaMemcpyHostToDevice, st));
+  PSB_CUDA(cudaStreamSynchronize(st));
+
+  P2PView c;
+  memset(&c, 0, sizeof(c));
+  c.my_slots = (const unsigned long long*)D->shm;
+  c.slot_ptrs = D->d_slot_ptrs;
+  c.nranks = D->comm->nranks; c.my_rank = D->comm->rank;
+  c.n_push = (int)D->pushes.size();
+  c.error = D->d_error;
+  for (int k = 0; k < c.n_push; ++k) {
+    c.push_off[k] = D->pushes[k].send_off; c.push_cnt[k] = D->pushes[k].cnt;
+    c.push_flag[k] = D->pushes[k].remote_flag;
+  }
+  auto view_for = [&](unsigned long long h) {
+    P2PView w = c;
+    for (int k = 0; k < w.n_push; ++k) w.push_remote[k] = D->pushes[k].remote[h & 1];
+    return w;
+  };
+  unsigned int e = D->red_epoch;
+  const unsigned long long h0e = D->halo_epoch;
+  const unsigned long long* my_flags = (const unsigned long long*)(D->shm + kSlotsBytes);
+  int n_wait = 0;
+  {
+    std::vector<int> owners;
+    for (auto& pr : D->peers) if (pr.recv_cnt > 0) owners.push_back(pr.rank);
+    n_wait = (int)owners.size();
+  }
+
+  const int grid = stream_grid(std::max<int64_t>(n, 1), rb.max_grid);
+  {
+    const unsigned int e_bb = e++;
+    p2p_init_kernel<<<grid, kBlock, 0, st>>>(S, n, d_b, d_x, r, pbuf[h0e & 1], rb, view_for(h0e), e_bb, h0e, ticket2);
+    PSB_LAUNCH_CHECK();
+    p2p_init_finish_kernel<<<1, 32, 0, st>>>(S, c, e_bb);
+    PSB_LAUNCH_CHECK();
+  }
+
+  // the three row ranges of the SpMV; the last one launched carries the peer push
+  struct Part { int64_t a, b; bool waits; };
+  std::vector<Part> parts;
+  if (D->r1 > D->r0) parts.push_back({D->r0, D->r1, false});
+  if (D->r0 > 0) parts.push_back({0, D->r0, true});
+  if (D->r1 < n) parts.push_back({D->r1, n, true});
+
+  const int chunk = 16;
+  int enq = 0, slot = 0;
+  bool pending[2] = {false, false};
+  bool finished = false;
+  while (!finished) {
+    const int todo = std::min(chunk, maxiter - enq);
+    for (int i = 0; i < todo; ++i) {
+      const int it = enq + i;
+      const unsigned long long h = h0e + (unsigned long long)it;
+      double* pcur = pbuf[h & 1];
+      double* pnext = pbuf[(h + 1) & 1];
+      const unsigned int e_pap = e++, e_rr = e++;
+      for (size_t k = 0; k < parts.size(); ++k) {
+        psb_csr vw = csr_row_view(D->A, parts[k].a, parts[k].b);
+        EpiArgs ea;
+        ea.dot = &S->loc[0];
+        ea.dot_accumulate = k > 0 ? 1 : 0;
+        ea.error_flag = D->d_error;
+        if (parts[k].waits && n_wait > 0) { ea.wait_flags = my_flags; ea.wait_n = n_wait; ea.wait_value = h; }
+        if (k + 1 == parts.size()) {
+          ea.push_slots = D->d_slot_ptrs + (size_t)(e_pap % kRing) * c.nranks;
+          ea.push_n = c.nranks;
+          ea.push_epoch = e_pap;
+        }
+        rc = spmv_launch(&vw, EPI_DOT, pcur, Ap, ea, &S->done, st);
+        if (rc != PSB_OK) return rc;
+      }
+      p2p_update_kernel<<<grid, kBlock, 0, st>>>(S, n, it, d_x, pcur, r, Ap, rb, c, e_pap, e_rr);
+      PSB_LAUNCH_CHECK();
+      p2p_direction_kernel<<<grid, kBlock, 0, st>>>(S, n, it, r, pcur, pnext, d_hist, view_for(h + 1), e_rr,
+                                                    h + 1, ticket2);
+      PSB_LAUNCH_CHECK();
+    }
+    enq += todo;
+    PSB_CUDA(cudaMemcpyAsync(&t_dpoll.pinned[slot], S, sizeof(DistState), cudaMemcpyDeviceToHost, st));
+    PSB_CUDA(cudaEventRecord(t_dpoll.ev[slot], st));
+    pending[slot] = true;
+    const int prev = slot ^ 1;
+    if (pending[prev]) {
+      PSB_CUDA(cudaEventSynchronize(t_dpoll.ev[prev]));
+      pending[prev] = false;
+      if (t_dpoll.pinned[prev].done) finished = true;
+    }
+    if (enq >= maxiter) finished = true;
+    slot ^= 1;
+  }
+  D->red_epoch = e;
+  D->halo_epoch = h0e + (unsigned long long)enq + 1;
+  PSB_CUDA(cudaStreamSynchronize(st));
+  DistState hs;
+  PSB_CUDA(cudaMemcpy(&hs, S, sizeof(hs), cudaMemcpyDeviceToHost));
+  int err = 0;
+  PSB_CUDA(cudaMemcpy(&err, D->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) {
+    set_error("psb_dist_pcg_solve: timed out waiting for a peer GPU (rank %d)", D->comm->rank);
+    return PSB_ERR_NCCL;
+  }
   if (!hs.done) {
     set_error("psb_dist_pcg_solve: device loop ended without a terminal state (k=%d)", hs.k);
     return PSB_ERR_CUDA;

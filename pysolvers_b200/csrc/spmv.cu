@@ -91,8 +91,27 @@ __device__ __forceinline__ void finish_dot(double acc, const psb_csr A, const Ep
   if (threadIdx.x == 0) A.partials[blockIdx.x] = t;
   if (last_block(A.ticket)) {
     double total = sum_partials(A.partials, gridDim.x, scratch);
-    if (threadIdx.x == 0) *ea.dot = total;
+    if (threadIdx.x == 0) {
+      if (ea.dot_accumulate) total = *ea.dot + total;
+      *ea.dot = total;
+      for (int q = 0; q < ea.push_n; ++q) peer_push(ea.push_slots[q], total, ea.push_epoch);   // NVLink
+    }
   }
+}
+
+// Multi-GPU: block until the neighbours have pushed this iteration's halo (dist.cu).
+__device__ __forceinline__ void wait_for_halo(const EpiArgs& ea) {
+  if (ea.wait_n == 0) return;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ea.wait_n; ++i) {
+      int spins = 0;
+      while (ld_vol_u64(ea.wait_flags + i) < ea.wait_value) {
+        if (++spins > kPeerSpinLimit) { if (ea.error_flag) *ea.error_flag = 1; break; }
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------
@@ -239,6 +258,7 @@ spmv_bulk_kernel(const psb_csr A, const double* __restrict__ x, double* __restri
   __shared__ __align__(8) uint64_t full[STAGES];
 
   if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
+  wait_for_halo(ea);
 
   const int tid = threadIdx.x;
   const size_t stage_bytes = (size_t)cap_v * 8 + (size_t)cap_c * 4 + (size_t)(R + 4) * 4;
@@ -345,13 +365,13 @@ spmv_bulk_kernel(const psb_csr A, const double* __restrict__ x, double* __restri
         int k = a;
         for (; k + 4 <= b; k += 4) {                   // 4 independent gathers in flight
           const int c0 = sc[k - offc], c1 = sc[k + 1 - offc], c2 = sc[k + 2 - offc], c3 = sc[k + 3 - offc];
-          const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+          const double x0 = ld_ca(x + c0), x1 = ld_ca(x + c1), x2 = ld_ca(x + c2), x3 = ld_ca(x + c3);
           sum += sv[k - offv] * x0;
           sum += sv[k + 1 - offv] * x1;
           sum += sv[k + 2 - offv] * x2;
           sum += sv[k + 3 - offv] * x3;
         }
-        for (; k < b; ++k) sum += sv[k - offv] * __ldg(x + sc[k - offc]);
+        for (; k < b; ++k) sum += sv[k - offv] * ld_ca(x + sc[k - offc]);
         epilogue<EPI>(A.row_off + row0 + lr, sum, x, y, ea, acc);
       }
     }

@@ -35,6 +35,18 @@ struct EpiArgs {
   const double* dinv  = nullptr;   // JACOBI
   double        omega = 1.0;       // JACOBI
   double*       dot   = nullptr;   // DOT: where the last CTA writes x . y
+  int dot_accumulate  = 0;         // DOT: add to *dot (row-range launches chained on one stream)
+  // ---- multi-GPU over NVLink peer memory (dist.cu) ------------------------------------
+  // once the dot is final, store it (epoch-tagged, see peer_push) into this rank's slot in
+  // every rank's memory
+  unsigned long long* const* push_slots = nullptr;   // device array [push_n] of peer addresses
+  int push_n = 0;
+  unsigned int push_epoch = 0;
+  // before touching x: wait until every wait_flags[i] >= wait_value (halo pushed by peers)
+  const unsigned long long* wait_flags = nullptr;
+  int wait_n = 0;
+  unsigned long long wait_value = 0;
+  int* error_flag = nullptr;       // set when a wait times out
 };
 
 // Enqueue one SpMV-shaped kernel.  `d_skip` (nullable): the kernel is a no-op

@@ -180,6 +180,57 @@ class DistCSR:
             peer_rank, send_off, send_cnt, idx_ptrs, recv_off, recv_cnt, C.byref(self._h)),
             'psb_dist_create')
 
+        self.p2p = False
+        if os.environ.get('PSB_DIST_MODE', 'p2p') != 'nccl' and comm.world > 1:
+            self._enable_p2p(gathered)
+
+    def _enable_p2p(self, all_recv):
+        """Map every rank's exported region (NVLink peer memory) so that the solve
+        can fuse the halo exchange and the scalar all-reduces into its kernels.
+        Needs contiguous send slices (true for slab partitions of banded
+        matrices); otherwise the NCCL path stays in force."""
+        import torch.distributed as dist
+        comm = self.comm
+        ok = all(np.array_equal(s, np.arange(s[0], s[0] + s.size, dtype=s.dtype))
+                 for s in self.send.values()) and len(self.send) <= 4 and comm.world <= 32 \
+            and self.A.info()['kind'] == nat.SPMV_STREAM
+        flags = [None] * comm.world
+        dist.all_gather_object(flags, bool(ok))
+        if not all(flags):
+            return
+        handle = (C.c_ubyte * 64)()
+        layout = (C.c_int64 * 4)()
+        nat.check(nat.lib().psb_dist_p2p_alloc(self._h, handle, layout), 'psb_dist_p2p_alloc')
+        info = [None] * comm.world
+        dist.all_gather_object(info, (bytes(handle), [int(v) for v in layout]))
+        handles = (C.c_ubyte * (64 * comm.world))()
+        for q, (hb, _) in enumerate(info):
+            handles[64 * q:64 * (q + 1)] = list(hb)
+        targets = sorted(self.send)
+        k = len(targets)
+        push_rank = (C.c_int32 * max(k, 1))()
+        send_off = (C.c_int64 * max(k, 1))()
+        send_cnt = (C.c_int64 * max(k, 1))()
+        roff0 = (C.c_int64 * max(k, 1))()
+        roff1 = (C.c_int64 * max(k, 1))()
+        fidx = (C.c_int32 * max(k, 1))()
+        for i, q in enumerate(targets):
+            s = self.send[q]
+            ids_q, owners_q = all_recv[q]
+            owners_q = np.asarray(owners_q)
+            first = int(np.flatnonzero(owners_q == comm.rank)[0])     # my slice inside q's halo
+            lay = info[q][1]
+            push_rank[i] = q
+            send_off[i] = int(s[0])
+            send_cnt[i] = int(s.size)
+            roff0[i] = lay[0] + 8 * (lay[2] + first)
+            roff1[i] = lay[1] + 8 * (lay[2] + first)
+            fidx[i] = int(np.flatnonzero(np.unique(owners_q) == comm.rank)[0])
+        nat.check(nat.lib().psb_dist_p2p_open(self._h, handles, k, push_rank, send_off, send_cnt,
+                                              roff0, roff1, fidx), 'psb_dist_p2p_open')
+        dist.barrier()
+        self.p2p = True
+
     @property
     def handle(self):
         return self._h

@@ -52,6 +52,10 @@ def main():
         with contextlib.redirect_stdout(io.StringIO()):
             st = solver.solve(D, b[lo:hi])
         ref = krylov.pcg(A, b, maxiter=maxiter, tau=tau)
+        with contextlib.redirect_stdout(io.StringIO()):
+            st_again = solver.solve(D, b[lo:hi])       # epochs / ping-pong buffers carry over
+        if st_again.iters() != st.iters() or not np.array_equal(st_again.soln(), st.soln()):
+            fails.append('%s: second solve differs from the first' % name)
         hist = np.asarray(hist)
         k = min(len(hist), len(ref['hist']))
         if name == 'dh12':
@@ -69,8 +73,8 @@ def main():
             if err > 1e-8:
                 fails.append('%s: solution rel err %.3e' % (name, err))
         if rank == 0:
-            print('%s: n=%d world=%d iters=%d (oracle %d) hist rel %.2e halo=%d r0=%d r1=%d'
-                  % (name, n, world, st.iters(), ref['iters'], rel, D.n_halo, D.r0, D.r1), flush=True)
+            print('%s: n=%d world=%d iters=%d (oracle %d) hist rel %.2e halo=%d r0=%d r1=%d p2p=%s'
+                  % (name, n, world, st.iters(), ref['iters'], rel, D.n_halo, D.r0, D.r1, D.p2p), flush=True)
         del D
     flag = torch.tensor([len(fails)], device='cuda')
     dist.all_reduce(flag)
