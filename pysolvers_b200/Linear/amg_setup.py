@@ -70,25 +70,32 @@ def build_aggregates(A, lvl=1, tol=None):
     has_diag[rows[rows == cols]] = True
     size = np.diff(s_ptr) + (~has_diag)
 
-    agg_of = np.full(n, -1, dtype=np.int64)
+    # isolated nodes first (SmoothedAggregation.py:72-76), then phase 1 (:84-89): a node whose
+    # whole strong neighbourhood is still free founds an aggregate.  Sequential by nature;
+    # plain Python containers keep the O(nnz) sweep at ~1 us per node.
+    agg_list = [-1] * n
     roots = []
-    # isolated nodes first (SmoothedAggregation.py:72-76)
-    for i in np.flatnonzero(size == 1):
-        agg_of[i] = len(roots)
+    for i in np.flatnonzero(size == 1).tolist():
+        agg_list[i] = len(roots)
         roots.append(i)
-    # phase 1 (:84-89): sequential by nature, O(nnz) total
-    free = agg_of < 0
+    ptr_l = s_ptr.tolist()
+    col_l = s_cols.tolist()
     for i in range(n):
-        if not free[i]:
+        if agg_list[i] >= 0:
             continue
-        nb = s_cols[s_ptr[i]:s_ptr[i + 1]]
-        if free[nb].all():
+        a, b = ptr_l[i], ptr_l[i + 1]
+        ok = True
+        for k in range(a, b):
+            if agg_list[col_l[k]] >= 0:
+                ok = False
+                break
+        if ok:
             j = len(roots)
-            agg_of[nb] = j
-            agg_of[i] = j
-            free[nb] = False
-            free[i] = False
+            for k in range(a, b):
+                agg_list[col_l[k]] = j
+            agg_list[i] = j
             roots.append(i)
+    agg_of = np.asarray(agg_list, dtype=np.int64)
     snapshot = agg_of.copy()
     n_agg = len(roots)
     # phase 2 (:104-127), all remaining nodes at once against the snapshot
@@ -173,9 +180,23 @@ def sa_coarsen(A, lvl=1):
     return P.tocsr(), agg_of
 
 
-def restriction_of(I_up, normalize=True):
-    """Transpose plus the reference's row normalisation, through the same scipy
-    calls (MLHierarchy.py:60-78) so that it tracks the installed scipy."""
+_NORMALIZE_IS_NOOP = None
+
+
+def _normalisation_is_noop():
+    """Does the reference's row "normalisation" (MLHierarchy.py:71-75) change anything under
+    the installed scipy?  Probed once with the very same calls on a 2 x 3 example: on scipy
+    1.18 ``row /= nrm`` on a ``lil.getrowview`` rebinds the view instead of mutating the
+    parent, i.e. it is a silent no-op."""
+    global _NORMALIZE_IS_NOOP
+    if _NORMALIZE_IS_NOOP is None:
+        probe = sp.csr_matrix(np.array([[1.0, 3.0, 0.0], [0.0, 2.0, 6.0]]))
+        _NORMALIZE_IS_NOOP = bool(np.array_equal(_restriction_literal(probe.T.tocsr(), True).toarray(),
+                                                 probe.toarray()))
+    return _NORMALIZE_IS_NOOP
+
+
+def _restriction_literal(I_up, normalize):
     I_down = I_up.transpose(copy=True).tolil()
     if normalize:
         with warnings.catch_warnings():
@@ -185,6 +206,16 @@ def restriction_of(I_up, normalize=True):
                 nrm = row.sum()
                 row /= nrm
     return I_down.tocsr()
+
+
+def restriction_of(I_up, normalize=True):
+    """Transpose plus the reference's row normalisation, through the same scipy calls
+    (MLHierarchy.py:60-78) so that it tracks the installed scipy.  When the probe shows the
+    normalisation loop to be a no-op (scipy 1.18) the O(rows) Python loop is skipped -- the
+    result is the same matrix."""
+    if normalize and _normalisation_is_noop():
+        normalize = False
+    return _restriction_literal(I_up, normalize)
 
 
 def build_hierarchy(A_fine, num_levels=2, normalize=True):

@@ -110,7 +110,7 @@ __device__ __forceinline__ unsigned long long ld_vol_u64(const unsigned long lon
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-constexpr int kPeerSpinLimit = 1 << 26;
+constexpr int kPeerSpinLimit = 1 << 24;   // ~5-10 s of polling before a wait is declared dead
 
 // Scalar exchange between GPUs over NVLink peer memory, NCCL-LL style: a double travels as two
 // 8-byte words, each carrying 32 data bits and the 32-bit epoch of the reduction it belongs

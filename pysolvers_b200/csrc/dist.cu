@@ -395,10 +395,19 @@ p2p_direction_kernel(DistState* st, int64_t n, int it, const double* __restrict_
   }
   if (conv || last) return;
   const double beta = rr / rr_old;
-  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
-    const double v = r[i] + beta * p_old[i];
-    p_new[i] = v;
-    p2p_push_halo(c, i, v);
+  const int64_t n2 = n >> 1;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n2; i += (int64_t)gridDim.x * kBlock) {
+    const double2 z0 = ld_stream2(r + 2 * i), p0 = ld_stream2(p_old + 2 * i);
+    double2 v;
+    v.x = z0.x + beta * p0.x; v.y = z0.y + beta * p0.y;
+    st_stream2(p_new + 2 * i, v);
+    p2p_push_halo(c, 2 * i, v.x);
+    p2p_push_halo(c, 2 * i + 1, v.y);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const double v = r[n - 1] + beta * p_old[n - 1];
+    p_new[n - 1] = v;
+    p2p_push_halo(c, n - 1, v);
   }
   p2p_raise_flags(c, ticket2, halo_epoch);
 }
@@ -817,6 +826,8 @@ static int dist_pcg_p2p(psb_dist_t D, const double* d_b, double* d_x, void* d_wo
   if (D->r0 > 0) parts.push_back({0, D->r0, true});
   if (D->r1 < n) parts.push_back({D->r1, n, true});
 
+  const bool one_launch = D->A->rpt == 1 && (D->r0 % 256) == 0 && ((D->r1 % 256) == 0 || D->r1 == n);
+
   const int chunk = 16;
   int enq = 0, slot = 0;
   bool pending[2] = {false, false};
@@ -829,20 +840,35 @@ static int dist_pcg_p2p(psb_dist_t D, const double* d_b, double* d_x, void* d_wo
       double* pcur = pbuf[h & 1];
       double* pnext = pbuf[(h + 1) & 1];
       const unsigned int e_pap = e++, e_rr = e++;
-      for (size_t k = 0; k < parts.size(); ++k) {
-        psb_csr vw = csr_row_view(D->A, parts[k].a, parts[k].b);
+      if (one_launch) {
+        // one SpMV launch: interior tiles first, a CTA waits for the halo flags only when it
+        // reaches its first boundary tile; the last CTA pushes p.Ap to every rank
         EpiArgs ea;
         ea.dot = &S->loc[0];
-        ea.dot_accumulate = k > 0 ? 1 : 0;
         ea.error_flag = D->d_error;
-        if (parts[k].waits && n_wait > 0) { ea.wait_flags = my_flags; ea.wait_n = n_wait; ea.wait_value = h; }
-        if (k + 1 == parts.size()) {
-          ea.push_slots = D->d_slot_ptrs + (size_t)(e_pap % kRing) * c.nranks;
-          ea.push_n = c.nranks;
-          ea.push_epoch = e_pap;
-        }
-        rc = spmv_launch(&vw, EPI_DOT, pcur, Ap, ea, &S->done, st);
+        if (n_wait > 0) { ea.wait_flags = my_flags; ea.wait_n = n_wait; ea.wait_value = h; }
+        ea.rot_t0 = D->r0 / 256; ea.rot_t1 = (D->r1 + 255) / 256;
+        ea.push_slots = D->d_slot_ptrs + (size_t)(e_pap % kRing) * c.nranks;
+        ea.push_n = c.nranks;
+        ea.push_epoch = e_pap;
+        rc = spmv_launch(D->A, EPI_DOT, pcur, Ap, ea, &S->done, st);
         if (rc != PSB_OK) return rc;
+      } else {
+        for (size_t k = 0; k < parts.size(); ++k) {
+          psb_csr vw = csr_row_view(D->A, parts[k].a, parts[k].b);
+          EpiArgs ea;
+          ea.dot = &S->loc[0];
+          ea.dot_accumulate = k > 0 ? 1 : 0;
+          ea.error_flag = D->d_error;
+          if (parts[k].waits && n_wait > 0) { ea.wait_flags = my_flags; ea.wait_n = n_wait; ea.wait_value = h; }
+          if (k + 1 == parts.size()) {
+            ea.push_slots = D->d_slot_ptrs + (size_t)(e_pap % kRing) * c.nranks;
+            ea.push_n = c.nranks;
+            ea.push_epoch = e_pap;
+          }
+          rc = spmv_launch(&vw, EPI_DOT, pcur, Ap, ea, &S->done, st);
+          if (rc != PSB_OK) return rc;
+        }
       }
       p2p_update_kernel<<<grid, kBlock, 0, st>>>(S, n, it, d_x, pcur, r, Ap, rb, c, e_pap, e_rr);
       PSB_LAUNCH_CHECK();

@@ -258,11 +258,16 @@ spmv_bulk_kernel(const psb_csr A, const double* __restrict__ x, double* __restri
   __shared__ __align__(8) uint64_t full[STAGES];
 
   if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
-  wait_for_halo(ea);
 
   const int tid = threadIdx.x;
   const size_t stage_bytes = (size_t)cap_v * 8 + (size_t)cap_c * 4 + (size_t)(R + 4) * 4;
   const int64_t n_tiles = (A.n_rows + R - 1) / R;
+  // logical -> physical tile: interior tiles [rot_t0, rot_t1) first (multi-GPU overlap)
+  const int64_t n_int = ea.rot_t1 - ea.rot_t0;
+  auto phys = [&](int64_t t) -> int64_t {
+    return t < n_int ? ea.rot_t0 + t : (t < ea.rot_t1 ? t - n_int : t);
+  };
+  bool waited = (ea.wait_n == 0);
   const int nnz_v_lim = (int)(A.nnz & ~(int64_t)1);          // bulk copies stop at the last
   const int nnz_c_lim = (int)(A.nnz & ~(int64_t)3);          // whole 16-byte chunk of each array
   const int rp_lim = (int)((A.n_rows + 1) & ~(int64_t)3);
@@ -283,8 +288,8 @@ spmv_bulk_kernel(const psb_csr A, const double* __restrict__ x, double* __restri
   __syncthreads();
 
   // producer (thread 0): stage tile `t` whose nonzero range is [s, e)
-  auto issue = [&](int64_t t, int st, int s, int e) {
-    const int64_t row0 = t * R;
+  auto issue = [&](int64_t lt, int st, int s, int e) {
+    const int64_t row0 = phys(lt) * R;
     const int nr = (int)min((int64_t)R, A.n_rows - row0);
     const int v0 = s & ~1, c0 = s & ~3;
     const int v1 = min((e + 1) & ~1, nnz_v_lim);
@@ -299,8 +304,8 @@ spmv_bulk_kernel(const psb_csr A, const double* __restrict__ x, double* __restri
     if (bc) bulk_g2s(stage_cols(st), A.colind + c0, bc, &full[st], pol);
     if (br) bulk_g2s(stage_rp(st), A.rowptr + row0, br, &full[st], pol);
   };
-  auto tile_bounds = [&](int64_t t, int& s, int& e) {
-    const int64_t row0 = t * R;
+  auto tile_bounds = [&](int64_t lt, int& s, int& e) {
+    const int64_t row0 = phys(lt) * R;
     s = ld_stream_i(A.rowptr + row0);
     e = ld_stream_i(A.rowptr + min(row0 + R, A.n_rows));
   };
@@ -326,8 +331,9 @@ spmv_bulk_kernel(const psb_csr A, const double* __restrict__ x, double* __restri
     }
     while (!mbar_try_wait(&full[st], (phase_bits >> st) & 1u)) {}
     phase_bits ^= (1u << st);
+    if (!waited && tile >= n_int) { wait_for_halo(ea); waited = true; }   // uniform per CTA
 
-    const int64_t row0 = tile * R;
+    const int64_t row0 = phys(tile) * R;
     const int nr = (int)min((int64_t)R, A.n_rows - row0);
     const double* sv = stage_vals(st);
     const int*    sc = stage_cols(st);

@@ -47,6 +47,9 @@ struct EpiArgs {
   int wait_n = 0;
   unsigned long long wait_value = 0;
   int* error_flag = nullptr;       // set when a wait times out
+  // tile order of the STREAM kernel: tiles [rot_t0, rot_t1) (rows without halo columns) are
+  // processed first, the wait above happens only when a CTA reaches the first other tile
+  long long rot_t0 = 0, rot_t1 = 0;
 };
 
 // Enqueue one SpMV-shaped kernel.  `d_skip` (nullable): the kernel is a no-op

@@ -1,0 +1,218 @@
+"""Measurements for the BASELINE.json configurations other than the bench.py headline
+(C1, C2, IC-PCG, C5) on one B200, with the oracle port timed on the host beside them.
+
+    python tools/config_bench.py [c1] [c2] [ic512] [ic1024] [c5_512] [c5_2048] > gpurun_out/configs.json
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import krylov, precond  # noqa: E402
+from pysolvers_b200 import CommonSolverArgs, _native as nat  # noqa: E402
+from pysolvers_b200.Linear import (PCG, GMRES, RightIC, RightILUT, AMG, DampedJacobiSmoother,  # noqa: E402
+                                   GaussSeidelSmoother)
+from pysolvers_b200.Nonlinear import NewtonSolver  # noqa: E402
+from pysolvers_b200.device import DeviceCSR, to_device, ptr, current_stream_ptr  # noqa: E402
+from pysolvers_b200.problems import fd_laplacian_2d, load_dh_matrix, FDBratu2D  # noqa: E402
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def run(solver, A, b):
+    hist = []
+    solver.reportIter = lambda k, nr, nb: hist.append(nr)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    st = quiet(solver.solve, A, b)
+    torch.cuda.synchronize()
+    return st, np.asarray(hist), time.perf_counter() - t0
+
+
+def time_gpu(fn, reps=10, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
+def c1():
+    A = -fd_laplacian_2d(0.0, 1.0, 256)
+    b = np.ones(A.shape[0])
+    s = PCG(CommonSolverArgs(maxiter=5000, tau=1e-8)).makeSolver()
+    run(s, A, b)
+    st, hist, dt = run(s, A, b)
+    t0 = time.perf_counter()
+    ref = krylov.pcg(A, b, maxiter=5000, tau=1e-8)
+    cpu = time.perf_counter() - t0
+    k = min(len(hist), len(ref['hist']))
+    return dict(config='C1: PCG, -FDLaplacian2D(0,1,256), b=1, tau=1e-8', iters=st.iters(), ref_iters=ref['iters'],
+                gpu_solve_s=dt, gpu_it_per_s=st.iters() / dt, cpu_s=cpu, cpu_it_per_s=ref['iters'] / cpu,
+                hist_max_rel_err=float(np.max(np.abs(hist[:k] - ref['hist'][:k]) / ref['hist'][:k])),
+                soln_rel_err=float(np.linalg.norm(st.soln() - ref['soln']) / np.linalg.norm(ref['soln'])))
+
+
+def c2():
+    out = []
+    for lev in (12, 15):
+        A = load_dh_matrix(lev)
+        b = A @ np.random.default_rng(2024).random(A.shape[0])
+        t0 = time.perf_counter()
+        pre = quiet(RightILUT().form, A)
+        setup = time.perf_counter() - t0
+        dev = pre.device_prec()
+        v = to_device(b)
+        z = torch.empty_like(v)
+        apply_s = time_gpu(lambda: dev.apply(v, z), reps=20)
+        infoL, infoU = pre._dL.info(), pre._dU.info()
+        s = GMRES(CommonSolverArgs(maxiter=30, tau=1e-8), precond=RightILUT()).makeSolver()
+        run(s, A, b)
+        st, hist, dt = run(s, A, b)
+        ilu = precond.ilut_factor(A)
+        t0 = time.perf_counter()
+        ref = krylov.gmres(A, b, prec=lambda x: precond.ilut_apply(ilu, x), maxiter=30, tau=1e-8)
+        cpu = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for _ in range(20):
+            precond.ilut_apply(ilu, b)
+        cpu_apply = (time.perf_counter() - t0) / 20
+        k = min(len(hist), len(ref['hist']))
+        out.append(dict(config='C2: GMRES(30)+RightILUT, DH-Matrix-%d (n=%d)' % (lev, A.shape[0]),
+                        iters=st.iters(), ref_iters=ref['iters'], ilut_setup_cpu_s=setup,
+                        gpu_solve_incl_setup_s=dt, gpu_ilut_apply_s=apply_s, cpu_ilut_apply_s=cpu_apply,
+                        levels_L=infoL['levels'], levels_U=infoU['levels'],
+                        us_per_level=1e6 * apply_s / (infoL['levels'] + infoU['levels']),
+                        cpu_solve_excl_setup_s=cpu,
+                        hist_max_rel_err=float(np.max(np.abs(hist[:k] - ref['hist'][:k]) / ref['hist'][:k]))))
+    return out
+
+
+def ic(m):
+    A = -fd_laplacian_2d(0.0, 1.0, m)
+    n = A.shape[0]
+    b = np.ones(n)
+    t0 = time.perf_counter()
+    pre = quiet(RightIC().form, A)
+    setup = time.perf_counter() - t0
+    dev = pre.device_prec()
+    v = to_device(b)
+    z = torch.empty_like(v)
+    apply_s = time_gpu(lambda: dev.apply(v, z), reps=5, warm=1)
+    iL, iLt = pre._dL.info(), pre._dLt.info()
+    t0 = time.perf_counter()
+    ref_z = precond.ic_apply(pre._L, pre._Lt, b)
+    cpu_apply = time.perf_counter() - t0
+    zz = z.cpu().numpy()
+    # solve with the already-formed preconditioner
+    s = PCG(CommonSolverArgs(maxiter=2000, tau=1e-8), precond=RightIC()).makeSolver()
+    s.precond = pre
+    s.freezePrec()
+    st, hist, dt = run(s, A, b)
+    bytes_ic = 12 * (iL['nnz_packed'] + iLt['nnz_packed']) + 2 * 24 * n
+    return dict(config='IC-PCG, -FDLaplacian2D(0,1,%d) (n=%d), RightIC() defaults' % (m, n),
+                ic_setup_cpu_s=setup, nnz_L=iL['nnz_off'] + n, levels_L=iL['levels'], levels_Lt=iLt['levels'],
+                gpu_ic_apply_s=apply_s, cpu_ic_apply_s=cpu_apply, apply_speedup=cpu_apply / apply_s,
+                us_per_level=1e6 * apply_s / (iL['levels'] + iLt['levels']),
+                ic_apply_algorithmic_GBps=bytes_ic / apply_s / 1e9,
+                apply_rel_err_vs_scipy=float(np.linalg.norm(zz - ref_z) / np.linalg.norm(ref_z)),
+                pcg_iters=st.iters(), pcg_success=st.success(), gpu_pcg_solve_s=dt,
+                est_cpu_pcg_solve_s=st.iters() * cpu_apply)
+
+
+def c5(m, gmres_too=False):
+    out = {}
+    func = FDBratu2D(m=m)
+    n = m * m
+    for name, sm in (('djac', DampedJacobiSmoother), ('gs', GaussSeidelSmoother)):
+        lin = []
+        newton = NewtonSolver(control=CommonSolverArgs(tau=1.0e-12, maxiter=10),
+                              solver=PCG(control=CommonSolverArgs(), precond=AMG(numIters=5, smoother=sm)),
+                              fixLinTol=False, minLinTol=1.0e-6, freezePrec=True)
+        inner = newton.solver
+        orig = inner.solve
+        t_lin = [0.0]
+
+        def spy(J, rhs, _o=orig):
+            t0 = time.perf_counter()
+            r = _o(J, rhs)
+            torch.cuda.synchronize()
+            t_lin[0] += time.perf_counter() - t0
+            lin.append(r.iters())
+            return r
+        inner.solve = spy
+        st, hist, dt = run(newton, func, func.initialU())
+        out['pcg_amg_' + name] = dict(newton_iters=st.iters(), success=st.success(), lin_iters=lin, total_s=dt,
+                                      linear_solves_s=t_lin[0], final_F=float(hist[-1]) if len(hist) else None)
+        if name == 'djac':
+            amg = inner.precond.device_amg()
+            v = to_device(np.ones(n))
+            z = torch.empty_like(v)
+            apply_s = time_gpu(lambda: amg.prec.apply(v, z), reps=5, warm=1)
+            out['amg_apply_5_vcycles_s'] = apply_s
+            dA = amg.A[-1]
+            dinv = amg.dinv[-1]
+            f = to_device(np.ones(n))
+            xa, xb = torch.zeros_like(f), torch.empty_like(f)
+            lib = nat.lib()
+            sweep_s = time_gpu(lambda: nat.check(lib.psb_jacobi_sweep(dA.handle, ptr(dinv), 2.0 / 3.0, ptr(f), ptr(xa),
+                                                                     ptr(xb), current_stream_ptr())), reps=20)
+            nnz = dA.nnz
+            out['jacobi_sweep_s'] = sweep_s
+            out['jacobi_sweep_GBps'] = (12 * nnz + 4 * (n + 1) + 32 * n) / sweep_s / 1e9
+            out['levels'] = [a.shape[0] for a in amg.A]
+    if gmres_too:
+        lin = []
+        newton = NewtonSolver(control=CommonSolverArgs(tau=1.0e-12, maxiter=10),
+                              solver=GMRES(control=CommonSolverArgs(maxiter=60),
+                                           precond=AMG(numIters=5, smoother=DampedJacobiSmoother)),
+                              fixLinTol=False, minLinTol=1.0e-6, freezePrec=True)
+        inner = newton.solver
+        orig = inner.solve
+
+        def spy2(J, rhs, _o=orig):
+            r = _o(J, rhs)
+            lin.append(r.iters())
+            return r
+        inner.solve = spy2
+        st, hist, dt = run(newton, func, func.initialU())
+        out['gmres_amg_djac'] = dict(newton_iters=st.iters(), success=st.success(), lin_iters=lin, total_s=dt)
+    out['config'] = 'C5: FDBratu2D(m=%d) Newton + Krylov + AMG(5 V-cycles, 2 levels)' % m
+    return out
+
+
+def main():
+    which = sys.argv[1:] or ['c1', 'c2', 'ic512', 'c5_512']
+    res = {}
+    for w in which:
+        t0 = time.perf_counter()
+        if w == 'c1':
+            res[w] = c1()
+        elif w == 'c2':
+            res[w] = c2()
+        elif w.startswith('ic'):
+            res[w] = ic(int(w[2:]))
+        elif w.startswith('c5_'):
+            res[w] = c5(int(w[3:]), gmres_too=True)
+        print('%s done in %.1f s' % (w, time.perf_counter() - t0), file=sys.stderr, flush=True)
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == '__main__':
+    main()
