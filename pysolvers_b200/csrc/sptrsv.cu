@@ -14,11 +14,16 @@
 //    level-major (ascending inside a level); the strictly triangular part is repacked in
 //    that order as SELL-32 (entry k of 32 consecutive items is contiguous) so every load of
 //    the solve is coalesced; the diagonal is split out.
-//  * solve: ONE persistent launch.  Warps claim 32 consecutive items with an atomic
-//    counter; each THREAD owns one row and accumulates b_i - sum L_ij x_j sequentially IN
-//    STORED COLUMN ORDER, dividing by the diagonal last (the reference's summation order,
-//    SURVEY.md section 7.3-2), so the dependency that arrives last -- the one nearest the
-//    diagonal -- is also the last operand and everything else is folded in beforehand.
+//  * solve: ONE persistent launch.  Warps claim work chunks with an atomic counter.  A chunk
+//    is either 32 consecutive SHORT rows (<= 32 off-diagonal entries): each THREAD owns one
+//    row and accumulates b_i - sum L_ij x_j sequentially IN STORED COLUMN ORDER, dividing by
+//    the diagonal last (the reference's summation order), so the
+//    dependency that arrives last -- the one nearest the diagonal -- is also the last operand
+//    and everything else is folded in beforehand; or ONE LONG row (exact LU factors of the
+//    AMG coarse level have rows of hundreds of entries) spread over the 32 lanes of the warp
+//    and combined with a shuffle tree.  Every lane keeps a window of 4 entries in registers:
+//    the 4 dependencies are polled with independent loads and consumed in order as far as
+//    they are ready, the next entries are fetched behind them.
 //    Readiness travels with the data: x is pre-filled with a NaN sentinel and a consumer
 //    polls x[j] (ld.volatile, L2) until it changes -- one L2 round trip per level on the
 //    critical path, no flags, no fences, no grid barrier.  The poll loop never blocks a
@@ -62,14 +67,25 @@ struct TrsvView {
   int64_t n;
   int n_groups;
   const int32_t* order;
+  const double* diag;
   const int64_t* grp_ptr;
+  const int32_t* grp_item;
+  const int32_t* grp_rows;
   const int32_t* cols;
   const double* vals;
-  const double* diag;
   unsigned int* counter;
   int* error;
   int unit_diag;
 };
+
+__device__ __forceinline__ double ld_relaxed(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed(double* p, double v) {
+  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
+}
 
 __global__ void __launch_bounds__(kBlock)
 trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
@@ -77,48 +93,84 @@ trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
                   const int32_t* __restrict__ out_map, const int* d_skip) {
   if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
   const int lane = threadIdx.x & 31;
+  const double kNotReady = __longlong_as_double((long long)kSentinelBits);
   for (;;) {
     unsigned int g = 0;
     if (lane == 0) g = atomicAdd(T.counter, 1u);
     g = __shfl_sync(0xffffffffu, g, 0);
     if (g >= (unsigned int)T.n_groups) return;
-    const int64_t q = (int64_t)g * 32 + lane;
-    const bool active = q < T.n;
+    const int64_t base = T.grp_ptr[g];
+    const int len = (int)((T.grp_ptr[g + 1] - base) >> 5);     // entries per lane
+    const int rows = T.grp_rows[g];                            // 0: one long row for the warp
+    const int item0 = T.grp_item[g];
+    const bool is_long = rows == 0;
+    const bool owner = is_long ? (lane == 0) : (lane < rows);  // lanes that own a row
     int row = 0;
     double acc = 0.0, d = 1.0;
-    const int64_t base = T.grp_ptr[g];
-    const int len = (int)((T.grp_ptr[g + 1] - base) >> 5);
-    if (active) {
+    if (owner) {
+      const int q = item0 + (is_long ? 0 : lane);
       row = T.order[q];
       acc = rhs_map ? rhs[rhs_map[row]] : rhs[row];
       d = T.diag[q];
     }
+    const int32_t* cp = T.cols + base + lane;
+    const double*  vp = T.vals + base + lane;
+    // window of 4 entries: (c0,v0) is the next one to consume
     int k = 0;
+    int c0 = -1, c1 = -1, c2 = -1, c3 = -1;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    if (len > 0) { c0 = cp[0];  v0 = vp[0]; }
+    if (len > 1) { c1 = cp[32]; v1 = vp[32]; }
+    if (len > 2) { c2 = cp[64]; v2 = vp[64]; }
+    if (len > 3) { c3 = cp[96]; v3 = vp[96]; }
     int spins = 0;
-    bool done = !active;
-    // prefetch the first entry
-    int c = -1;
-    double v = 0.0;
-    if (active && len > 0) { c = T.cols[base + lane]; v = T.vals[base + lane]; }
+    bool fed = !(c0 >= 0);            // all entries of this lane consumed (padding ends a lane's list)
+    bool done = false;
     while (!__all_sync(0xffffffffu, done)) {
-      if (!done) {
-        if (k < len && c >= 0) {
-          const double xv = ld_volatile(x + c);
-          if (is_ready(xv)) {
-            acc = acc - v * xv;                       // stored order, product rounded first
+      if (!fed) {
+        // poll the window with independent loads
+        double x0 = ld_relaxed(x + c0);
+        double x1 = c1 >= 0 ? ld_relaxed(x + c1) : kNotReady;
+        double x2 = c2 >= 0 ? ld_relaxed(x + c2) : kNotReady;
+        double x3 = c3 >= 0 ? ld_relaxed(x + c3) : kNotReady;
+        bool progressed = false;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          if (c0 >= 0 && is_ready(x0)) {
+            acc = acc - v0 * x0;                      // stored order, product rounded first
             ++k;
-            if (k < len) {
-              c = T.cols[base + (int64_t)k * 32 + lane];
-              v = T.vals[base + (int64_t)k * 32 + lane];
-            }
-          } else if (++spins > kSpinLimit) {
-            *T.error = 1;                             // dependency never arrived: give up loudly
-            k = len;
+            progressed = true;
+            c0 = c1; v0 = v1; x0 = x1;
+            c1 = c2; v1 = v2; x1 = x2;
+            c2 = c3; v2 = v3; x2 = x3;
+            const int nk = k + 3;
+            if (nk < len) { c3 = cp[(int64_t)nk * 32]; v3 = vp[(int64_t)nk * 32]; } else { c3 = -1; v3 = 0.0; }
+            x3 = kNotReady;
           }
-        } else {
-          const double r = T.unit_diag ? acc : acc / d;   // divide by the diagonal last
-          st_volatile(x + row, r);
-          if (out2 != nullptr) out2[out_map[row]] = r;
+        }
+        if (c0 < 0) fed = true;
+        else if (!progressed && ++spins > kSpinLimit) { *T.error = 1; fed = true; }
+      }
+      if (!done) {
+        if (is_long) {
+          // the row is complete when every lane has consumed its share
+          if (__all_sync(0xffffffffu, fed)) {
+            double t = acc;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) {
+              const double r = T.unit_diag ? t : t / d;
+              st_relaxed(x + row, r);
+              if (out2 != nullptr) out2[out_map[row]] = r;
+            }
+            done = true;
+          }
+        } else if (fed) {
+          if (owner) {
+            const double r = T.unit_diag ? acc : acc / d;   // divide by the diagonal last
+            st_relaxed(x + row, r);
+            if (out2 != nullptr) out2[out_map[row]] = r;
+          }
           done = true;
         }
       }
@@ -139,8 +191,8 @@ int trsv_solve(const psb_trsv* T, const double* rhs, double* x, const int32_t* r
   }
   const int64_t warps_needed = T->n_groups;
   int64_t grid = std::min<int64_t>((int64_t)per_sm * sm_count(), (warps_needed + kWarps - 1) / kWarps);
-  TrsvView V{T->n, T->n_groups, T->d_order, T->d_grp_ptr, T->d_cols, T->d_vals, T->d_diag,
-             T->d_counter, T->d_error, T->unit_diag};
+  TrsvView V{T->n, T->n_groups, T->d_order, T->d_diag, T->d_grp_ptr, T->d_grp_item, T->d_grp_rows,
+             T->d_cols, T->d_vals, T->d_counter, T->d_error, T->unit_diag};
   trsv_solve_kernel<<<(int)std::max<int64_t>(grid, 1), kBlock, 0, st>>>(V, rhs, x, rhs_map, out2, out_map, d_skip);
   PSB_LAUNCH_CHECK();
   return PSB_OK;
@@ -151,8 +203,8 @@ int trsv_solve(const psb_trsv* T, const double* rhs, double* x, const int32_t* r
 // ---------------------------------------------------------------------------
 static void free_trsv(psb_trsv* T) {
   if (!T) return;
-  cudaFree(T->d_order); cudaFree(T->d_grp_ptr); cudaFree(T->d_cols); cudaFree(T->d_vals);
-  cudaFree(T->d_diag); cudaFree(T->d_counter); cudaFree(T->d_error);
+  cudaFree(T->d_order); cudaFree(T->d_grp_ptr); cudaFree(T->d_grp_item); cudaFree(T->d_grp_rows);
+  cudaFree(T->d_cols); cudaFree(T->d_vals); cudaFree(T->d_diag); cudaFree(T->d_counter); cudaFree(T->d_error);
   delete T;
 }
 
@@ -266,41 +318,71 @@ extern "C" int psb_trsv_create(int64_t n, const int32_t* h_rowptr, const int32_t
     for (int64_t i = 0; i < n; ++i) T->h_level_rows[cursor[level[i]]++] = (int32_t)i;
   }
 
-  // ---- SELL-32 packing in that order --------------------------------------------------
-  T->n_groups = (int)((n + 31) / 32);
-  std::vector<int64_t> grp_ptr((size_t)T->n_groups + 1, 0);
-  for (int g = 0; g < T->n_groups; ++g) {
-    int32_t w = 0;
-    for (int l = 0; l < 32; ++l) {
-      const int64_t q = (int64_t)g * 32 + l;
-      if (q < n) w = std::max(w, off_count[T->h_level_rows[q]]);
+  // ---- processing order: inside a level the short rows first, then the long ones ------------
+  constexpr int kLongRow = 32;                 // more off-diagonal entries than this -> warp per row
+  std::vector<int32_t> order((size_t)n);
+  {
+    int64_t q = 0;
+    for (int l = 0; l < T->n_levels; ++l) {
+      const int32_t a0 = T->h_level_ptr[l], b0 = T->h_level_ptr[l + 1];
+      for (int32_t p = a0; p < b0; ++p) { const int32_t i = T->h_level_rows[p]; if (off_count[i] <= kLongRow) order[q++] = i; }
+      for (int32_t p = a0; p < b0; ++p) { const int32_t i = T->h_level_rows[p]; if (off_count[i] > kLongRow) order[q++] = i; }
     }
-    grp_ptr[g + 1] = grp_ptr[g] + (int64_t)w * 32;
   }
-  T->nnz_packed = grp_ptr[T->n_groups];
+  // ---- chunks: up to 32 consecutive short rows (SELL-32), or one long row over 32 lanes -------
+  std::vector<int64_t> grp_ptr(1, 0);
+  std::vector<int32_t> grp_item, grp_rows;
+  for (int64_t q = 0; q < n;) {
+    if (off_count[order[q]] > kLongRow) {
+      const int64_t w = (off_count[order[q]] + 31) / 32;
+      grp_item.push_back((int32_t)q); grp_rows.push_back(0);
+      grp_ptr.push_back(grp_ptr.back() + w * 32);
+      ++T->n_long;
+      ++q;
+    } else {
+      int cnt = 0;
+      int32_t w = 0;
+      while (q + cnt < n && cnt < 32 && off_count[order[q + cnt]] <= kLongRow) {
+        w = std::max(w, off_count[order[q + cnt]]);
+        ++cnt;
+      }
+      grp_item.push_back((int32_t)q); grp_rows.push_back(cnt);
+      grp_ptr.push_back(grp_ptr.back() + (int64_t)w * 32);
+      q += cnt;
+    }
+  }
+  T->n_groups = (int)grp_item.size();
+  T->nnz_packed = grp_ptr.back();
   std::vector<int32_t> cols((size_t)T->nnz_packed, -1);
   std::vector<double> vals((size_t)T->nnz_packed, 0.0);
   std::vector<double> diag((size_t)n, 1.0);
   int64_t nnz_off = 0;
-  for (int64_t q = 0; q < n; ++q) {
-    const int32_t i = T->h_level_rows[q];
-    const int g = (int)(q >> 5), l = (int)(q & 31);
-    diag[q] = diag_by_row[i];
-    int k = 0;
-    for (int32_t p = h_rowptr[i]; p < h_rowptr[i + 1]; ++p) {
-      const int32_t j = h_colind[p];
-      if (j == i) continue;
-      const bool dep = lower ? (j < i) : (j > i);
-      if (!dep) continue;
-      cols[grp_ptr[g] + (int64_t)k * 32 + l] = j;
-      vals[grp_ptr[g] + (int64_t)k * 32 + l] = h_vals[p];
-      ++k; ++nnz_off;
+  for (int g = 0; g < T->n_groups; ++g) {
+    const int nrows = grp_rows[g] == 0 ? 1 : grp_rows[g];
+    for (int l = 0; l < nrows; ++l) {
+      const int64_t q = grp_item[g] + l;
+      const int32_t i = order[q];
+      diag[q] = diag_by_row[i];
+      int k = 0;
+      for (int32_t p = h_rowptr[i]; p < h_rowptr[i + 1]; ++p) {
+        const int32_t j = h_colind[p];
+        if (j == i) continue;
+        const bool dep = lower ? (j < i) : (j > i);
+        if (!dep) continue;
+        // short rows: entry k of lane l; long row: entry k spread as (k / 32, k % 32)
+        const int64_t pos = grp_rows[g] == 0 ? grp_ptr[g] + k : grp_ptr[g] + (int64_t)k * 32 + l;
+        cols[pos] = j;
+        vals[pos] = h_vals[p];
+        ++k; ++nnz_off;
+      }
     }
   }
   T->nnz_off = nnz_off;
 
-  cudaError_t e = upload(&T->d_order, T->h_level_rows, st);
+  cudaError_t e = upload(&T->d_order, order, st);
   if (e == cudaSuccess) e = upload(&T->d_grp_ptr, grp_ptr, st);
+  if (e == cudaSuccess) e = upload(&T->d_grp_item, grp_item, st);
+  if (e == cudaSuccess) e = upload(&T->d_grp_rows, grp_rows, st);
   if (e == cudaSuccess) e = upload(&T->d_cols, cols, st);
   if (e == cudaSuccess) e = upload(&T->d_vals, vals, st);
   if (e == cudaSuccess) e = upload(&T->d_diag, diag, st);
@@ -325,7 +407,7 @@ extern "C" int psb_trsv_destroy(psb_trsv_t T) {
 extern "C" int psb_trsv_info(psb_trsv_t T, int64_t info[8]) {
   PSB_REQUIRE(T && info, PSB_ERR_ARG, "psb_trsv_info: NULL argument");
   info[0] = T->n; info[1] = T->n_levels; info[2] = T->nnz_off; info[3] = T->nnz_packed;
-  info[4] = T->lower; info[5] = T->unit_diag; info[6] = T->n_groups; info[7] = 0;
+  info[4] = T->lower; info[5] = T->unit_diag; info[6] = T->n_groups; info[7] = T->n_long;
   return PSB_OK;
 }
 
