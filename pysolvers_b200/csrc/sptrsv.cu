@@ -123,10 +123,11 @@ trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
     if (len > 1) { c1 = cp[32]; v1 = vp[32]; }
     if (len > 2) { c2 = cp[64]; v2 = vp[64]; }
     if (len > 3) { c3 = cp[96]; v3 = vp[96]; }
-    int spins = 0;
+    int spins = 0, idle = 0;
     bool fed = !(c0 >= 0);            // all entries of this lane consumed (padding ends a lane's list)
     bool done = false;
     while (!__all_sync(0xffffffffu, done)) {
+      bool made_progress = false;
       if (!fed) {
         // poll the window with independent loads
         double x0 = ld_relaxed(x + c0);
@@ -150,7 +151,11 @@ trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
         }
         if (c0 < 0) fed = true;
         else if (!progressed && ++spins > kSpinLimit) { *T.error = 1; fed = true; }
+        made_progress = progressed;
       }
+      // warps whose dependencies are still levels away back off instead of hammering L2
+      if (__any_sync(0xffffffffu, made_progress)) idle = 0;
+      else if (++idle > 2) __nanosleep(idle < 12 ? 64u * (unsigned)(idle - 2) : 640u);
       if (!done) {
         if (is_long) {
           // the row is complete when every lane has consumed its share
@@ -189,7 +194,11 @@ int trsv_solve(const psb_trsv* T, const double* rhs, double* x, const int32_t* r
     PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_solve_kernel, kBlock, 0));
     if (per_sm < 1) per_sm = 1;
   }
-  const int64_t warps_needed = T->n_groups;
+  // Only the warps working a few dozen levels ahead of the wavefront do useful work; the rest
+  // would just poll.  Size the grid for `kLookahead` levels of average width.
+  constexpr int64_t kLookahead = 48;
+  const int64_t chunks_per_level = T->n_groups / std::max(T->n_levels, 1) + 1;
+  int64_t warps_needed = std::min<int64_t>(T->n_groups, chunks_per_level * kLookahead);
   int64_t grid = std::min<int64_t>((int64_t)per_sm * sm_count(), (warps_needed + kWarps - 1) / kWarps);
   TrsvView V{T->n, T->n_groups, T->d_order, T->d_diag, T->d_grp_ptr, T->d_grp_item, T->d_grp_rows,
              T->d_cols, T->d_vals, T->d_counter, T->d_error, T->unit_diag};
