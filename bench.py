@@ -322,7 +322,8 @@ def main():
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
-    if args.gpus == 1 and int(os.environ.get('WORLD_SIZE', '1')) == 1:
+    if (args.gpus == 1 and int(os.environ.get('WORLD_SIZE', '1')) == 1
+            and os.environ.get('PSB_BENCH_WORKLOAD', 'c3') == 'c3'):
         return run_single_gpu(args)
     from pysolvers_b200.dist import bench_multi_gpu
     return bench_multi_gpu(args, sys.modules[__name__])

@@ -22,6 +22,7 @@
 #include "spmv.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace psb {
 
@@ -253,7 +254,7 @@ dot_kernel(int64_t n, const double* __restrict__ a, const double* __restrict__ b
 struct PcgWork {
   PcgState* st;
   ReduceBuf rb;
-  double *r, *p, *Ap, *z;
+  double *r, *p, *Ap, *z, *p2;
 };
 
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
@@ -275,7 +276,8 @@ static PcgWork carve(void* d_work, int64_t n, bool has_prec) {
   w.r = (double*)v;
   w.p = (double*)(v + vec);
   w.Ap = (double*)(v + 2 * vec);
-  w.z = has_prec ? (double*)(v + 3 * vec) : w.r;
+  w.p2 = (double*)(v + 3 * vec);
+  w.z = has_prec ? (double*)(v + 4 * vec) : w.r;
   return w;
 }
 
@@ -299,7 +301,7 @@ using namespace psb;
 
 extern "C" int64_t psb_pcg_workspace_bytes(int64_t n, int has_prec) {
   if (n < 0) return PSB_ERR_ARG;
-  return header_bytes() + (3 + (has_prec ? 1 : 0)) * align_up(n * (int64_t)sizeof(double), 256);
+  return header_bytes() + (4 + (has_prec ? 1 : 0)) * align_up(n * (int64_t)sizeof(double), 256);
 }
 
 extern "C" int psb_dot(int64_t n, const double* d_x, const double* d_y, double* d_out, void* stream) {
@@ -362,12 +364,26 @@ extern "C" int psb_pcg_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, do
   bool pending[2] = {false, false};
   bool finished = false;
   EpiArgs ea; ea.dot = &w.st->pAp;
+  // p ping-pong for the fused direction update (STREAM kernel); otherwise p is updated in place
+  const bool fuse = (A->kind == PSB_SPMV_STREAM) && (getenv("PSB_PCG_NOFUSE") == nullptr);
+  double* pbuf[2] = {w.p, fuse ? w.p2 : w.p};
   while (!finished) {
     const int todo = std::min(chunk, maxiter - enq);
-    for (int it = 0; it < todo; ++it) {
-      rc = spmv_launch(A, EPI_DOT, w.p, w.Ap, ea, &w.st->done, st);
+    for (int i = 0; i < todo; ++i) {
+      const int it = enq + i;                       // == device k while the solve is running
+      double* pcur = pbuf[it & 1];
+      if (fuse && it > 0) {
+        // K3 folded into K1: p_k = z + beta p_{k-1} is formed on the fly by the SpMV (gathers
+        // and own row, same rounding as the separate kernel), stored once, never re-read.
+        EpiArgs eb = ea;
+        eb.pold = pbuf[(it - 1) & 1]; eb.pnew = pcur;
+        eb.beta_num = &w.st->udr[it & 1]; eb.beta_den = &w.st->udr[(it - 1) & 1];
+        rc = spmv_launch(A, EPI_DOT_PUP, w.z, w.Ap, eb, &w.st->done, st);
+      } else {
+        rc = spmv_launch(A, EPI_DOT, pcur, w.Ap, ea, &w.st->done, st);
+      }
       if (rc != PSB_OK) return rc;
-      pcg_update_kernel<<<grid, kBlock, 0, st>>>(w.st, n, d_x, w.p, w.r, w.Ap, d_hist, w.rb);
+      pcg_update_kernel<<<grid, kBlock, 0, st>>>(w.st, n, d_x, pcur, w.r, w.Ap, d_hist, w.rb);
       PSB_LAUNCH_CHECK();
       if (has_prec) {
         rc = prec->apply(w.r, w.z, &w.st->done, st);
@@ -375,8 +391,10 @@ extern "C" int psb_pcg_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, do
         pcg_zr_kernel<<<grid, kBlock, 0, st>>>(w.st, n, w.z, w.r, w.rb, 1);
         PSB_LAUNCH_CHECK();
       }
-      pcg_direction_kernel<<<grid, kBlock, 0, st>>>(w.st, n, w.z, w.p);
-      PSB_LAUNCH_CHECK();
+      if (!fuse) {
+        pcg_direction_kernel<<<grid, kBlock, 0, st>>>(w.st, n, w.z, w.p);
+        PSB_LAUNCH_CHECK();
+      }
     }
     enq += todo;
     PSB_CUDA(cudaMemcpyAsync(&t_poll.pinned[slot], w.st, sizeof(PcgState), cudaMemcpyDeviceToHost, st));

@@ -86,7 +86,7 @@ __device__ __forceinline__ void epilogue(int64_t row, double sum, const double* 
 template <int EPI>
 __device__ __forceinline__ void finish_dot(double acc, const psb_csr A, const EpiArgs& ea,
                                            double* scratch) {
-  if (EPI != EPI_DOT) return;
+  if (EPI != EPI_DOT && EPI != EPI_DOT_PUP) return;
   double t = block_sum(acc, scratch);
   if (threadIdx.x == 0) A.partials[blockIdx.x] = t;
   if (last_block(A.ticket)) {
@@ -268,6 +268,8 @@ spmv_bulk_kernel(const psb_csr A, const double* __restrict__ x, double* __restri
     return t < n_int ? ea.rot_t0 + t : (t < ea.rot_t1 ? t - n_int : t);
   };
   bool waited = (ea.wait_n == 0);
+  double beta = 0.0;
+  if (EPI == EPI_DOT_PUP) beta = ld_cg(ea.beta_num) / ld_cg(ea.beta_den);     // PCGSolver.py:135
   const int nnz_v_lim = (int)(A.nnz & ~(int64_t)1);          // bulk copies stop at the last
   const int nnz_c_lim = (int)(A.nnz & ~(int64_t)3);          // whole 16-byte chunk of each array
   const int rp_lim = (int)((A.n_rows + 1) & ~(int64_t)3);
@@ -371,14 +373,31 @@ spmv_bulk_kernel(const psb_csr A, const double* __restrict__ x, double* __restri
         int k = a;
         for (; k + 4 <= b; k += 4) {                   // 4 independent gathers in flight
           const int c0 = sc[k - offc], c1 = sc[k + 1 - offc], c2 = sc[k + 2 - offc], c3 = sc[k + 3 - offc];
-          const double x0 = ld_ca(x + c0), x1 = ld_ca(x + c1), x2 = ld_ca(x + c2), x3 = ld_ca(x + c3);
+          double x0 = ld_ca(x + c0), x1 = ld_ca(x + c1), x2 = ld_ca(x + c2), x3 = ld_ca(x + c3);
+          if (EPI == EPI_DOT_PUP) {                    // p[c] = z[c] + beta * pold[c], as K3 would store it
+            x0 = x0 + beta * ld_ca(ea.pold + c0); x1 = x1 + beta * ld_ca(ea.pold + c1);
+            x2 = x2 + beta * ld_ca(ea.pold + c2); x3 = x3 + beta * ld_ca(ea.pold + c3);
+          }
           sum += sv[k - offv] * x0;
           sum += sv[k + 1 - offv] * x1;
           sum += sv[k + 2 - offv] * x2;
           sum += sv[k + 3 - offv] * x3;
         }
-        for (; k < b; ++k) sum += sv[k - offv] * ld_ca(x + sc[k - offc]);
-        epilogue<EPI>(A.row_off + row0 + lr, sum, x, y, ea, acc);
+        for (; k < b; ++k) {
+          const int c = sc[k - offc];
+          double xv = ld_ca(x + c);
+          if (EPI == EPI_DOT_PUP) xv = xv + beta * ld_ca(ea.pold + c);
+          sum += sv[k - offv] * xv;
+        }
+        if (EPI == EPI_DOT_PUP) {
+          const int64_t row = A.row_off + row0 + lr;
+          const double pn = ld_ca(x + row) + beta * ld_ca(ea.pold + row);
+          ea.pnew[row] = pn;
+          y[row] = sum;
+          acc += pn * sum;
+        } else {
+          epilogue<EPI>(A.row_off + row0 + lr, sum, x, y, ea, acc);
+        }
       }
     }
     __syncthreads();                                   // stage st may be refilled now
@@ -535,6 +554,12 @@ psb_csr csr_row_view(const psb_csr* A, int64_t r0, int64_t r1) {
 
 int spmv_launch(const psb_csr* A, Epi epi, const double* x, double* y, const EpiArgs& ea,
                 const int* d_skip, cudaStream_t st) {
+  if (epi == EPI_DOT_PUP) {
+    if (A->kind != PSB_SPMV_STREAM) { set_error("spmv_launch: EPI_DOT_PUP needs the STREAM kernel"); return PSB_ERR_UNSUPP; }
+    if (A->n_rows == 0) return PSB_OK;
+    return A->rpt == 2 ? launch_bulk<EPI_DOT_PUP, 2>(A, x, y, ea, d_skip, st)
+                       : launch_bulk<EPI_DOT_PUP, 1>(A, x, y, ea, d_skip, st);
+  }
   switch (epi) {
     case EPI_STORE:  return launch_epi<EPI_STORE>(A, x, y, ea, d_skip, st);
     case EPI_DOT:    return launch_epi<EPI_DOT>(A, x, y, ea, d_skip, st);

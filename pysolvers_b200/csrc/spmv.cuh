@@ -27,6 +27,8 @@ enum Epi : int {
   EPI_RESID = 2,   // y = f - A x
   EPI_ADD   = 3,   // y += A x
   EPI_JACOBI = 4,  // y = x + omega * dinv .* (f - A x)
+  EPI_DOT_PUP = 5, // PCG: p = x + beta*pold formed on the fly (gathers and own row), pnew = p,
+                   // y = A p, dot = p . y   (STREAM kernel only)
   EPI_COUNT
 };
 
@@ -36,6 +38,11 @@ struct EpiArgs {
   double        omega = 1.0;       // JACOBI
   double*       dot   = nullptr;   // DOT: where the last CTA writes x . y
   int dot_accumulate  = 0;         // DOT: add to *dot (row-range launches chained on one stream)
+  // DOT_PUP: beta = *beta_num / *beta_den, p = x + beta * pold, stored to pnew
+  const double* pold = nullptr;
+  double*       pnew = nullptr;
+  const double* beta_num = nullptr;
+  const double* beta_den = nullptr;
   // ---- multi-GPU over NVLink peer memory (dist.cu) ------------------------------------
   // once the dot is final, store it (epoch-tagged, see peer_push) into this rank's slot in
   // every rank's memory

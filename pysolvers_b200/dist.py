@@ -401,37 +401,42 @@ def bench_multi_gpu(args, bench):
     value = args.steps * iters / (dev_ms * 1e-3)
 
     # e2e: public API with host operands on every rank (upload block + b, download x)
-    ip_h, ix_h, dt_h = indptr.cpu().numpy(), None, data.cpu().numpy()
-    # global column ids are rebuilt on the host side of the API call from the device copy
-    cols_h = laplacian_block_device(dim, 0.0, 1.0, m, lo, hi, dev)[1].cpu().numpy()
-    b_h = np.ones(n_loc)
-    solver = DistributedPCG(CommonSolverArgs(maxiter=iters, tau=0.0, failOnMaxiter=False,
-                                             showIters=False, showFinal=False))
-    del D
-    torch.cuda.empty_cache()
-
-    def api_step():
-        Dm = DistCSR(comm, ip_h, cols_h, dt_h, lo, hi, n)
-        with contextlib.redirect_stdout(io.StringIO()):
-            st = solver.solve(Dm, b_h)
-        assert st.success() and st.iters() == iters
-        return st
-    api_step()
-    torch.cuda.synchronize()
-    dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        st = api_step()
-    torch.cuda.synchronize()
-    dist.barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = args.steps * iters / float(e2e_s.item())
-    h2d = torch.tensor([ip_h.nbytes + cols_h.nbytes + dt_h.nbytes + b_h.nbytes], dtype=torch.float64, device=dev)
-    dist.all_reduce(h2d)
+    skip_e2e = os.environ.get('PSB_BENCH_SKIP_E2E', '0') == '1'
+    e2e_value, h2d_total, final_resid = None, 0, float(hist_d[-1].item())
     nnz_t = torch.tensor([nnz_loc], dtype=torch.float64, device=dev)
     dist.all_reduce(nnz_t)
     nnz = int(nnz_t.item())
+    mode = 'nvlink-p2p' if D.p2p else 'nccl'
+    if not skip_e2e:
+        ip_h, dt_h = indptr.cpu().numpy(), data.cpu().numpy()
+        cols_h = laplacian_block_device(dim, 0.0, 1.0, m, lo, hi, dev)[1].cpu().numpy()
+        b_h = np.ones(n_loc)
+        solver = DistributedPCG(CommonSolverArgs(maxiter=iters, tau=0.0, failOnMaxiter=False,
+                                                 showIters=False, showFinal=False))
+        del D
+        torch.cuda.empty_cache()
+
+        def api_step():
+            Dm = DistCSR(comm, ip_h, cols_h, dt_h, lo, hi, n)
+            with contextlib.redirect_stdout(io.StringIO()):
+                st = solver.solve(Dm, b_h)
+            assert st.success() and st.iters() == iters
+            return st
+        api_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            st = api_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        e2e_value = args.steps * iters / float(e2e_s.item())
+        h2d = torch.tensor([ip_h.nbytes + cols_h.nbytes + dt_h.nbytes + b_h.nbytes], dtype=torch.float64, device=dev)
+        dist.all_reduce(h2d)
+        h2d_total = int(h2d.item())
+        final_resid = float(st.resid())
 
     if rank == 0:
         peak, peak_src = bench.peaks()
@@ -444,11 +449,10 @@ def bench_multi_gpu(args, bench):
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
             'config': {'workload': name, 'n': n, 'nnz': nnz, 'iters_per_step': iters,
-                       'parallelism': 'row partition over %d GPUs: NCCL send/recv halo overlapped with '
-                                      'interior SpMV, 2 scalar all-reduces per iteration' % world,
+                       'parallelism': 'row partition over %d GPUs, collectives: %s' % (world, mode),
                        'l2': 'inputs larger than L2: %.2f GB touched per iteration per GPU'
                              % (iter_bytes / world / 1e9)},
-            'e2e': {'value': e2e_value, 'unit': bench.UNIT, 'h2d_bytes_per_step': int(h2d.item()),
+            'e2e': {'value': e2e_value, 'unit': bench.UNIT, 'h2d_bytes_per_step': h2d_total,
                     'd2h_bytes_per_step': int(8 * n + 8 * iters * world)},
             'gpu_launches': int(launches), 'clocks': clocks,
             'roofline': {'bound': 'hbm', 'kernel': 'whole PCG iteration (aggregate over GPUs)',
@@ -457,7 +461,7 @@ def bench_multi_gpu(args, bench):
                          'bytes_per_iteration': iter_bytes, 'ms_per_iteration': iter_ms,
                          'peak_source': peak_src + ' x %d GPUs' % world},
             'cpu_baseline': None,
-            'final_residual': float(st.resid()),
+            'final_residual': final_resid,
         }
         print(json.dumps(line))
     comm.close()
