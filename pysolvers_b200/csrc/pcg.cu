@@ -18,6 +18,7 @@
 // Reductions are deterministic (fixed tree per CTA, per-CTA partials added in
 // index order by the last CTA).  No FMA contraction (-fmad=false): x + alpha*p
 // rounds the product first, like numpy.
+#include "pcg_mega.cuh"
 #include "prec.cuh"
 #include "spmv.cuh"
 
@@ -341,6 +342,47 @@ extern "C" int psb_pcg_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, do
 
   PcgWork w = carve(d_work, n, has_prec);
   PSB_CUDA(cudaMemsetAsync(d_work, 0, kHeaderBytes, st));
+
+  // ---- identity preconditioner + STREAM matrix: the whole solve is ONE persistent cooperative
+  // kernel (pcg_mega.cu); the reductions double as grid barriers, no launch per phase ----------
+  {
+    const char* env = getenv("PSB_PCG_MEGA");
+    const bool mega = !has_prec && A->kind == PSB_SPMV_STREAM && A->rpt == 1 && n > 0 &&
+                      !(env && env[0] == '0');
+    if (mega) {
+      char* base = (char*)d_work;
+      MegaParams P;
+      memset(&P, 0, sizeof(P));
+      P.A = *A; P.n = n; P.n_halo = 0;
+      P.b = d_b; P.x = d_x; P.r = w.r; P.Ap = w.Ap; P.pbuf[0] = w.p; P.pbuf[1] = w.p2;
+      P.hist = d_hist;
+      P.st = (MegaState*)base;
+      P.ticket = (unsigned int*)(base + 1024);
+      P.partials = w.rb.partials;
+      unsigned long long* slots = (unsigned long long*)(base + 2048);
+      unsigned long long** d_ptrs = (unsigned long long**)(base + 1536);
+      unsigned long long* h_ptrs[kRing];
+      for (int e = 0; e < kRing; ++e) h_ptrs[e] = slots + (size_t)e * kMaxRanks * 2;
+      PSB_CUDA(cudaMemcpyAsync(d_ptrs, h_ptrs, sizeof(h_ptrs), cudaMemcpyHostToDevice, st));
+      PSB_CUDA(cudaStreamSynchronize(st));                  // h_ptrs is on the stack
+      P.my_slots = slots; P.slot_ptrs = d_ptrs; P.nranks = 1; P.epoch0 = 1;
+      P.n_push = 0; P.n_wait = 0; P.halo_epoch0 = 1;
+      P.rot_t0 = P.rot_t1 = 0;
+      P.maxiter = maxiter; P.tau = tau; P.fail_on_maxiter = fail_on_maxiter;
+      size_t smem;
+      pcg_mega_caps(A, &P.cap_v, &P.cap_c, &smem);
+      P.error = (int*)(base + 1024 + 128);
+      rc = pcg_mega_launch(P, st);
+      if (rc != PSB_OK) return rc;
+      PSB_CUDA(cudaStreamSynchronize(st));
+      MegaState ms;
+      PSB_CUDA(cudaMemcpy(&ms, P.st, sizeof(ms), cudaMemcpyDeviceToHost));
+      if (!ms.done) { set_error("psb_pcg_solve: persistent kernel ended without a terminal state"); return PSB_ERR_CUDA; }
+      result->status = ms.status; result->k = ms.k_final; result->n_hist = ms.n_hist; result->lucky = 0;
+      result->norm_r = ms.norm_r; result->norm_b = ms.norm_b; result->norm_r_rec = ms.norm_r;
+      return PSB_OK;
+    }
+  }
   PcgState h0;
   memset(&h0, 0, sizeof(h0));
   h0.tau = tau; h0.maxiter = maxiter; h0.fail_on_maxiter = fail_on_maxiter; h0.has_prec = has_prec;

@@ -43,6 +43,11 @@ struct EpiArgs {
   double*       pnew = nullptr;
   const double* beta_num = nullptr;
   const double* beta_den = nullptr;
+  // DOT_PUP, multi-GPU: rows in [pp_off, pp_off+pp_cnt) of the new p are also stored into the
+  // neighbour's halo at pp_remote
+  int pp_n = 0;
+  long long pp_off[4] = {0, 0, 0, 0}, pp_cnt[4] = {0, 0, 0, 0};
+  double* pp_remote[4] = {nullptr, nullptr, nullptr, nullptr};
   // ---- multi-GPU over NVLink peer memory (dist.cu) ------------------------------------
   // once the dot is final, store it (epoch-tagged, see peer_push) into this rank's slot in
   // every rank's memory
