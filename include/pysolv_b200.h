@@ -229,17 +229,19 @@ int psb_dist_create(psb_comm_t comm, psb_csr_t A_local, int64_t n_loc, int64_t n
 int psb_dist_destroy(psb_dist_t D);
 /* NVLink peer-memory mode (optional; without it the solve uses NCCL collectives).  Each rank
  * allocates a region holding its two p buffers, reduction slots and halo flags and exports
- * it (cudaIpc handle, 64 bytes; layout = {p buffer 0 offset, p buffer 1 offset, n_loc,
- * n_halo}); after the handles have been exchanged every rank maps its peers' regions.  Push
+ * it (cudaIpc handle, 64 bytes; layout = {p buffer 0, p buffer 1, r buffer byte offsets,
+ * n_loc, n_halo, 0}); after the handles have been exchanged every rank maps its peers' regions.  Push
  * i: the contiguous slice [send_off, send_off+send_cnt) of p goes to rank push_rank[i] at
- * byte offset remote_off{0,1}[i] of its region (one per p buffer), and its halo flag number
+ * byte offset remote_off{0,1}[i] of its region (one per p buffer; remote_off_r[i] for the r
+ * halo used by the single-launch persistent solve), and its halo flag number
  * remote_flag_index[i] is raised.  Then psb_dist_pcg_solve fuses the collectives into the
  * compute kernels: scalar all-reduces and halo exchange are peer stores + local polling. */
-int psb_dist_p2p_alloc(psb_dist_t D, void* h_handle64, int64_t layout[4]);
+int psb_dist_p2p_alloc(psb_dist_t D, void* h_handle64, int64_t layout[6]);
 int psb_dist_p2p_open(psb_dist_t D, const void* h_handles, int32_t n_push,
                       const int32_t* h_push_rank, const int64_t* h_send_off,
                       const int64_t* h_send_cnt, const int64_t* h_remote_off0,
-                      const int64_t* h_remote_off1, const int32_t* h_remote_flag_index);
+                      const int64_t* h_remote_off1, const int64_t* h_remote_off_r,
+                      const int32_t* h_remote_flag_index);
 /* y_loc = A_loc [x_loc | halo]; d_x_ext has n_loc + n_halo entries, the halo part is
  * filled by the exchange (NCCL send/recv on a side stream, overlapped with interior rows). */
 int psb_dist_spmv(psb_dist_t D, double* d_x_ext, double* d_y, void* stream);

@@ -76,7 +76,7 @@ SIGNATURES = {
                                   C.POINTER(_vp)]),
     'psb_dist_destroy': (C.c_int, [_vp]),
     'psb_dist_p2p_alloc': (C.c_int, [_vp, _vp, C.POINTER(_i64)]),
-    'psb_dist_p2p_open': (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'psb_dist_p2p_open': (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'psb_dist_spmv': (C.c_int, [_vp, _vp, _vp, _vp]),
     'psb_dist_pcg_workspace_bytes': (_i64, [_i64, _i64]),
     'psb_dist_pcg_solve': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _dbl, _i32, _vp,

@@ -15,6 +15,7 @@
 //
 // NCCL is resolved at run time from the libnccl.so.2 torch has already loaded (dlopen), so
 // the single-GPU path has no NCCL dependency.
+#include "pcg_mega.cuh"
 #include "prec.cuh"
 #include "spmv.cuh"
 
@@ -22,6 +23,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -99,12 +101,13 @@ struct psb_dist {
   char* shm = nullptr;                 // this rank's exported region (cudaMalloc + IPC handle)
   size_t shm_bytes = 0;
   int64_t pbuf_off[2] = {0, 0};        // byte offsets of the two p buffers (n_loc + n_halo each)
+  int64_t rbuf_off = 0;                // ... and of the r buffer (persistent-kernel path)
   std::vector<char*> peer_shm;         // [nranks] mapped base pointers (self = shm)
   unsigned long long** d_slot_ptrs = nullptr;   // device [kRing][nranks]: my slot in rank q, ring e
   int* d_error = nullptr;
   unsigned int red_epoch = 1;          // next reduction epoch (host-assigned, same on all ranks)
   unsigned long long halo_epoch = 1;   // epoch of the next p vector
-  struct Push { int64_t send_off, cnt; double* remote[2]; unsigned long long* remote_flag; };
+  struct Push { int64_t send_off, cnt; double* remote[2]; double* remote_r; unsigned long long* remote_flag; };
   std::vector<Push> pushes;            // contiguous halo pushes (one per receiving peer)
 };
 
@@ -243,9 +246,6 @@ dist_direction_kernel(DistState* st, int64_t n, int it, const double* __restrict
 // Layout of the exported region: [slots: kRing x 32 ranks x 2 words][flags: 32 x u64]
 // [p buffer 0][p buffer 1].
 // ---------------------------------------------------------------------------------------
-constexpr int kRing = 4;
-constexpr int kMaxRanks = 32;
-constexpr int kMaxPush = 4;
 constexpr int64_t kSlotsBytes = 4096;    // kRing * kMaxRanks * 16 B = 2048
 constexpr int64_t kFlagsBytes = 4096;
 
@@ -551,14 +551,15 @@ extern "C" int psb_dist_destroy(psb_dist_t D) {
 }
 
 // ---- NVLink peer-memory mode: export / map the shared regions ---------------------------------
-extern "C" int psb_dist_p2p_alloc(psb_dist_t D, void* h_handle64, int64_t layout[4]) {
+extern "C" int psb_dist_p2p_alloc(psb_dist_t D, void* h_handle64, int64_t layout[6]) {
   PSB_REQUIRE(D && h_handle64 && layout, PSB_ERR_ARG, "psb_dist_p2p_alloc: NULL argument");
   PSB_REQUIRE(D->comm->nranks <= kMaxRanks, PSB_ERR_UNSUPP, "psb_dist_p2p_alloc: too many ranks");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
   const int64_t vec = align_up((D->n_loc + D->n_halo) * 8, 256);
   D->pbuf_off[0] = kSlotsBytes + kFlagsBytes;
   D->pbuf_off[1] = D->pbuf_off[0] + vec;
-  D->shm_bytes = (size_t)(D->pbuf_off[1] + vec);
+  D->rbuf_off = D->pbuf_off[1] + vec;
+  D->shm_bytes = (size_t)(D->rbuf_off + vec);
   PSB_CUDA(cudaMalloc((void**)&D->shm, D->shm_bytes));
   PSB_CUDA(cudaMemset(D->shm, 0, D->shm_bytes));
   PSB_CUDA(cudaMalloc((void**)&D->d_error, sizeof(int)));
@@ -566,14 +567,16 @@ extern "C" int psb_dist_p2p_alloc(psb_dist_t D, void* h_handle64, int64_t layout
   cudaIpcMemHandle_t h;
   PSB_CUDA(cudaIpcGetMemHandle(&h, D->shm));
   memcpy(h_handle64, &h, sizeof(h));
-  layout[0] = D->pbuf_off[0]; layout[1] = D->pbuf_off[1]; layout[2] = D->n_loc; layout[3] = D->n_halo;
+  layout[0] = D->pbuf_off[0]; layout[1] = D->pbuf_off[1]; layout[2] = D->rbuf_off;
+  layout[3] = D->n_loc; layout[4] = D->n_halo; layout[5] = 0;
   return PSB_OK;
 }
 
 extern "C" int psb_dist_p2p_open(psb_dist_t D, const void* h_handles, int32_t n_push,
                                  const int32_t* h_push_rank, const int64_t* h_send_off,
                                  const int64_t* h_send_cnt, const int64_t* h_remote_off0,
-                                 const int64_t* h_remote_off1, const int32_t* h_remote_flag_index) {
+                                 const int64_t* h_remote_off1, const int64_t* h_remote_off_r,
+                                 const int32_t* h_remote_flag_index) {
   PSB_REQUIRE(D && h_handles && D->shm, PSB_ERR_ARG, "psb_dist_p2p_open: call psb_dist_p2p_alloc first");
   PSB_REQUIRE(n_push >= 0 && n_push <= kMaxPush, PSB_ERR_UNSUPP, "psb_dist_p2p_open: too many halo targets");
   PSB_REQUIRE(D->A->kind == PSB_SPMV_STREAM, PSB_ERR_UNSUPP,
@@ -603,6 +606,7 @@ extern "C" int psb_dist_p2p_open(psb_dist_t D, const void* h_handles, int32_t n_
     P.send_off = h_send_off[i]; P.cnt = h_send_cnt[i];
     P.remote[0] = (double*)(D->peer_shm[q] + h_remote_off0[i]);
     P.remote[1] = (double*)(D->peer_shm[q] + h_remote_off1[i]);
+    P.remote_r = (double*)(D->peer_shm[q] + h_remote_off_r[i]);
     P.remote_flag = (unsigned long long*)(D->peer_shm[q] + kSlotsBytes) + h_remote_flag_index[i];
     D->pushes.push_back(P);
   }
@@ -811,6 +815,54 @@ static int dist_pcg_p2p(psb_dist_t D, const double* d_b, double* d_x, void* d_wo
   }
 
   const int grid = stream_grid(std::max<int64_t>(n, 1), rb.max_grid);
+  {
+    const char* env = getenv("PSB_DIST_MEGA");
+    const bool mega_ok = D->A->kind == PSB_SPMV_STREAM && D->A->rpt == 1 && (D->r0 % 256) == 0 &&
+                         ((D->r1 % 256) == 0 || D->r1 == n) && n > 0 && !(env && env[0] == '0');
+    if (mega_ok) {
+      // the whole solve as ONE persistent kernel per GPU; halo + all-reduces over NVLink peer memory
+      MegaParams P;
+      memset(&P, 0, sizeof(P));
+      P.A = *D->A; P.n = n; P.n_halo = D->n_halo;
+      P.b = d_b; P.x = d_x; P.Ap = Ap;
+      P.r = (double*)(D->shm + D->rbuf_off);
+      P.pbuf[0] = pbuf[0]; P.pbuf[1] = pbuf[1];
+      // ping-pong parity: iteration `it` writes pbuf[it & 1]; halo flags count from h0e
+      P.hist = d_hist;
+      P.st = (MegaState*)(base + 2048);
+      P.ticket = rb.ticket; P.partials = rb.partials;
+      P.my_slots = (const unsigned long long*)D->shm; P.slot_ptrs = D->d_slot_ptrs;
+      P.nranks = c.nranks; P.epoch0 = e;
+      P.n_push = c.n_push;
+      for (int k = 0; k < c.n_push; ++k) {
+        P.push_off[k] = D->pushes[k].send_off; P.push_cnt[k] = D->pushes[k].cnt;
+        P.push_r[k] = D->pushes[k].remote_r;
+        P.push_p[0][k] = D->pushes[k].remote[0]; P.push_p[1][k] = D->pushes[k].remote[1];
+        P.push_flag[k] = D->pushes[k].remote_flag;
+      }
+      P.n_wait = n_wait; P.my_flags = my_flags; P.halo_epoch0 = h0e;
+      P.rot_t0 = D->r0 / 256; P.rot_t1 = (D->r1 + 255) / 256;
+      P.maxiter = maxiter; P.tau = tau; P.fail_on_maxiter = fail_on_maxiter;
+      size_t smem;
+      pcg_mega_caps(D->A, &P.cap_v, &P.cap_c, &smem);
+      P.error = D->d_error;
+      rc = pcg_mega_launch(P, st);
+      if (rc != PSB_OK) return rc;
+      PSB_CUDA(cudaStreamSynchronize(st));
+      MegaState ms;
+      PSB_CUDA(cudaMemcpy(&ms, P.st, sizeof(ms), cudaMemcpyDeviceToHost));
+      int err = 0;
+      PSB_CUDA(cudaMemcpy(&err, D->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+      D->red_epoch = e + ms.epochs_used;
+      D->halo_epoch = h0e + ms.halo_epochs_used;
+      if (err) { set_error("psb_dist_pcg_solve: timed out waiting for a peer GPU (rank %d)", D->comm->rank); return PSB_ERR_NCCL; }
+      if (!ms.done) { set_error("psb_dist_pcg_solve: persistent kernel ended without a terminal state"); return PSB_ERR_CUDA; }
+      result->status = ms.status; result->k = ms.k_final; result->n_hist = ms.n_hist; result->lucky = 0;
+      result->norm_r = ms.norm_r; result->norm_b = ms.norm_b; result->norm_r_rec = ms.norm_r;
+      return PSB_OK;
+    }
+  }
+
   {
     const unsigned int e_bb = e++;
     p2p_init_kernel<<<grid, kBlock, 0, st>>>(S, n, d_b, d_x, r, pbuf[h0e & 1], rb, view_for(h0e), e_bb, h0e, ticket2);

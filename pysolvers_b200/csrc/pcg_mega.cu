@@ -62,6 +62,12 @@ __device__ __forceinline__ double mega_allreduce(const MegaParams& P, double v, 
   return s_sum;
 }
 
+__device__ __forceinline__ double2 mega_ld2(const double* p) {     // coherent, no L1 allocation
+  double2 v;
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ void mega_push_r(const MegaParams& P, long long i, double v) {
 #pragma unroll
   for (int k = 0; k < kMaxPush; ++k)
@@ -125,17 +131,32 @@ pcg_mega_kernel(const MegaParams P) {
       const double* p = P.pbuf[it & 1];
       acc = 0.0;
       const long long n2 = n >> 1;
-      for (long long i = gtid; i < n2; i += gstride) {
-        double2 xv = *reinterpret_cast<const double2*>(P.x + 2 * i);
-        const double2 pv = __ldcg(reinterpret_cast<const double2*>(p + 2 * i));
-        double2 rv = *reinterpret_cast<const double2*>(P.r + 2 * i);
-        const double2 av = __ldcg(reinterpret_cast<const double2*>(P.Ap + 2 * i));
-        xv.x = xv.x + alpha * pv.x; xv.y = xv.y + alpha * pv.y;
-        rv.x = rv.x - alpha * av.x; rv.y = rv.y - alpha * av.y;
-        *reinterpret_cast<double2*>(P.x + 2 * i) = xv;
-        *reinterpret_cast<double2*>(P.r + 2 * i) = rv;
-        if (P.n_push > 0) { mega_push_r(P, 2 * i, rv.x); mega_push_r(P, 2 * i + 1, rv.y); }
-        acc += rv.x * rv.x; acc += rv.y * rv.y;
+      // two independent 128-bit chunks per thread per trip, streaming (no L1 allocation)
+      long long i = gtid;
+      for (; i + gstride < n2; i += 2 * gstride) {
+        const long long j = i + gstride;
+        double2 x0 = mega_ld2(P.x + 2 * i), p0 = mega_ld2(p + 2 * i), r0 = mega_ld2(P.r + 2 * i), a0 = mega_ld2(P.Ap + 2 * i);
+        double2 x1 = mega_ld2(P.x + 2 * j), p1 = mega_ld2(p + 2 * j), r1 = mega_ld2(P.r + 2 * j), a1 = mega_ld2(P.Ap + 2 * j);
+        x0.x = x0.x + alpha * p0.x; x0.y = x0.y + alpha * p0.y;
+        r0.x = r0.x - alpha * a0.x; r0.y = r0.y - alpha * a0.y;
+        x1.x = x1.x + alpha * p1.x; x1.y = x1.y + alpha * p1.y;
+        r1.x = r1.x - alpha * a1.x; r1.y = r1.y - alpha * a1.y;
+        st_stream2(P.x + 2 * i, x0); st_stream2(P.r + 2 * i, r0);
+        st_stream2(P.x + 2 * j, x1); st_stream2(P.r + 2 * j, r1);
+        if (P.n_push > 0) {
+          mega_push_r(P, 2 * i, r0.x); mega_push_r(P, 2 * i + 1, r0.y);
+          mega_push_r(P, 2 * j, r1.x); mega_push_r(P, 2 * j + 1, r1.y);
+        }
+        acc += r0.x * r0.x; acc += r0.y * r0.y;
+        acc += r1.x * r1.x; acc += r1.y * r1.y;
+      }
+      for (; i < n2; i += gstride) {
+        double2 x0 = mega_ld2(P.x + 2 * i), p0 = mega_ld2(p + 2 * i), r0 = mega_ld2(P.r + 2 * i), a0 = mega_ld2(P.Ap + 2 * i);
+        x0.x = x0.x + alpha * p0.x; x0.y = x0.y + alpha * p0.y;
+        r0.x = r0.x - alpha * a0.x; r0.y = r0.y - alpha * a0.y;
+        st_stream2(P.x + 2 * i, x0); st_stream2(P.r + 2 * i, r0);
+        if (P.n_push > 0) { mega_push_r(P, 2 * i, r0.x); mega_push_r(P, 2 * i + 1, r0.y); }
+        acc += r0.x * r0.x; acc += r0.y * r0.y;
       }
       if ((n & 1) && leader) {
         const long long i = n - 1;

@@ -199,7 +199,7 @@ class DistCSR:
         if not all(flags):
             return
         handle = (C.c_ubyte * 64)()
-        layout = (C.c_int64 * 4)()
+        layout = (C.c_int64 * 6)()
         nat.check(nat.lib().psb_dist_p2p_alloc(self._h, handle, layout), 'psb_dist_p2p_alloc')
         info = [None] * comm.world
         dist.all_gather_object(info, (bytes(handle), [int(v) for v in layout]))
@@ -213,6 +213,7 @@ class DistCSR:
         send_cnt = (C.c_int64 * max(k, 1))()
         roff0 = (C.c_int64 * max(k, 1))()
         roff1 = (C.c_int64 * max(k, 1))()
+        roffr = (C.c_int64 * max(k, 1))()
         fidx = (C.c_int32 * max(k, 1))()
         for i, q in enumerate(targets):
             s = self.send[q]
@@ -223,11 +224,12 @@ class DistCSR:
             push_rank[i] = q
             send_off[i] = int(s[0])
             send_cnt[i] = int(s.size)
-            roff0[i] = lay[0] + 8 * (lay[2] + first)
-            roff1[i] = lay[1] + 8 * (lay[2] + first)
+            roff0[i] = lay[0] + 8 * (lay[3] + first)
+            roff1[i] = lay[1] + 8 * (lay[3] + first)
+            roffr[i] = lay[2] + 8 * (lay[3] + first)
             fidx[i] = int(np.flatnonzero(np.unique(owners_q) == comm.rank)[0])
         nat.check(nat.lib().psb_dist_p2p_open(self._h, handles, k, push_rank, send_off, send_cnt,
-                                              roff0, roff1, fidx), 'psb_dist_p2p_open')
+                                              roff0, roff1, roffr, fidx), 'psb_dist_p2p_open')
         dist.barrier()
         self.p2p = True
 
