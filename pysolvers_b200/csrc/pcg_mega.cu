@@ -24,6 +24,7 @@
 #include "spmv_bulk.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace psb {
 
@@ -75,7 +76,8 @@ __device__ __forceinline__ void mega_push_r(const MegaParams& P, long long i, do
       P.push_r[k][i - P.push_off[k]] = v;
 }
 
-__global__ void __launch_bounds__(kBlock, 4)
+template <int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
 pcg_mega_kernel(const MegaParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double scratch[kWarps];
@@ -193,7 +195,8 @@ void pcg_mega_caps(const psb_csr* A, int* cap_v, int* cap_c, size_t* smem) {
   *smem = 2 * ((size_t)*cap_v * 8 + (size_t)*cap_c * 4 + (size_t)(kBlock + 4) * 4);
 }
 
-int pcg_mega_launch(const MegaParams& P, cudaStream_t stream) {
+template <int MINB>
+static int mega_launch_t(const MegaParams& P, cudaStream_t stream) {
   int cv, cc;
   size_t smem;
   pcg_mega_caps(&P.A, &cv, &cc, &smem);
@@ -201,8 +204,8 @@ int pcg_mega_launch(const MegaParams& P, cudaStream_t stream) {
   static thread_local size_t cached_smem = 0;
   if (per_sm == 0 || cached_smem != smem) {
     if (smem > 48 * 1024)
-      PSB_CUDA(cudaFuncSetAttribute(pcg_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_mega_kernel, kBlock, smem));
+      PSB_CUDA(cudaFuncSetAttribute(pcg_mega_kernel<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_mega_kernel<MINB>, kBlock, smem));
     if (per_sm < 1) { set_error("pcg_mega_launch: kernel does not fit on an SM"); return PSB_ERR_UNSUPP; }
     cached_smem = smem;
   }
@@ -212,10 +215,23 @@ int pcg_mega_launch(const MegaParams& P, cudaStream_t stream) {
   grid = std::min<long long>(grid, (long long)sm_count() * 16);       // partial buffers hold this many
   MegaParams Q = P;
   void* args[] = {(void*)&Q};
-  PSB_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_mega_kernel, dim3((unsigned)grid), dim3(kBlock), args,
-                                       smem, stream));
+  PSB_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_mega_kernel<MINB>, dim3((unsigned)grid), dim3(kBlock),
+                                       args, smem, stream));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return PSB_OK;
+}
+
+int pcg_mega_launch(const MegaParams& P, cudaStream_t stream) {
+  // resident CTAs per SM the kernel is compiled for: 4 (64 registers), 5 (48) or 6 (40)
+  static int minb = 0;
+  if (minb == 0) {
+    const char* env = getenv("PSB_MEGA_MINB");
+    minb = env ? atoi(env) : 5;       // measured best on B200: 5 CTAs/SM, 48 registers, no spills
+    if (minb < 4 || minb > 6) minb = 5;
+  }
+  if (minb == 6) return mega_launch_t<6>(P, stream);
+  if (minb == 4) return mega_launch_t<4>(P, stream);
+  return mega_launch_t<5>(P, stream);
 }
 
 }  // namespace psb
