@@ -3,6 +3,10 @@
 #pragma once
 #include "spmv.cuh"
 
+#ifndef PSB_PUP_WINDOW
+#define PSB_PUP_WINDOW 0
+#endif
+
 namespace psb {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -204,6 +208,38 @@ __device__ __forceinline__ void bulk_pass(const psb_csr& A, const double* x, dou
 
     const int s = rp[0];
     const int offv = s & ~1, offc = s & ~3;
+    // EPI_DOT_PUP: the tile's own rows of p = x + beta * pold are formed once, kept in shared
+    // memory and stored; gathers that fall inside the tile's row window (the k, k-1, k+1 entries
+    // of a stencil) read them back instead of two global gathers each.
+    __shared__ double ptile[EPI == EPI_DOT_PUP ? R : 1];
+    constexpr bool kWindow = PSB_PUP_WINDOW != 0;       // serve in-tile gathers from ptile
+    const long long win0 = A.row_off + row0;
+    if constexpr (EPI == EPI_DOT_PUP) {
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        const int lr = tid + j * kBlock;
+        if (lr < nr) {
+          const int64_t row = win0 + lr;
+          const double pn = ld_ca(x + row) + beta * ld_ca(ea.pold + row);   // as K3 would store it
+          ptile[lr] = pn;
+          ea.pnew[row] = pn;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)                 // boundary rows also go to the neighbours' halo
+            if (q < ea.pp_n && row >= ea.pp_off[q] && row < ea.pp_off[q] + ea.pp_cnt[q])
+              ea.pp_remote[q][row - ea.pp_off[q]] = pn;
+        }
+      }
+      if (kWindow) __syncthreads();
+    }
+    auto gather = [&](int c) -> double {
+      if constexpr (EPI == EPI_DOT_PUP) {
+        const long long d = (long long)c - win0;
+        if (kWindow && d >= 0 && d < nr) return ptile[d];
+        return ld_ca(x + c) + beta * ld_ca(ea.pold + c);
+      } else {
+        return ld_ca(x + c);
+      }
+    };
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
       const int lr = tid + j * kBlock;
@@ -213,32 +249,18 @@ __device__ __forceinline__ void bulk_pass(const psb_csr& A, const double* x, dou
         int k = a;
         for (; k + 4 <= b; k += 4) {                   // 4 independent gathers in flight
           const int c0 = sc[k - offc], c1 = sc[k + 1 - offc], c2 = sc[k + 2 - offc], c3 = sc[k + 3 - offc];
-          double x0 = ld_ca(x + c0), x1 = ld_ca(x + c1), x2 = ld_ca(x + c2), x3 = ld_ca(x + c3);
-          if (EPI == EPI_DOT_PUP) {                    // p[c] = z[c] + beta * pold[c], as K3 would store it
-            x0 = x0 + beta * ld_ca(ea.pold + c0); x1 = x1 + beta * ld_ca(ea.pold + c1);
-            x2 = x2 + beta * ld_ca(ea.pold + c2); x3 = x3 + beta * ld_ca(ea.pold + c3);
-          }
+          const double x0 = gather(c0), x1 = gather(c1), x2 = gather(c2), x3 = gather(c3);
           sum += sv[k - offv] * x0;
           sum += sv[k + 1 - offv] * x1;
           sum += sv[k + 2 - offv] * x2;
           sum += sv[k + 3 - offv] * x3;
         }
         for (; k < b; ++k) {
-          const int c = sc[k - offc];
-          double xv = ld_ca(x + c);
-          if (EPI == EPI_DOT_PUP) xv = xv + beta * ld_ca(ea.pold + c);
-          sum += sv[k - offv] * xv;
+          sum += sv[k - offv] * gather(sc[k - offc]);
         }
         if constexpr (EPI == EPI_DOT_PUP) {
-          const int64_t row = A.row_off + row0 + lr;
-          const double pn = ld_ca(x + row) + beta * ld_ca(ea.pold + row);
-          ea.pnew[row] = pn;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)                 // boundary rows also go to the neighbours' halo
-            if (q < ea.pp_n && row >= ea.pp_off[q] && row < ea.pp_off[q] + ea.pp_cnt[q])
-              ea.pp_remote[q][row - ea.pp_off[q]] = pn;
-          y[row] = sum;
-          acc += pn * sum;
+          y[win0 + lr] = sum;
+          acc += ptile[lr] * sum;                   // own element: written by this very thread
         } else {
           epilogue<EPI>(A.row_off + row0 + lr, sum, x, y, ea, acc);
         }

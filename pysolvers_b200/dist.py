@@ -181,7 +181,7 @@ class DistCSR:
             'psb_dist_create')
 
         self.p2p = False
-        if os.environ.get('PSB_DIST_MODE', 'p2p') != 'nccl' and comm.world > 1:
+        if os.environ.get('PSB_DIST_MODE', 'p2p') != 'nccl':
             self._enable_p2p(gathered)
 
     def _enable_p2p(self, all_recv):
