@@ -128,3 +128,39 @@ def test_pcg_large_properties(cuda):
     assert true_r <= 5e-8 * np.linalg.norm(b)
     st2, _ = _run(PCG(CommonSolverArgs(maxiter=4000, tau=1e-8)).makeSolver(), A, 3.0 * b)
     assert np.linalg.norm(st2.soln() - 3.0 * st.soln()) <= 1e-6 * np.linalg.norm(st2.soln())
+
+
+@pytest.mark.parametrize('mode', ['persistent', 'fused-kernels', 'kernel-per-phase'])
+def test_pcg_driver_variants_agree(cuda, golden, mode, monkeypatch):
+    """The three PCG drivers (one persistent cooperative kernel; SpMV with the direction update
+    folded in + update kernel; three kernels per iteration) run the same arithmetic: same
+    iteration count, histories within 1e-10 of the reference's, solutions within 1e-8."""
+    from pysolvers_b200 import CommonSolverArgs
+    from pysolvers_b200.Linear import PCG
+    if mode != 'persistent':
+        monkeypatch.setenv('PSB_PCG_MEGA', '0')
+    if mode == 'kernel-per-phase':
+        monkeypatch.setenv('PSB_PCG_NOFUSE', '1')
+    A = _lap(64)
+    b = A @ np.random.default_rng(12345).random(A.shape[0])
+    st, hist = _run(PCG(CommonSolverArgs(maxiter=5000, tau=1e-8)).makeSolver(), A, b)
+    key = 'pcg/lap2d_m64_rand'
+    assert st.success() and st.iters() == int(golden[key + '/iters'])
+    assert rel_err(hist, golden[key + '/hist']) < HIST_RTOL
+    gx = golden[key + '/x']
+    assert np.linalg.norm(st.soln() - gx) <= SOLN_RTOL * np.linalg.norm(gx)
+    # exits through every driver
+    st, h = _run(PCG(CommonSolverArgs(maxiter=7, tau=1e-12)).makeSolver(), _lap(16), np.ones(256))
+    assert (st.success(), st.iters(), len(h)) == (False, 6, 7)
+    st, h = _run(PCG(CommonSolverArgs(maxiter=7, tau=1e-12, failOnMaxiter=False)).makeSolver(), _lap(16), np.ones(256))
+    assert (st.success(), st.iters(), len(h)) == (True, 7, 7)
+
+
+def test_pcg_breakdown_pap(cuda):
+    """dot(p, Ap) == 0 at the first iteration -> handleBreakdown(k=0) (PCGSolver.py:114-115)."""
+    import scipy.sparse as sp
+    from pysolvers_b200 import CommonSolverArgs
+    from pysolvers_b200.Linear import PCG
+    A = sp.csr_matrix(np.array([[0.0, 1.0], [-1.0, 0.0]]))       # x'Ax = 0 for every x
+    st, h = _run(PCG(CommonSolverArgs(maxiter=5)).makeSolver(), A, np.array([1.0, 2.0]))
+    assert (st.success(), st.iters(), st.soln(), st.msg()) == (False, 0, None, 'breakdown dot(p, Ap)==0')
