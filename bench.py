@@ -186,9 +186,9 @@ def run_reference(args):
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': workload_name(M_GRID), 'sample': '%d iterations per step' % iters},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': '%d steps x %d PCG iterations of the full 16.8 M-row system; '
+                         'sample': '%d steps x %d PCG iterations of the full %d-row system; '
                                    'scipy csr_matvec is single-threaded, OpenBLAS ddot uses %d thread(s); '
-                                   'os.cpu_count()=%d' % (args.steps, iters, cores, os.cpu_count())},
+                                   'os.cpu_count()=%d' % (args.steps, iters, A.shape[0], cores, os.cpu_count())},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
@@ -338,9 +338,9 @@ def run_single_gpu(args):
                           'frac': iter_gbs / peak_gbs, 'bytes_per_iteration': iter_bytes,
                           'ms_per_iteration': iter_ms},
         'cpu_baseline': {'value': cpu_rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': '%d PCG iterations of the same 16.8 M-row system (%.1f s); scipy '
+                         'sample': '%d PCG iterations of the same %d-row system (%.1f s); scipy '
                                    'csr_matvec single-threaded, OpenBLAS %d thread(s), os.cpu_count()=%d'
-                                   % (cpu_iters, cpu_s, cores, os.cpu_count())},
+                                   % (cpu_iters, n, cpu_s, cores, os.cpu_count())},
         'final_residual': hist_last,
     }
     print(json.dumps(line))
