@@ -41,6 +41,8 @@ namespace psb {
 
 static constexpr unsigned long long kSentinelBits = 0xFFF8DEADBEEF0B20ull;   // a quiet NaN payload
 static constexpr int kSpinLimit = 1 << 22;   // polls per lane before giving up (>= 1 s)
+static constexpr int kIdleTrips = 10;        // a warp this many polls (~3 us) without progress is >= 2 levels
+                                              // behind the wavefront: it may sleep between polls
 
 __device__ __forceinline__ double ld_volatile(const double* p) {
   double v;
@@ -129,33 +131,36 @@ trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
     while (!__all_sync(0xffffffffu, done)) {
       bool made_progress = false;
       if (!fed) {
-        // poll the window with independent loads
+        // waiting mode: one poll of the next dependency, nothing else on the path
         double x0 = ld_relaxed(x + c0);
-        double x1 = c1 >= 0 ? ld_relaxed(x + c1) : kNotReady;
-        double x2 = c2 >= 0 ? ld_relaxed(x + c2) : kNotReady;
-        double x3 = c3 >= 0 ? ld_relaxed(x + c3) : kNotReady;
-        bool progressed = false;
+        if (is_ready(x0)) {
+          made_progress = true;
+          // streaming mode: the following three entries are polled together and consumed in
+          // order as far as they are ready; new entries are fetched behind them
+          double x1 = c1 >= 0 ? ld_relaxed(x + c1) : kNotReady;
+          double x2 = c2 >= 0 ? ld_relaxed(x + c2) : kNotReady;
+          double x3 = c3 >= 0 ? ld_relaxed(x + c3) : kNotReady;
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          if (c0 >= 0 && is_ready(x0)) {
-            acc = acc - v0 * x0;                      // stored order, product rounded first
-            ++k;
-            progressed = true;
-            c0 = c1; v0 = v1; x0 = x1;
-            c1 = c2; v1 = v2; x1 = x2;
-            c2 = c3; v2 = v3; x2 = x3;
-            const int nk = k + 3;
-            if (nk < len) { c3 = cp[(int64_t)nk * 32]; v3 = vp[(int64_t)nk * 32]; } else { c3 = -1; v3 = 0.0; }
-            x3 = kNotReady;
+          for (int s = 0; s < 4; ++s) {
+            if (c0 >= 0 && is_ready(x0)) {
+              acc = acc - v0 * x0;                    // stored order, product rounded first
+              ++k;
+              c0 = c1; v0 = v1; x0 = x1;
+              c1 = c2; v1 = v2; x1 = x2;
+              c2 = c3; v2 = v3; x2 = x3;
+              const int nk = k + 3;
+              if (nk < len) { c3 = cp[(int64_t)nk * 32]; v3 = vp[(int64_t)nk * 32]; } else { c3 = -1; v3 = 0.0; }
+              x3 = kNotReady;
+            }
           }
+          if (c0 < 0) fed = true;
+        } else if (++spins > kSpinLimit) {
+          *T.error = 1; fed = true;
         }
-        if (c0 < 0) fed = true;
-        else if (!progressed && ++spins > kSpinLimit) { *T.error = 1; fed = true; }
-        made_progress = progressed;
       }
       // warps whose dependencies are still levels away back off instead of hammering L2
       if (__any_sync(0xffffffffu, made_progress)) idle = 0;
-      else if (++idle > 2) __nanosleep(idle < 12 ? 64u * (unsigned)(idle - 2) : 640u);
+      else if (++idle > kIdleTrips) __nanosleep(idle < kIdleTrips + 8 ? 32u * (unsigned)(idle - kIdleTrips) : 256u);
       if (!done) {
         if (is_long) {
           // the row is complete when every lane has consumed its share

@@ -1,0 +1,174 @@
+"""Host-side mirror of the reference API, on CPU: control / result protocol, report formats,
+the preconditioner protocol, the Newton driver with the direct-solver passthrough, and the
+error behaviour of the device solvers when the GPU path cannot serve a request."""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import numpy.linalg as npla
+import pytest
+import scipy.sparse as sp
+
+import pysolvers_b200 as P
+from pysolvers_b200 import CommonSolverArgs, SolveStatus
+from pysolvers_b200.core import IterativeSolver
+from pysolvers_b200.Linear import (PCG, GMRES, PCGSolver, IdentityPreconditioner, IdentityPreconditionerType,
+                                   LeftPreconditioner, RightPreconditioner, GenericPreconditioner,
+                                   PreconditionerType, DefaultDirect, AMGVCycle, LinearSolver)
+from pysolvers_b200.Linear.precond import right_handle_of
+from pysolvers_b200.Nonlinear import NewtonSolver, FuncAdapter1D, SimpleBacktrack, PreconditionerFreeze
+
+
+def _out(fn, *a, **k):
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        r = fn(*a, **k)
+    return r, buf.getvalue()
+
+
+def test_package_surface_matches_reference():
+    # PySolvers/__init__.py:1-3 and PySolvers/Linear/__init__.py:1-12
+    for name in ('Linear', 'Nonlinear', 'CommonSolverArgs'):
+        assert hasattr(P, name)
+    for name in ('IterativeLinearSolver', 'mvmult', 'DefaultDirect', 'DefaultDirectSolver', 'PCG', 'PCGSolver',
+                 'GMRES', 'GMRESSolver', 'IdentityPreconditionerType', 'IdentityPreconditioner',
+                 'ICRightPreconditioner', 'RightIC', 'LeftILUT', 'RightILUT', 'AMGVCycle', 'AMGVCycleSolver',
+                 'AMGPreconditioner', 'AMG'):
+        assert hasattr(P.Linear, name), name
+    for name in ('NewtonSolver', 'FuncAdapter1D'):
+        assert hasattr(P.Nonlinear, name)
+
+
+def test_control_defaults_and_shared_default_instance():
+    c = CommonSolverArgs()
+    assert (c.maxiter, c.failOnMaxiter, c.tau, c.showIters, c.showFinal, c.interval) == (100, True, 1e-8, True, True, 1)
+    assert c.norm is npla.norm
+    # def-time singleton shared between solvers built with defaults
+    a, b = PCG().makeSolver(), PCG().makeSolver()
+    assert a._control is b._control
+    old = a.tau()
+    a.setTolerance(1e-3)
+    assert b.tau() == 1e-3
+    a.setTolerance(old)
+
+
+def test_exit_conventions_and_report_text():
+    s = IterativeSolver(CommonSolverArgs(maxiter=7), name='S')
+    st, text = _out(s.handleConvergence, 3, 'x', 1e-9, 2.0)
+    assert (st.success(), st.iters(), st.soln(), st.resid(), st.msg()) == (True, 4, 'x', 1e-9, None)
+    assert text == 'S solve succeeded: iters=%7d, ||r||/r0=%12.5g\n' % (4, 1e-9 / 2.0)
+    st, text = _out(s.handleBreakdown, 2, 'why')
+    assert (st.success(), st.iters(), st.soln(), st.resid(), st.msg()) == (False, 2, None, None, 'why')
+    assert text == 'S solve broke down: why\n'
+    st, text = _out(s.handleMaxiter, 6, 'x', 0.5, 2.0)
+    assert (st.success(), st.iters(), st.msg()) == (False, 6, 'failure to converge')
+    assert text == 'S solve FAILED: iters=%7d, ||r||/r0=%12.5g\n' % (6, 0.25)
+    s2 = IterativeSolver(CommonSolverArgs(maxiter=7, failOnMaxiter=False), name='S')
+    st, _ = _out(s2.handleMaxiter, 6, 'x', 0.5, 2.0)
+    assert (st.success(), st.iters()) == (True, 6)
+    _, text = _out(s.reportIter, 4, 3.0, 6.0)
+    assert text == 'S iter=%7d ||r||=%12.5g ||r||/r0=%12.5g\n' % (4, 3.0, 0.5)
+    quiet = IterativeSolver(CommonSolverArgs(showIters=False, showFinal=False), name='S')
+    assert _out(quiet.reportIter, 0, 1.0, 1.0)[1] == '' and _out(quiet.handleConvergence, 0, 0, 1.0, 1.0)[1] == ''
+    assert str(SolveStatus(True, None, 0.5, 3)) == 'SolverState(success=True, resid=0.5, iters=3)'
+
+
+def test_preconditioner_protocol():
+    v = np.arange(3.0)
+    ident = IdentityPreconditionerType().form(None)
+    assert ident.applyLeft(v) is v and ident.applyRight(v) is v and right_handle_of(ident) is None
+
+    class MyLeft(LeftPreconditioner):
+        def applyLeft(self, vec):
+            return 2 * vec
+    assert MyLeft().applyRight(v) is v and right_handle_of(MyLeft()) is None
+
+    class HostOnly(RightPreconditioner):
+        def applyRight(self, vec):
+            return vec / 2
+    with pytest.raises(NotImplementedError):
+        right_handle_of(HostOnly())            # no CPU fallback on the solve path
+
+    class Unknown:
+        def applyRight(self, vec):
+            return vec
+    with pytest.raises(NotImplementedError):
+        right_handle_of(Unknown())
+
+
+def test_shape_asserts_and_unsupported_norm():
+    A = sp.identity(4, format='csr')
+    with pytest.raises(AssertionError):
+        PCG().makeSolver().solve(sp.csr_matrix((3, 4)), np.ones(3))
+    with pytest.raises(AssertionError):
+        GMRES().makeSolver().solve(A, np.ones(5))
+    s = PCG(CommonSolverArgs(norm=lambda x: np.max(np.abs(x)))).makeSolver()
+    with pytest.raises(NotImplementedError):
+        s.solve(A, np.ones(4))
+
+
+def test_missing_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a CUDA device is present')
+    from pysolvers_b200 import _native
+    with pytest.raises(_native.NativeError):
+        _out(PCG().makeSolver().solve, sp.identity(4, format='csr'), np.ones(4))
+
+
+class _Root2(FuncAdapter1D):
+    def _evalF(self, x):
+        return x * x - 2
+
+    def _evalJ(self, x):
+        return 2.0 * x
+
+
+class _ArcTan(FuncAdapter1D):
+    def _evalF(self, x):
+        return np.arctan(x)
+
+    def _evalJ(self, x):
+        return 1.0 / (1.0 + x * x)
+
+
+def test_newton_examples_with_direct_solver():
+    """examples/NewtonExample_Root2.py and NewtonExample_ArcTan.py (CPU: DefaultDirect)."""
+    solver = NewtonSolver(control=CommonSolverArgs(tau=1.0e-15, maxiter=10), solver=DefaultDirect())
+    st, text = _out(solver.solve, _Root2(), np.array([3.0]))
+    assert st.success() and abs(st.soln()[0] - np.sqrt(2.0)) < 1e-14
+    assert 'Newton iter=' in text
+    solver = NewtonSolver(control=CommonSolverArgs(tau=1.0e-15, maxiter=10), solver=DefaultDirect(), freezePrec=False)
+    st, text = _out(solver.solve, _ArcTan(), np.array([10.0]))
+    assert st.success() and abs(st.soln()[0]) < 1e-14
+    assert 'k=   0 t=' in text                       # the line search had to backtrack from x0 = 10
+
+
+def test_newton_linear_failure_is_a_breakdown():
+    class Failing(LinearSolver):
+        def solve(self, A, b):
+            return SolveStatus(False, None, None, None, 'nope')
+
+    class Type:
+        def makeSolver(self):
+            return Failing()
+    st, _ = _out(NewtonSolver(solver=Type()).solve, _Root2(), np.array([3.0]))
+    assert not st.success() and 'solve for Newton step failed with msg=nope' in st.msg()
+
+
+def test_preconditioner_freeze_never_unfreezes():
+    s = PCG().makeSolver()
+    PreconditionerFreeze(s, True)
+    assert s.precFrozen()                             # and stays so: __def__ typo reproduced
+    s.unfreezePrec()
+    PreconditionerFreeze(s, False)
+    assert not s.precFrozen()
+
+
+def test_backtracking_line_search():
+    ls = SimpleBacktrack(report=False)
+    ls.setNorm(npla.norm)
+    ok, x, F, nF = ls.search(np.array([10.0]), abs(np.arctan(10.0)), np.array([-10.0 * 101 * np.arctan(10.0) / 10.0]), _ArcTan())
+    assert ok and nF < abs(np.arctan(10.0))
