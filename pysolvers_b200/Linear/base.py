@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from ..core import CommonSolverArgs, IterativeSolver, NamedObject
-from ..device import DeviceCSR, to_device
+from ..device import DeviceCSR, to_device, to_host
 from .precond import IdentityPreconditionerType
 
 
@@ -97,18 +97,7 @@ class IterativeLinearSolver(LinearSolver, IterativeSolver):
 
     @staticmethod
     def _to_host(t, like):
-        """Device vector -> fresh numpy array owned by the caller.  Large vectors land in
-        page-locked memory (torch's caching host allocator): a pageable destination costs
-        ~60 ms per 134 MB in first-touch page faults, the pinned one 2.5 ms (measured,
-        tools/e2e_probe.py); the array keeps the block alive and returns it to the cache when
-        it is garbage-collected."""
-        if t.numel() >= (1 << 17):
-            stage = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            stage.copy_(t, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            out = stage.numpy()
-        else:
-            out = t.cpu().numpy()
+        out = to_host(t)
         return out if out.dtype == like.dtype else out.astype(like.dtype)
 
 
@@ -116,4 +105,4 @@ def mvmult(A, x):
     """y = A x through the device SpMV; returns a numpy vector."""
     dA = A if isinstance(A, DeviceCSR) else DeviceCSR(A)
     y = dA.matvec(to_device(x))
-    return y.cpu().numpy()
+    return to_host(y)

@@ -25,7 +25,7 @@ import torch
 from .. import _native as nat
 from ..core import CommonSolverArgs, Tab
 from ..device import (DeviceCSR, DevicePrec, DeviceTrsv, current_stream_ptr, ptr,
-                      require_cuda, to_device)
+                      require_cuda, to_device, to_host)
 from . import amg_setup
 from .base import IterativeLinearSolver, IterativeLinearSolverType
 from .precond import GenericPreconditioner, PreconditionerType
@@ -225,7 +225,7 @@ class DeviceAMG:
         res = nat.SolveResult()
         nat.check(nat.lib().psb_amg_solve(self.handle, ptr(b_d), ptr(x_d), int(maxiter), float(tau),
                                           ptr(hist), C.byref(res), current_stream_ptr()), 'psb_amg_solve')
-        return x_d.cpu().numpy(), res, hist[:res.n_hist].cpu().numpy()
+        return to_host(x_d), res, hist[:res.n_hist].cpu().numpy()
 
 
 class VCycleManager:

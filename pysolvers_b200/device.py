@@ -49,6 +49,19 @@ def to_device(a, dtype=torch.float64):
     return torch.from_numpy(arr).cuda(non_blocking=True)
 
 
+def to_host(t):
+    """Device tensor -> fresh numpy array.  Large vectors land in page-locked memory (torch's
+    caching host allocator): a pageable destination costs ~60 ms per 134 MB in first-touch
+    page faults, the pinned one 2.5 ms (measured, tools/e2e_probe.py).  The array keeps the
+    block alive and hands it back to the cache when it is garbage-collected."""
+    if t.is_cuda and t.numel() >= (1 << 17):
+        stage = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        stage.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return stage.numpy()
+    return t.cpu().numpy()
+
+
 def as_csr(A):
     """Accept what the reference accepts as a matrix operand: a scipy sparse
     matrix (converted to CSR if needed) or a dense 2-D ndarray.  A dense matrix
@@ -218,7 +231,7 @@ class DevicePrec:
         """numpy in, numpy out (upload, apply on the device, download)."""
         v = np.asarray(vec, dtype=np.float64)
         out = self.apply(to_device(v))
-        return out.cpu().numpy()
+        return to_host(out)
 
     def __del__(self):
         try:

@@ -26,7 +26,7 @@ import torch
 
 from . import _native as nat
 from .core import CommonSolverArgs, IterativeSolver, SolveStatus
-from .device import DeviceCSR, current_stream_ptr, ptr, to_device
+from .device import DeviceCSR, current_stream_ptr, ptr, to_device, to_host
 
 TILE = 256     # interior range is aligned to SpMV tiles (and so to the 16-byte bulk copies)
 
@@ -285,7 +285,7 @@ class DistributedPCG(IterativeSolver):
         self.last_history = hist
         for k in range(res.n_hist):
             self.reportIter(k, hist[k], res.norm_b)
-        x = x_d[:n] if keep_on_device else x_d[:n].cpu().numpy()
+        x = x_d[:n] if keep_on_device else to_host(x_d[:n])
         if res.status == nat.TRIVIAL:
             return self.handleConvergence(0, x * 0, 0, 0)
         if res.status == nat.BREAKDOWN_PAP:
