@@ -113,8 +113,9 @@ def ncu_traffic(kernel_substr):
     for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_ncu_full.json'))):
         try:
             for d in json.load(open(path)):
-                if kernel_substr in d.get('kernel', '') and d.get('dram_traffic_bytes'):
-                    best = float(d['dram_traffic_bytes'])
+                v = d.get('dram_traffic_bytes')
+                if kernel_substr in d.get('kernel', '') and v and v == v:      # skip NaN captures
+                    best = float(v)
         except Exception:
             pass
     return best

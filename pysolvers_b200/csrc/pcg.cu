@@ -373,7 +373,7 @@ extern "C" int psb_pcg_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, do
       pcg_mega_caps(A, &P.cap_v, &P.cap_c, &smem);
       P.error = (int*)(base + 1024 + 128);
       rc = pcg_mega_launch(P, st);
-      if (rc != PSB_OK) return rc;
+      if (rc == PSB_OK) {
       PSB_CUDA(cudaStreamSynchronize(st));
       MegaState ms;
       PSB_CUDA(cudaMemcpy(&ms, P.st, sizeof(ms), cudaMemcpyDeviceToHost));
@@ -381,6 +381,11 @@ extern "C" int psb_pcg_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, do
       result->status = ms.status; result->k = ms.k_final; result->n_hist = ms.n_hist; result->lucky = 0;
       result->norm_r = ms.norm_r; result->norm_b = ms.norm_b; result->norm_r_rec = ms.norm_r;
       return PSB_OK;
+      }
+      // the cooperative launch was refused (e.g. the device is shared and the grid cannot be
+      // co-resident): clear the error and run the kernel-per-phase driver below -- still on the GPU
+      (void)cudaGetLastError();
+      PSB_CUDA(cudaMemsetAsync(d_work, 0, kHeaderBytes, st));
     }
   }
   PcgState h0;
