@@ -206,6 +206,15 @@ int psb_amg_create(int32_t n_levels, const psb_csr_t* A, const psb_csr_t* P,
 int psb_amg_solve(psb_prec_t amg, const double* d_b, double* d_x, int32_t maxiter,
                   double tau, double* d_hist, psb_solve_result* result, void* stream);
 
+/* ------------------------------------- Bratu residual / Jacobian on the device -- */
+/* F = Au - alpha exp(-u)   (examples/FDBratu2D.py:20-21; Au from psb_spmv) */
+int psb_bratu_residual(int64_t n, const double* d_Au, const double* d_u, double alpha,
+                       double* d_F, void* stream);
+/* vals[diag_pos[i]] = a_diag[i] + alpha exp(-u[i]): the Jacobian of FDBratu2D.py:23-29
+ * written into the VALUES of a device CSR whose structure is A's. */
+int psb_bratu_jacobian(int64_t n, const int64_t* d_diag_pos, const double* d_a_diag,
+                       const double* d_u, double alpha, double* d_vals, void* stream);
+
 /* ------------------------------------------------- multi-GPU (one rank per GPU) -- */
 /* The reference has no distributed code; contract: SURVEY.md section 8e.  NCCL is
  * taken from the libnccl.so.2 already loaded in the process (torch's). */

@@ -14,12 +14,14 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 from .. import _native as nat
-from ..device import DevicePrec, DeviceTrsv, current_stream_ptr
+from ..device import DeviceCSR, DevicePrec, DeviceTrsv, current_stream_ptr
 from .precond import (LeftPreconditioner, Preconditioner, PreconditionerType,
                       RightPreconditioner)
 
 
 def _host_matrix(A):
+    if isinstance(A, DeviceCSR):
+        return A.to_scipy()          # setup runs on the host (SuperLU), as in the reference
     if not sp.issparse(A):
         raise TypeError('IC / ILUT need a scipy sparse matrix (the reference '
                         'calls A.tocsc()); got %r' % type(A))

@@ -63,12 +63,15 @@ class PCGSolver(IterativeLinearSolver):
         n = self._check_system(A, b)
         self._require_euclidean_norm()
         require_cuda()
-        b = np.asarray(b)
+        on_device = isinstance(b, torch.Tensor)      # device vector in -> device vector out
+        if not on_device:
+            b = np.asarray(b)
         b_d = to_device(b)
+        zeros = (lambda: torch.zeros_like(b_d)) if on_device else (lambda: np.zeros_like(b))
 
         # b == 0 short cut, before any preconditioner work (PCGSolver.py:86-88)
         if n == 0 or _device_norm(b_d) == 0.0:
-            return self.handleConvergence(0, np.zeros_like(b), 0, 0)
+            return self.handleConvergence(0, zeros(), 0, 0)
 
         print('prec frozen = ', self.precFrozen())
         if self.precond is None or not self.precFrozen():
@@ -97,12 +100,12 @@ class PCGSolver(IterativeLinearSolver):
 
         st = res.status
         if st == nat.TRIVIAL:
-            return self.handleConvergence(0, np.zeros_like(b), 0, 0)
+            return self.handleConvergence(0, zeros(), 0, 0)
         if st == nat.BREAKDOWN_UR:
             return self.handleBreakdown(0, 'breakdown dot(u,r)==0')
         if st == nat.BREAKDOWN_PAP:
             return self.handleBreakdown(res.k, 'breakdown dot(p, Ap)==0')
-        x = self._to_host(x_d, b)
+        x = x_d if on_device else self._to_host(x_d, b)
         if st == nat.CONVERGED:
             return self.handleConvergence(res.k, x, res.norm_r, normB)
         return self.handleMaxiter(res.k, x, res.norm_r, normB)
@@ -149,10 +152,13 @@ class GMRESSolver(IterativeLinearSolver):
         n = self._check_system(A, b)
         self._require_euclidean_norm()
         require_cuda()
-        b = np.asarray(b)
+        on_device = isinstance(b, torch.Tensor)
+        if not on_device:
+            b = np.asarray(b)
         b_d = to_device(b)
+        zeros = (lambda: torch.zeros_like(b_d)) if on_device else (lambda: np.zeros_like(b))
         if n == 0 or _device_norm(b_d) == 0.0:
-            return self.handleConvergence(0, np.zeros_like(b), 0, 0)
+            return self.handleConvergence(0, zeros(), 0, 0)
 
         precond = self.precondType().form(A)          # always rebuilt, see class doc
         prec_h = right_handle_of(precond)
@@ -177,8 +183,8 @@ class GMRESSolver(IterativeLinearSolver):
         for k in range(res.n_hist):
             self.reportIter(k, hist[k], normB)
         if res.status == nat.TRIVIAL:
-            return self.handleConvergence(0, np.zeros_like(b), 0, 0)
-        x = self._to_host(x_d, b)
+            return self.handleConvergence(0, zeros(), 0, 0)
+        x = x_d if on_device else self._to_host(x_d, b)
         if res.status == nat.CONVERGED:
             return self.handleConvergence(res.k, x, res.norm_r, normB)
         if res.status == nat.GMRES_FALSE_CONV:

@@ -152,6 +152,8 @@ class SmoothedAggregationMLHierarchy(MLHierarchy):
         tab = Tab()
         for lev in reversed(range(numLevels - 1)):
             print('{}making prolongator from level {} to {}'.format(tab, lev, lev + 1))
+        if isinstance(A_fine, DeviceCSR):
+            A_fine = A_fine.to_scipy()       # setup runs on the host, as in the reference
         ops, ups, downs = amg_setup.build_hierarchy(sp.csr_matrix(A_fine), numLevels, normalize)
         self._ops, self._updates, self._downdates = ops, ups, downs
 

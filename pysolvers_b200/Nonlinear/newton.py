@@ -139,7 +139,7 @@ class NewtonSolver(IterativeSolver):
 
     def solve(self, func, xInit):
         tab = Tab()
-        xCur = xInit.copy()
+        xCur = xInit.clone() if hasattr(xInit, 'clone') else xInit.copy()
         FCur = func.evalF(xCur)
         print('freeze prec for solver=', self.freezePrec)
         PreconditionerFreeze(self.solver, self.freezePrec)

@@ -68,6 +68,8 @@ SIGNATURES = {
     'psb_gmres_workspace_bytes': (_i64, [_i64, _i32]),
     'psb_gmres_solve': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _dbl, _i32, _i32, _vp,
                                   C.POINTER(SolveResult), _vp]),
+    'psb_bratu_residual': (C.c_int, [_i64, _vp, _vp, _dbl, _vp, _vp]),
+    'psb_bratu_jacobian': (C.c_int, [_i64, _vp, _vp, _vp, _dbl, _vp, _vp]),
     'psb_nccl_unique_id': (C.c_int, [_vp]),
     'psb_comm_create': (C.c_int, [_vp, _i32, _i32, C.POINTER(_vp)]),
     'psb_comm_destroy': (C.c_int, [_vp]),

@@ -16,6 +16,21 @@ into the reference's numbers.
 import numpy.linalg as npla
 
 
+def _is_cuda_tensor(x):
+    return type(x).__module__.startswith('torch') and getattr(x, 'is_cuda', False)
+
+
+def _device_norm2(x):
+    import ctypes as C
+    import torch
+    from . import _native as nat
+    out = torch.empty(1, dtype=torch.float64, device=x.device)
+    nat.check(nat.lib().psb_dot(x.numel(), C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()),
+                                C.c_void_p(out.data_ptr()),
+                                C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'psb_dot')
+    return float(out.item()) ** 0.5
+
+
 class Tab:
     """Indentation prefix for nested solver output (the reference uses the
     un-vendored PyTab package for this)."""
@@ -113,6 +128,8 @@ class IterativeSolver(NamedObject):
         self._control.tau = tau
 
     def norm(self, x):
+        if self._control.norm is npla.norm and _is_cuda_tensor(x):
+            return _device_norm2(x)             # same 2-norm, evaluated where the vector lives
         return self._control.norm(x)
 
     def _require_euclidean_norm(self):

@@ -126,6 +126,11 @@ class DeviceCSR:
                                      current_stream_ptr()), 'psb_spmv')
         return out
 
+    def to_scipy(self):
+        """Download as a scipy csr_matrix (same stored order)."""
+        return sp.csr_matrix((self.data.cpu().numpy(), self.indices.cpu().numpy(),
+                              self.indptr.cpu().numpy()), shape=self.shape)
+
     def algorithmic_bytes(self):
         """HBM bytes one SpMV must move."""
         n, m = self.shape

@@ -132,3 +132,47 @@ def dh_test_problem(lev, seed=2024, root=None):
     A = load_dh_matrix(lev, root)
     x = np.random.default_rng(seed).random(A.shape[0])
     return A, A * x, x
+
+
+class DeviceFDBratu2D:
+    """FDBratu2D with u, F and the Jacobian resident in HBM:
+    evalF / evalJ take and return CUDA tensors / a DeviceCSR whose diagonal values are
+    rewritten in place -- the structure is uploaded once.  Drop it into NewtonSolver exactly
+    like the host class; the linear solvers accept the DeviceCSR and the device right-hand
+    side and return a device solution."""
+
+    def __init__(self, m=4, alpha=0.5):
+        import torch
+        from .device import DeviceCSR, to_device
+        self.m, self.alpha = m, alpha
+        self.A = -fd_laplacian_2d(-1.0, 1.0, m)
+        n = m * m
+        rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(self.A.indptr))
+        dpos = np.flatnonzero(rows == self.A.indices)
+        assert dpos.size == n
+        self._dA = DeviceCSR(self.A)
+        self._dJ = DeviceCSR(self.A)
+        self._diag_pos = torch.from_numpy(dpos).cuda()
+        self._a_diag = to_device(self.A.diagonal())
+        self._torch = torch
+
+    def initialU(self):
+        return self._torch.ones(self.m * self.m, dtype=self._torch.float64, device='cuda')
+
+    def evalF(self, u):
+        import ctypes as C
+        from . import _native as nat
+        from .device import current_stream_ptr, ptr
+        Au = self._dA.matvec(u)
+        F = self._torch.empty_like(u)
+        nat.check(nat.lib().psb_bratu_residual(u.numel(), ptr(Au), ptr(u), float(self.alpha), ptr(F),
+                                               current_stream_ptr()), 'psb_bratu_residual')
+        return F
+
+    def evalJ(self, u):
+        from . import _native as nat
+        from .device import current_stream_ptr, ptr
+        nat.check(nat.lib().psb_bratu_jacobian(u.numel(), ptr(self._diag_pos), ptr(self._a_diag), ptr(u),
+                                               float(self.alpha), ptr(self._dJ.data), current_stream_ptr()),
+                  'psb_bratu_jacobian')
+        return self._dJ

@@ -126,3 +126,45 @@ def test_newton_bratu_vs_reference_golden(cuda, golden, m, sm):
     assert rel_err(hist[sel], g[sel]) < 1e-6
     gx = golden[key + '/x']
     assert np.linalg.norm(st.soln() - gx) <= 1e-8 * np.linalg.norm(gx)
+
+
+@pytest.mark.parametrize('sm', ['gs', 'djac'])
+def test_newton_bratu_device_resident(cuda, golden, sm):
+    """u, F and J stay in HBM across the Newton loop (DeviceFDBratu2D); same
+    Newton / linear iteration counts and residual history as the reference's host loop."""
+    import torch
+    from pysolvers_b200 import CommonSolverArgs
+    from pysolvers_b200.Linear import PCG, AMG
+    from pysolvers_b200.Nonlinear import NewtonSolver
+    from pysolvers_b200.problems import DeviceFDBratu2D, FDBratu2D
+    m = 32
+    func = DeviceFDBratu2D(m=m)
+    host = FDBratu2D(m=m)
+    u = np.linspace(0.5, 1.5, m * m)
+    ud = torch.from_numpy(u).cuda()
+    assert np.allclose(func.evalF(ud).cpu().numpy(), host.evalF(u), rtol=1e-14, atol=0)
+    Jd, Jh = func.evalJ(ud).to_scipy(), host.evalJ(u)
+    assert np.array_equal(Jd.indices, Jh.indices) and np.allclose(Jd.data, Jh.data, rtol=1e-15, atol=0)
+    lin_iters = []
+    newton = NewtonSolver(control=CommonSolverArgs(tau=1.0e-12, maxiter=10),
+                          solver=PCG(control=CommonSolverArgs(), precond=AMG(numIters=5, smoother=_smoother(sm))),
+                          fixLinTol=False, minLinTol=1.0e-6, freezePrec=True)
+    inner = newton.solver
+    orig = inner.solve
+
+    def spy(J, rhs):
+        assert isinstance(rhs, torch.Tensor) and rhs.is_cuda
+        r = orig(J, rhs)
+        assert isinstance(r.soln(), torch.Tensor) and r.soln().is_cuda
+        lin_iters.append(r.iters())
+        return r
+    inner.solve = spy
+    st, hist = _run(newton, func, func.initialU())
+    key = 'newton/bratu_m%d_%s' % (m, sm)
+    assert st.success() and st.iters() == int(golden[key + '/iters'])
+    assert lin_iters == golden[key + '/lin_iters'].tolist()
+    g = golden[key + '/hist']
+    sel = g > 1e-9 * g[0]
+    assert rel_err(hist[sel], g[sel]) < 1e-6
+    gx = golden[key + '/x']
+    assert np.linalg.norm(st.soln().cpu().numpy() - gx) <= 1e-8 * np.linalg.norm(gx)
