@@ -111,6 +111,19 @@ int psb_trsv_destroy(psb_trsv_t T);
 /* info[0]=n, [1]=levels, [2]=off-diagonal nnz, [3]=packed (padded) nnz,
  * [4]=lower, [5]=unit_diag, [6]=32-row groups. */
 int psb_trsv_info(psb_trsv_t T, int64_t info[8]);
+/* Which solve kernel the analysis chose, and the data of the shared-memory window kernel:
+ * info[0]=kernel (0 grid-wide, hand-over through L2; 1 one CTA, hand-over through shared
+ * memory), [1]=window slots, [2]=dependencies older than the window (read from the global
+ * vector), [3]=largest distance of a dependency in processing order, [4]=forced kernel or -1. */
+int psb_trsv_info2(psb_trsv_t T, int64_t info[8]);
+/* Force a kernel for this factor (0 / 1), or -1 to return to the analysis' choice.  Both
+ * kernels produce bit-identical results. */
+int psb_trsv_set_kernel(psb_trsv_t T, int kernel);
+/* Debugging aid of the one-CTA kernel: when d_trace (device, 12 * groups int64) is not NULL every
+ * chunk records clock64 at its start, at its first missing dependency, after sleeping, at its
+ * last batch of entries, when its last dependency arrived and after its store, plus the entry
+ * index of the first miss and the entries per lane. */
+int psb_trsv_set_trace(psb_trsv_t T, long long* d_trace);
 /* Copies out the level sets (host arrays of levels+1 and n int32): level of a row
  * = 1 + max level of its dependencies; rows level-major, ascending in a level. */
 int psb_trsv_get_levels(psb_trsv_t T, int32_t* h_level_ptr, int32_t* h_level_rows);

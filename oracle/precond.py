@@ -85,21 +85,36 @@ def level_sets(T, lower=True):
 
 
 def trsv_rowwise(T, b, lower=True, unit_diagonal=False):
-    """Row-oriented substitution accumulating in stored column order and
-    dividing by the diagonal last -- the summation order the device kernel
-    uses.  Pure Python: small cases only."""
+    """Row-oriented substitution, the summation order of the device kernels:
+    the dependencies of a row are subtracted in the order in which they become
+    available -- ascending dependency LEVEL (level_sets), ties in stored
+    column order -- product rounded first, and the result is multiplied by the
+    rounded reciprocal of the diagonal last.
+
+    Why this order: a row's newest dependency is then its last operand, so a
+    wavefront solver has one multiply-subtract left when it arrives (in stored
+    order an IC row of the 2-D Laplacian still has ~8 operands to go).  The
+    reference imposes no order of its own here: scipy's spsolve_triangular
+    (ICPreconditioner.py:61,63) hands the factor to SuperLU's column-oriented
+    gstrs.  The reciprocal IS the reference's arithmetic: spsolve_triangular
+    forms ``invdiag = 1/diag`` once and finishes with ``x = y * invdiag``; it
+    never divides on the data path.  Pure Python: small cases only."""
     T = sp.csr_matrix(T)
     n = T.shape[0]
+    level, _, _ = level_sets(T, lower=lower)
     x = np.zeros(n)
     rows = range(n) if lower else range(n - 1, -1, -1)
     for i in rows:
         acc = b[i]
         d = 1.0
+        deps = []
         for jj in range(T.indptr[i], T.indptr[i + 1]):
             j = T.indices[jj]
             if j == i:
                 d = T.data[jj]
             elif (j < i) == lower:
-                acc = acc - T.data[jj] * x[j]
-        x[i] = acc if unit_diagonal else acc / d
+                deps.append((level[j], jj))
+        for _, jj in sorted(deps):
+            acc = acc - T.data[jj] * x[T.indices[jj]]
+        x[i] = acc if unit_diagonal else acc * (1.0 / d)
     return x

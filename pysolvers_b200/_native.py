@@ -52,6 +52,9 @@ SIGNATURES = {
     'psb_trsv_create': (C.c_int, [_i64, _vp, _vp, _vp, C.c_int, C.c_int, _vp, C.POINTER(_vp)]),
     'psb_trsv_destroy': (C.c_int, [_vp]),
     'psb_trsv_info': (C.c_int, [_vp, C.POINTER(_i64)]),
+    'psb_trsv_info2': (C.c_int, [_vp, C.POINTER(_i64)]),
+    'psb_trsv_set_kernel': (C.c_int, [_vp, C.c_int]),
+    'psb_trsv_set_trace': (C.c_int, [_vp, _vp]),
     'psb_trsv_get_levels': (C.c_int, [_vp, _vp, _vp]),
     'psb_trsv_solve': (C.c_int, [_vp, _vp, _vp, _vp]),
     'psb_trsv_error': (C.c_int, [_vp, C.POINTER(_i32)]),

@@ -16,8 +16,10 @@
 //    the solve is coalesced; the diagonal is split out.
 //  * solve: ONE persistent launch.  Warps claim work chunks with an atomic counter.  A chunk
 //    is either 32 consecutive SHORT rows (<= 32 off-diagonal entries): each THREAD owns one
-//    row and accumulates b_i - sum L_ij x_j sequentially IN STORED COLUMN ORDER, dividing by
-//    the diagonal last (the reference's summation order), so the
+//    row and accumulates b_i - sum L_ij x_j sequentially in the order in which the dependencies
+//    become available (ascending level, ties in stored order) and multiplies by the reciprocal
+//    of the diagonal last (scipy's spsolve_triangular forms invdiag = 1/diag once and ends with
+//    x = y * invdiag), so the
 //    dependency that arrives last -- the one nearest the diagonal -- is also the last operand
 //    and everything else is folded in beforehand; or ONE LONG row (exact LU factors of the
 //    AMG coarse level have rows of hundreds of entries) spread over the 32 lanes of the warp
@@ -35,7 +37,10 @@
 #include "prec.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <new>
+#include <utility>
 
 namespace psb {
 
@@ -75,6 +80,7 @@ struct TrsvView {
   const int32_t* grp_rows;
   const int32_t* cols;
   const double* vals;
+  const int32_t* row_cnt;    // off-diagonal entries of item q
   unsigned int* counter;
   int* error;
   int unit_diag;
@@ -102,7 +108,7 @@ trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
     g = __shfl_sync(0xffffffffu, g, 0);
     if (g >= (unsigned int)T.n_groups) return;
     const int64_t base = T.grp_ptr[g];
-    const int len = (int)((T.grp_ptr[g + 1] - base) >> 5);     // entries per lane
+    int len = (int)((T.grp_ptr[g + 1] - base) >> 5);           // entries per lane
     const int rows = T.grp_rows[g];                            // 0: one long row for the warp
     const int item0 = T.grp_item[g];
     const bool is_long = rows == 0;
@@ -115,9 +121,15 @@ trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
       acc = rhs_map ? rhs[rhs_map[row]] : rhs[row];
       d = T.diag[q];
     }
-    const int32_t* cp = T.cols + base + lane;
-    const double*  vp = T.vals + base + lane;
+    // short rows are RIGHT-aligned in their chunk (every row's newest dependency in the last
+    // entry row, for the lock-step walk of the one-CTA kernel): this lane's list starts further in
+    const int width = len;
+    const int first = (is_long || !owner) ? 0 : width - T.row_cnt[item0 + lane];
+    const int32_t* cp = T.cols + base + lane + (int64_t)first * 32;
+    const double*  vp = T.vals + base + lane + (int64_t)first * 32;
     // window of 4 entries: (c0,v0) is the next one to consume
+    len -= first;
+    if (!is_long && !owner) len = 0;
     int k = 0;
     int c0 = -1, c1 = -1, c2 = -1, c3 = -1;
     double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
@@ -169,7 +181,7 @@ trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
             if (lane == 0) {
-              const double r = T.unit_diag ? t : t / d;
+              const double r = T.unit_diag ? t : t * d;       // d = 1 / diagonal
               st_relaxed(x + row, r);
               if (out2 != nullptr) out2[out_map[row]] = r;
             }
@@ -177,7 +189,7 @@ trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
           }
         } else if (fed) {
           if (owner) {
-            const double r = T.unit_diag ? acc : acc / d;   // divide by the diagonal last
+            const double r = T.unit_diag ? acc : acc * d;   // times the reciprocal of the diagonal, last
             st_relaxed(x + row, r);
             if (out2 != nullptr) out2[out_map[row]] = r;
           }
@@ -188,9 +200,29 @@ trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
   }
 }
 
+// PSB_TRSV_KERNEL=grid|cta overrides the analysis (A/B measurements, tests of both kernels)
+static int trsv_kernel_override() {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("PSB_TRSV_KERNEL");
+    v = e == nullptr ? -1 : (strcmp(e, "cta") == 0 ? PSB_TRSV_CTA : (strcmp(e, "grid") == 0 ? PSB_TRSV_GRID : -1));
+  }
+  return v;
+}
+
 int trsv_solve(const psb_trsv* T, const double* rhs, double* x, const int32_t* rhs_map,
                double* out2, const int32_t* out_map, const int* d_skip, cudaStream_t st) {
   if (T->n == 0) return PSB_OK;
+  const int forced = T->forced_kernel >= 0 ? T->forced_kernel : trsv_kernel_override();
+  const int kernel = forced >= 0 ? forced : T->kernel;
+  if (kernel == PSB_TRSV_CTA) {
+    if (T->n_far > 0) {      // far dependencies are polled in the global vector: sentinel first
+      const int fg = (int)std::min<int64_t>((T->n + kBlock * 4 - 1) / (kBlock * 4), (int64_t)sm_count() * 8);
+      trsv_prepare_kernel<<<std::max(fg, 1), kBlock, 0, st>>>(x, T->n, T->d_counter, d_skip);
+      PSB_LAUNCH_CHECK();
+    }
+    return trsv_solve_cta(T, rhs, x, rhs_map, out2, out_map, d_skip, st);
+  }
   const int fill_grid = (int)std::min<int64_t>((T->n + kBlock * 4 - 1) / (kBlock * 4), (int64_t)sm_count() * 8);
   trsv_prepare_kernel<<<std::max(fill_grid, 1), kBlock, 0, st>>>(x, T->n, T->d_counter, d_skip);
   PSB_LAUNCH_CHECK();
@@ -206,7 +238,7 @@ int trsv_solve(const psb_trsv* T, const double* rhs, double* x, const int32_t* r
   int64_t warps_needed = std::min<int64_t>(T->n_groups, chunks_per_level * kLookahead);
   int64_t grid = std::min<int64_t>((int64_t)per_sm * sm_count(), (warps_needed + kWarps - 1) / kWarps);
   TrsvView V{T->n, T->n_groups, T->d_order, T->d_diag, T->d_grp_ptr, T->d_grp_item, T->d_grp_rows,
-             T->d_cols, T->d_vals, T->d_counter, T->d_error, T->unit_diag};
+             T->d_cols, T->d_vals, T->d_row_cnt, T->d_counter, T->d_error, T->unit_diag};
   trsv_solve_kernel<<<(int)std::max<int64_t>(grid, 1), kBlock, 0, st>>>(V, rhs, x, rhs_map, out2, out_map, d_skip);
   PSB_LAUNCH_CHECK();
   return PSB_OK;
@@ -218,7 +250,7 @@ int trsv_solve(const psb_trsv* T, const double* rhs, double* x, const int32_t* r
 static void free_trsv(psb_trsv* T) {
   if (!T) return;
   cudaFree(T->d_order); cudaFree(T->d_grp_ptr); cudaFree(T->d_grp_item); cudaFree(T->d_grp_rows);
-  cudaFree(T->d_cols); cudaFree(T->d_vals); cudaFree(T->d_diag); cudaFree(T->d_counter); cudaFree(T->d_error);
+  cudaFree(T->d_cols); cudaFree(T->d_wcols); cudaFree(T->d_wmeta); cudaFree(T->d_vals); cudaFree(T->d_diag); cudaFree(T->d_row_cnt); cudaFree(T->d_counter); cudaFree(T->d_error);
   delete T;
 }
 
@@ -354,9 +386,12 @@ extern "C" int psb_trsv_create(int64_t n, const int32_t* h_rowptr, const int32_t
       ++T->n_long;
       ++q;
     } else {
+      // a chunk never spans two levels: its rows are independent of each other, so the lanes of
+      // a warp never wait for one another (the one-CTA kernel relies on it)
       int cnt = 0;
       int32_t w = 0;
-      while (q + cnt < n && cnt < 32 && off_count[order[q + cnt]] <= kLongRow) {
+      const int32_t lv = level[order[q]];
+      while (q + cnt < n && cnt < 32 && off_count[order[q + cnt]] <= kLongRow && level[order[q + cnt]] == lv) {
         w = std::max(w, off_count[order[q + cnt]]);
         ++cnt;
       }
@@ -370,22 +405,35 @@ extern "C" int psb_trsv_create(int64_t n, const int32_t* h_rowptr, const int32_t
   std::vector<int32_t> cols((size_t)T->nnz_packed, -1);
   std::vector<double> vals((size_t)T->nnz_packed, 0.0);
   std::vector<double> diag((size_t)n, 1.0);
+  std::vector<int32_t> row_cnt((size_t)n, 0);
   int64_t nnz_off = 0;
+  std::vector<std::pair<int32_t, int32_t>> deps;
   for (int g = 0; g < T->n_groups; ++g) {
     const int nrows = grp_rows[g] == 0 ? 1 : grp_rows[g];
+    const int64_t width = (grp_ptr[g + 1] - grp_ptr[g]) / 32;
     for (int l = 0; l < nrows; ++l) {
       const int64_t q = grp_item[g] + l;
       const int32_t i = order[q];
-      diag[q] = diag_by_row[i];
-      int k = 0;
+      row_cnt[q] = off_count[i];
+      diag[q] = unit_diag ? 1.0 : 1.0 / diag_by_row[i];   // invdiag = 1/diag like scipy (IEEE division, once)
+      // the dependencies of a row in the order in which they become available: ascending level,
+      // ties in stored order -- the newest one is the last operand (oracle.precond.trsv_rowwise)
+      deps.clear();
       for (int32_t p = h_rowptr[i]; p < h_rowptr[i + 1]; ++p) {
         const int32_t j = h_colind[p];
         if (j == i) continue;
         const bool dep = lower ? (j < i) : (j > i);
-        if (!dep) continue;
-        // short rows: entry k of lane l; long row: entry k spread as (k / 32, k % 32)
-        const int64_t pos = grp_rows[g] == 0 ? grp_ptr[g] + k : grp_ptr[g] + (int64_t)k * 32 + l;
-        cols[pos] = j;
+        if (dep) deps.push_back(std::make_pair(level[j], p));
+      }
+      std::sort(deps.begin(), deps.end());
+      int k = 0;
+      for (const auto& dp : deps) {
+        const int32_t p = dp.second;
+        // short rows: lane l, right-aligned (the row's last entry in the chunk's last entry row);
+        // long row: entry k spread as (k / 32, k % 32)
+        const int64_t pos = grp_rows[g] == 0 ? grp_ptr[g] + k
+                                             : grp_ptr[g] + (int64_t)(width - (int64_t)deps.size() + k) * 32 + l;
+        cols[pos] = h_colind[p];
         vals[pos] = h_vals[p];
         ++k; ++nnz_off;
       }
@@ -393,13 +441,69 @@ extern "C" int psb_trsv_create(int64_t n, const int32_t* h_rowptr, const int32_t
   }
   T->nnz_off = nnz_off;
 
+  // ---- the same entries for the shared-memory window kernel: dependencies as positions ------
+  // near (<= near_limit positions back): polled in the window; far: polled in the global vector
+  // Shared memory of the one-CTA kernel = window + 16 staging buffers (384 B per entry row).  A
+  // vector of up to 16 384 rows lives in the window whole; beyond that the window wraps around
+  // and is sized so that a whole chunk of typical length can be staged: 16 384 slots while the
+  // chunks are short, 8 192 slots (26 entries per lane staged) for the longer rows of IC factors.
+  const double mean_len = (double)T->nnz_packed / 32.0 / std::max(T->n_groups, 1);
+  if (n <= kTrsvMaxSlots) { T->wslots = 32; while (T->wslots < n) T->wslots <<= 1; }
+  else T->wslots = mean_len <= 12.0 ? kTrsvMaxSlots : kTrsvMaxSlots / 2;
+  T->stage_len = (int)std::min<int64_t>(32, (kTrsvSmemBudget - 128 - (int64_t)T->wslots * 8) / (kTrsvCtaWarps * 384));
+  const int64_t near_limit = n <= T->wslots ? n : (int64_t)T->wslots - 32 * (2 * kTrsvAhead + 2);
+  // entry encoding: byte offset into the window (near), the always-zero slot right behind the window
+  // (padding), or -(row) - 2 (far)
+  const int32_t zero_off = T->wslots * 8;
+  const int32_t wmask = T->wslots - 1;
+  std::vector<int32_t> wcols((size_t)T->nnz_packed, zero_off);
+  std::vector<int32_t> wmeta((size_t)T->n_groups * 4);
+  {
+    std::vector<int32_t> pos_of((size_t)n);
+    for (int64_t q = 0; q < n; ++q) pos_of[order[q]] = (int32_t)q;
+    for (int g = 0; g < T->n_groups; ++g) {
+      const int nrows = grp_rows[g] == 0 ? 1 : grp_rows[g];
+      const int64_t width = (grp_ptr[g + 1] - grp_ptr[g]) / 32;
+      int has_far = 0;
+      for (int l = 0; l < nrows; ++l) {
+        const int64_t q = grp_item[g] + l;
+        for (int64_t k = 0; k < (grp_rows[g] == 0 ? width * 32 : width); ++k) {
+          const int64_t at = grp_rows[g] == 0 ? grp_ptr[g] + k : grp_ptr[g] + k * 32 + l;
+          const int32_t j = cols[at];
+          if (j < 0) continue;
+          const int64_t dist = q - pos_of[j];
+          T->max_dist = std::max(T->max_dist, dist);
+          if (dist <= near_limit) wcols[at] = (pos_of[j] & wmask) * 8;
+          else { wcols[at] = -j - 2; ++T->n_far; has_far = 1; }
+        }
+      }
+      wmeta[4 * (size_t)g + 0] = (int32_t)(uint32_t)(grp_ptr[g] & 0xffffffffll);
+      wmeta[4 * (size_t)g + 1] = (int32_t)(grp_ptr[g] >> 32);
+      wmeta[4 * (size_t)g + 2] = grp_item[g];
+      wmeta[4 * (size_t)g + 3] = (int32_t)(grp_rows[g] | (has_far << 6) | (width << 7));
+    }
+  }
+  // One CTA wins while the solve is bound by the latency of the dependency chain: few chunks per
+  // level (16 warps cover the wavefront) and the dependencies inside the window.  Wide levels, many
+  // long rows (one chunk each) or many far dependencies have enough parallelism for / need the
+  // whole grid.  Thresholds measured on B200 (profiles/round1d_trsv.md).
+  {
+    const double cpl = (double)T->n_groups / std::max(T->n_levels, 1);
+    const bool narrow = cpl <= kTrsvCtaMaxChunksPerLevel;
+    const bool local = (double)T->n_far <= 0.02 * (double)std::max<int64_t>(T->nnz_off, 1);
+    T->kernel = (narrow && local) ? PSB_TRSV_CTA : PSB_TRSV_GRID;
+  }
+
   cudaError_t e = upload(&T->d_order, order, st);
+  if (e == cudaSuccess) e = upload(&T->d_wcols, wcols, st);
+  if (e == cudaSuccess) e = upload(&T->d_wmeta, wmeta, st);
   if (e == cudaSuccess) e = upload(&T->d_grp_ptr, grp_ptr, st);
   if (e == cudaSuccess) e = upload(&T->d_grp_item, grp_item, st);
   if (e == cudaSuccess) e = upload(&T->d_grp_rows, grp_rows, st);
   if (e == cudaSuccess) e = upload(&T->d_cols, cols, st);
   if (e == cudaSuccess) e = upload(&T->d_vals, vals, st);
   if (e == cudaSuccess) e = upload(&T->d_diag, diag, st);
+  if (e == cudaSuccess) e = upload(&T->d_row_cnt, row_cnt, st);
   if (e == cudaSuccess) e = cudaMalloc((void**)&T->d_counter, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMalloc((void**)&T->d_error, sizeof(int));
   if (e == cudaSuccess) e = cudaMemsetAsync(T->d_error, 0, sizeof(int), st);
@@ -422,6 +526,26 @@ extern "C" int psb_trsv_info(psb_trsv_t T, int64_t info[8]) {
   PSB_REQUIRE(T && info, PSB_ERR_ARG, "psb_trsv_info: NULL argument");
   info[0] = T->n; info[1] = T->n_levels; info[2] = T->nnz_off; info[3] = T->nnz_packed;
   info[4] = T->lower; info[5] = T->unit_diag; info[6] = T->n_groups; info[7] = T->n_long;
+  return PSB_OK;
+}
+
+extern "C" int psb_trsv_info2(psb_trsv_t T, int64_t info[8]) {
+  PSB_REQUIRE(T && info, PSB_ERR_ARG, "psb_trsv_info2: NULL argument");
+  info[0] = T->kernel; info[1] = T->wslots; info[2] = T->n_far; info[3] = T->max_dist;
+  info[4] = T->forced_kernel; info[5] = T->stage_len; info[6] = info[7] = 0;
+  return PSB_OK;
+}
+
+extern "C" int psb_trsv_set_trace(psb_trsv_t T, long long* d_trace) {
+  PSB_REQUIRE(T != nullptr, PSB_ERR_ARG, "psb_trsv_set_trace: NULL argument");
+  T->d_trace = d_trace;
+  return PSB_OK;
+}
+
+extern "C" int psb_trsv_set_kernel(psb_trsv_t T, int kernel) {
+  PSB_REQUIRE(T != nullptr, PSB_ERR_ARG, "psb_trsv_set_kernel: NULL argument");
+  PSB_REQUIRE(kernel >= -1 && kernel <= PSB_TRSV_CTA, PSB_ERR_ARG, "psb_trsv_set_kernel: unknown kernel");
+  T->forced_kernel = kernel;
   return PSB_OK;
 }
 

@@ -180,6 +180,17 @@ class DeviceTrsv:
                     nnz_packed=int(buf[3]), lower=bool(buf[4]), unit_diag=bool(buf[5]),
                     groups=int(buf[6]))
 
+    def info2(self):
+        buf = (C.c_int64 * 8)()
+        nat.check(nat.lib().psb_trsv_info2(self._h, buf), 'psb_trsv_info2')
+        return dict(kernel='cta' if buf[0] == 1 else 'grid', wslots=int(buf[1]), n_far=int(buf[2]),
+                    max_dist=int(buf[3]), forced=int(buf[4]))
+
+    def set_kernel(self, kernel):
+        """'grid' (hand-over through L2), 'cta' (one CTA, shared-memory window) or None (analysis)."""
+        k = {'grid': 0, 'cta': 1, None: -1}[kernel]
+        nat.check(nat.lib().psb_trsv_set_kernel(self._h, k), 'psb_trsv_set_kernel')
+
     def levels(self):
         """(level_ptr, level_rows) as int32 numpy arrays."""
         nlev = self.info()['levels']

@@ -81,6 +81,57 @@ def test_trsv_edge_cases(cuda):
     assert DeviceTrsv(chain, lower=True).info()['levels'] == n
 
 
+def _both_kernels(T, lower, unit, v):
+    """Solve with the grid-wide kernel (hand-over through L2) and with the one-CTA kernel
+    (hand-over through the shared-memory window): the results must be the same bits."""
+    from pysolvers_b200.device import DeviceTrsv, to_device
+    dT = DeviceTrsv(T, lower=lower, unit_diag=unit)
+    out = {}
+    for kern in ('grid', 'cta'):
+        dT.set_kernel(kern)
+        assert dT.info2()['forced'] == {'grid': 0, 'cta': 1}[kern]
+        xs = [dT.solve(to_device(v)).cpu().numpy() for _ in range(2)]    # twice: state carried over
+        dT.check()
+        assert np.array_equal(xs[0], xs[1])
+        out[kern] = xs[0]
+    assert np.array_equal(out['grid'], out['cta'])
+    return dT, out['cta']
+
+
+def test_both_kernels_bit_identical(cuda):
+    from oracle import precond
+    rng = np.random.default_rng(5)
+    cases = []
+    for m in (24, 140):          # 140^2 = 19 600 rows: the window wraps around
+        L, Lt = _factors(m)
+        cases += [(L, True, False), (Lt, False, False)]
+    # random dependencies all over the vector: most of them are "far" (older than the window)
+    n = 40000
+    R = sp.tril(sp.random(n, n, density=3.0 / n, random_state=rng), k=-1) + sp.diags(rng.random(n) + 2.0)
+    cases.append((R.tocsr(), True, False))
+    band = sp.diags([np.full(n - 1, -0.4), np.full(n - 9000, 0.1), np.full(n - 15000, 0.2), np.full(n, 1.5)],
+                    [-1, -9000, -15000, 0]).tocsr()          # a chain with far dependencies on it
+    cases.append((band, True, False))
+    cases.append((band.T.tocsr(), False, False))
+    lu = spla.splu(sp.csc_matrix(_lap(48)))                   # long rows (warp per row)
+    cases += [(lu.L.tocsr(), True, True), (lu.U.tocsr(), False, False)]
+    for T, lower, unit in cases:
+        v = rng.standard_normal(T.shape[0])
+        dT, x = _both_kernels(T, lower, unit, v)
+        i2 = dT.info2()
+        assert T.shape[0] <= i2['wslots'] <= 16384 or i2['wslots'] in (8192, 16384)
+        if T.shape[0] <= 20000 and T is not cases[-1][0] and T is not cases[-2][0]:
+            # thread-per-row chunks follow the row-wise restatement bit for bit (a long row summed by
+            # a whole warp does not: shuffle tree)
+            assert np.array_equal(x, precond.trsv_rowwise(T, v, lower=lower, unit_diagonal=unit))
+        ref = spla.spsolve_triangular(T.tocsr(), v, lower=lower, unit_diagonal=unit)
+        assert np.linalg.norm(x - ref) <= 1e-11 * np.linalg.norm(ref), (T.shape, lower, unit)
+    # the banded case must really exercise the far path
+    from pysolvers_b200.device import DeviceTrsv
+    i2 = DeviceTrsv(band, lower=True).info2()
+    assert i2['n_far'] > 0 and i2['max_dist'] >= 15000
+
+
 def test_ic_apply_vs_reference_golden(cuda, golden):
     from pysolvers_b200.Linear import RightIC
     A = _lap(32)

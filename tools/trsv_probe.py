@@ -1,31 +1,59 @@
-"""Per-level latency of the SpTRSV kernel: a pure chain (one row per level) and an IC factor."""
+"""Per-level latency of the two SpTRSV kernels (grid-wide / one CTA with a shared-memory window)
+on a pure chain, IC factors of the 2-D Laplacian, an ILUT factor pair and a Gauss-Seidel triangle."""
 import os, sys, time
-import numpy as np, scipy.sparse as sp, torch
+import numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spla, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pysolvers_b200.device import DeviceTrsv, to_device
 from oracle import precond
-from pysolvers_b200.problems import fd_laplacian_2d
+from pysolvers_b200.problems import fd_laplacian_2d, load_dh_matrix
 
 
-def bench(T, lower, name, reps=5):
-    dT = DeviceTrsv(T, lower=lower)
+def bench(T, lower, name, unit=False, reps=5):
+    dT = DeviceTrsv(T, lower=lower, unit_diag=unit)
     v = to_device(np.ones(T.shape[0]))
     out = torch.empty_like(v)
-    dT.solve(v, out)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
+    res = {}
+    for kern in ('grid', 'cta'):
+        dT.set_kernel(kern)
         dT.solve(v, out)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    lv = dT.info()['levels']
-    print('%s tune=%s: %.2f ms, %d levels, %.2f us/level' % (name, os.environ.get('PSB_TRSV_TUNE', '0'), ms, lv, 1e3 * ms / lv))
+        torch.cuda.synchronize()
+        dT.check()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            dT.solve(v, out)
+        e1.record()
+        torch.cuda.synchronize()
+        res[kern] = (e0.elapsed_time(e1) / reps, out.clone())
+    assert torch.equal(res['grid'][1], res['cta'][1]), name
+    i, i2 = dT.info(), dT.info2()
+    lv = i['levels']
+    gb = (12 * i['nnz_packed'] + 24 * i['n']) / 1e9
+    print('%-14s n=%8d lev=%6d rows/lev=%7.1f far=%d | grid %8.3f ms %6.2f us/lev | cta %8.3f ms %6.3f us/lev %6.1f GB/s | x%.1f  auto=%s'
+          % (name, i['n'], lv, i['n'] / lv, i2['n_far'], res['grid'][0], 1e3 * res['grid'][0] / lv,
+             res['cta'][0], 1e3 * res['cta'][0] / lv, gb / (res['cta'][0] * 1e-3),
+             res['grid'][0] / res['cta'][0], i2['kernel']), flush=True)
 
 
-n = 20000
-chain = sp.diags([np.full(n - 1, -0.5), np.full(n, 1.5)], [-1, 0]).tocsr()
-bench(chain, True, 'chain20000')
-L, Lt = precond.ic_factor(-fd_laplacian_2d(0.0, 1.0, 256))
-bench(L, True, 'IC256-L')
+which = sys.argv[1:] or ['chain', 'ic128', 'ic256', 'ic512', 'dh15', 'gs512', 'gs2048', 'lu']
+for w in which:
+    if w == 'chain':
+        n = 20000
+        bench(sp.diags([np.full(n - 1, -0.5), np.full(n, 1.5)], [-1, 0]).tocsr(), True, 'chain20000')
+    elif w.startswith('ic'):
+        m = int(w[2:])
+        L, Lt = precond.ic_factor(-fd_laplacian_2d(0.0, 1.0, m))
+        bench(L, True, 'IC%d-L' % m)
+        bench(Lt, False, 'IC%d-Lt' % m)
+    elif w.startswith('dh'):
+        A = load_dh_matrix(int(w[2:]))
+        ilu = spla.spilu(sp.csc_matrix(A), drop_tol=1e-3, fill_factor=15)
+        bench(ilu.L.tocsr(), True, w + '-L', unit=True)
+        bench(ilu.U.tocsr(), False, w + '-U')
+    elif w.startswith('gs'):
+        m = int(w[2:])
+        bench(sp.triu(-fd_laplacian_2d(0.0, 1.0, m)).tocsr(), False, 'GS%d-triu' % m)
+    elif w == 'lu':
+        lu = spla.splu(sp.csc_matrix(-fd_laplacian_2d(0.0, 1.0, 160)))
+        bench(lu.L.tocsr(), True, 'LU160-L', unit=True)
+        bench(lu.U.tocsr(), False, 'LU160-U')
