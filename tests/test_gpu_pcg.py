@@ -130,6 +130,34 @@ def test_pcg_large_properties(cuda):
     assert np.linalg.norm(st2.soln() - 3.0 * st.soln()) <= 1e-6 * np.linalg.norm(st2.soln())
 
 
+def test_full_size_c3_properties(cuda):
+    """BASELINE.json's headline size (2-D 5-point Laplacian, m = 4096, n = 16 777 216) through
+    size-independent properties: the SpMV is bit-identical to scipy's csr_matvec on the whole
+    matrix; the recorded residual norm equals the true residual of the returned iterate; and PCG
+    is exactly homogeneous under a power-of-two scaling of b (every operation scales exactly)."""
+    from pysolvers_b200 import CommonSolverArgs
+    from pysolvers_b200.Linear import PCG
+    from pysolvers_b200.device import DeviceCSR, to_device
+    A = _lap(4096)
+    n = A.shape[0]
+    assert n == 16777216 and A.nnz == 83869696
+    x = np.random.default_rng(3).standard_normal(n)
+    dA = DeviceCSR(A)
+    assert dA.info()['kind'] == 1                               # the TMA-staged STREAM kernel
+    y = dA.matvec(to_device(x)).cpu().numpy()
+    assert np.array_equal(y, A @ x)
+    del dA
+    b = np.ones(n)
+    args = dict(maxiter=60, tau=0.0, failOnMaxiter=False)
+    st, hist = _run(PCG(CommonSolverArgs(**args)).makeSolver(), A, b)
+    assert st.success() and st.iters() == 60 and len(hist) == 60
+    true_r = np.linalg.norm(b - A @ st.soln())
+    assert abs(true_r - hist[-1]) <= 1e-9 * hist[-1]
+    st4, hist4 = _run(PCG(CommonSolverArgs(**args)).makeSolver(), A, 4.0 * b)
+    assert np.array_equal(st4.soln(), 4.0 * st.soln())
+    assert np.array_equal(hist4, 4.0 * hist)
+
+
 @pytest.mark.parametrize('mode', ['persistent', 'fused-kernels', 'kernel-per-phase'])
 def test_pcg_driver_variants_agree(cuda, golden, mode, monkeypatch):
     """The three PCG drivers (one persistent cooperative kernel; SpMV with the direction update

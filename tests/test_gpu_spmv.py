@@ -122,3 +122,17 @@ def test_mvmult_drop_in(cuda):
     A = load_dh_matrix(9)
     x = np.random.default_rng(4).random(A.shape[0])
     assert np.array_equal(mvmult(A, x), A * x)
+
+
+def test_spmv_3d_slab_full_width(cuda):
+    """The 3-D 7-point Laplacian at the per-GPU share of C4 on 8 GPUs (256^3 = 16.8 M rows, 117 M
+    nonzeros, stored order [k, k-m^2, k+m^2, k-m, k+m, k-1, k+1]): bit-identical to scipy."""
+    from pysolvers_b200.device import DeviceCSR, to_device
+    from pysolvers_b200.problems import fd_laplacian_3d
+    A = fd_laplacian_3d(0.0, 1.0, 256)
+    n = A.shape[0]
+    assert n == 256 ** 3 and A.nnz == 7 * n - 6 * 256 ** 2
+    x = np.random.default_rng(11).standard_normal(n)
+    dA = DeviceCSR(A)
+    y = dA.matvec(to_device(x)).cpu().numpy()
+    assert np.array_equal(y, A @ x)
