@@ -141,6 +141,17 @@ int psb_ic_create(psb_trsv_t L, psb_trsv_t Lt, psb_prec_t* out);
  * lower L -- SuperLU.solve (ILUTPreconditioner.py:67,78).  perm arrays: HOST int32. */
 int psb_ilu_create(psb_trsv_t L, psb_trsv_t U, const int32_t* h_perm_r,
                    const int32_t* h_perm_c, void* stream, psb_prec_t* out);
+/* The same exact LU solve with the trailing n - n1 rows of L and U treated as DENSE blocks
+ * whose inverses (row-major (n-n1)^2 fp64, device, kept by the caller) are applied as triangular
+ * matrix-vector products: L = [L11 0; L21 L22], U = [U11 U12; 0 U22]; L11/U11 are factors of
+ * order n1 (unit lower / upper), L21 is (n-n1) x n1 and U12 n1 x (n-n1) CSR; n1 may be 0
+ * (then those four may be NULL).  Replaces the coarsest-level spsolve of the V-cycle
+ * (PySolvers/Linear/VCycleManager.py:34-37): the dense tail of the factors is one dependency
+ * level per row for a sparse triangular solve, and plain HBM streaming as a GEMV. */
+int psb_splitlu_create(int64_t n, int64_t n1, psb_trsv_t L11, psb_trsv_t U11, psb_csr_t L21,
+                       psb_csr_t U12, const double* d_invL22, const double* d_invU22,
+                       const int32_t* h_perm_r, const int32_t* h_perm_c, void* stream,
+                       psb_prec_t* out);
 /* z = M^-1 r (z must not alias r).  Preconditioner.applyRight / applyLeft. */
 int psb_prec_apply(psb_prec_t P, const double* d_r, double* d_z, void* stream);
 int psb_prec_destroy(psb_prec_t P);

@@ -60,6 +60,7 @@ SIGNATURES = {
     'psb_trsv_error': (C.c_int, [_vp, C.POINTER(_i32)]),
     'psb_ic_create': (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     'psb_ilu_create': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    'psb_splitlu_create': (C.c_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     'psb_prec_apply': (C.c_int, [_vp, _vp, _vp, _vp]),
     'psb_prec_destroy': (C.c_int, [_vp]),
     'psb_amg_create': (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dbl, _i32, _i32, _i32, _dbl,

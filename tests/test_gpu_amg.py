@@ -168,3 +168,28 @@ def test_newton_bratu_device_resident(cuda, golden, sm):
     assert rel_err(hist[sel], g[sel]) < 1e-6
     gx = golden[key + '/x']
     assert np.linalg.norm(st.soln().cpu().numpy() - gx) <= 1e-8 * np.linalg.norm(gx)
+
+
+@pytest.mark.parametrize('tail', [0, 7, 300, 100000])
+def test_split_lu_matches_superlu(cuda, tail):
+    """The coarse-level solve: x = Pc U^-1 L^-1 Pr v with the trailing rows of L and U as dense,
+    explicitly inverted blocks must agree with SuperLU.solve (what spsolve does in
+    VCycleManager.py:34-37) to rounding, for every split position incl. all-dense and tail = 1."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from pysolvers_b200.Linear.multigrid import DeviceSplitLU, COARSE_PERMC_SPEC
+    from pysolvers_b200.device import to_device
+    from pysolvers_b200.problems import fd_laplacian_2d
+    rng = np.random.default_rng(4)
+    A = sp.csc_matrix(-fd_laplacian_2d(0.0, 1.0, 40)) + sp.random(1600, 1600, density=0.002, random_state=rng, format='csc')
+    lu = spla.splu(A, permc_spec=COARSE_PERMC_SPEC)
+    S = DeviceSplitLU(lu, tail=max(tail, 1))
+    assert S.n2 == min(max(tail, 1), 1600) and S.n1 + S.n2 == 1600
+    for _ in range(2):
+        v = rng.standard_normal(1600)
+        x = S.apply(to_device(v)).cpu().numpy()
+        ref = lu.solve(v)
+        assert np.linalg.norm(x - ref) <= 1e-12 * np.linalg.norm(ref)
+    if S.n1 > 0:
+        full = DeviceSplitLU(lu, tail=1).levels()
+        assert S.levels()[0] <= full[0] and S.levels()[1] <= full[1]

@@ -157,8 +157,8 @@ def c5(m, gmres_too=False):
         cv = to_device(np.ones(amg.A[0].shape[0]))
         cz = torch.empty_like(cv)
         out['coarse_solve_s'] = time_gpu(lambda: amg.coarse.apply(cv, cz), reps=3, warm=1)
-        out['coarse_levels_L_U'] = [amg.cL.info()['levels'], amg.cU.info()['levels']]
-        out['coarse_long_rows_L_U'] = [amg.cL.info()['groups'], amg.cU.info()['groups']]
+        out['coarse_levels_L11_U11'] = list(amg.coarse.levels())
+        out['coarse_dense_tail_rows'] = amg.coarse.n2
         out['levels'] = [a.shape[0] for a in amg.A]
         if name == 'djac':
             dA, dinv = amg.A[-1], amg.dinv[-1]
