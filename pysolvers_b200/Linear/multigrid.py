@@ -24,7 +24,7 @@ import torch
 
 from .. import _native as nat
 from ..core import CommonSolverArgs, Tab
-from ..device import (DeviceCSR, DevicePrec, DeviceTrsv, current_stream_ptr, ptr,
+from ..device import (DeviceCSR, DevicePrec, DeviceSplitLU, DeviceTrsv, current_stream_ptr, ptr,
                       require_cuda, to_device, to_host)
 from . import amg_setup
 from .base import IterativeLinearSolver, IterativeLinearSolverType
@@ -171,63 +171,6 @@ def SA_coarsen(A, tol=None, lvl=1):
 
 
 COARSE_PERMC_SPEC = 'MMD_AT_PLUS_A'
-# trailing rows of the coarse L / U handled as explicitly inverted dense blocks: doubling the tail
-# roughly halves the levels left for the sparse triangular solves (0.85 us each, twice per solve)
-# and quadruples the GEMV bytes (8 192 rows: 0.27 GB per factor, 45 us) -- 16 384 pays off once
-# the factors have several thousand levels
-COARSE_DENSE_TAIL = 8192
-COARSE_DENSE_TAIL_LARGE = 16384
-COARSE_LARGE_N = 300000
-
-
-class DeviceSplitLU(DevicePrec):
-    """x = Pc U^-1 L^-1 Pr v for a SuperLU factorisation, with the trailing ``tail`` rows of L
-    and U as dense, explicitly inverted blocks (psb_splitlu_create).  With a fill-reducing
-    ordering those rows are the top separators of the elimination tree: an almost dense
-    triangle, one dependency level per row for a sparse triangular solve (at Bratu 1024^2 the
-    leading blocks keep 1 079 of 3 494 levels).  The blocks are well conditioned (cond 20 - 60,
-    measured), the result agrees with SuperLU.solve to 5e-16.  The inverses are formed once
-    on the device (setup; torch.linalg.solve_triangular); the apply is our own kernels."""
-
-    def __init__(self, lu, tail=None):
-        require_cuda()
-        n = int(lu.shape[0])
-        if tail is None:
-            tail = COARSE_DENSE_TAIL_LARGE if n >= COARSE_LARGE_N else COARSE_DENSE_TAIL
-        n2 = min(n, int(tail))
-        n1 = n - n2
-        L = lu.L.tocsr()
-        U = lu.U.tocsr()
-        dev = torch.device('cuda', torch.cuda.current_device())
-        eye = torch.eye(n2, dtype=torch.float64, device=dev)
-        L22 = torch.from_numpy(L[n1:, n1:].toarray()).to(dev)
-        self.invL22 = torch.linalg.solve_triangular(L22, eye, upper=False, unitriangular=True).contiguous()
-        del L22
-        U22 = torch.from_numpy(U[n1:, n1:].toarray()).to(dev)
-        self.invU22 = torch.linalg.solve_triangular(U22, eye, upper=True).contiguous()
-        del U22, eye
-        self.L11 = self.U11 = self.L21 = self.U12 = None
-        if n1 > 0:
-            self.L11 = DeviceTrsv(L[:n1, :n1].tocsr(), lower=True, unit_diag=True)
-            self.U11 = DeviceTrsv(U[:n1, :n1].tocsr(), lower=False)
-            self.L21 = DeviceCSR(L[n1:, :n1].tocsr())
-            self.U12 = DeviceCSR(U[:n1, n1:].tocsr())
-        pr = np.ascontiguousarray(lu.perm_r, dtype=np.int32)
-        pc = np.ascontiguousarray(lu.perm_c, dtype=np.int32)
-        h = C.c_void_p()
-        hd = lambda o: None if o is None else o.handle
-        nat.check(nat.lib().psb_splitlu_create(
-            n, n1, hd(self.L11), hd(self.U11), hd(self.L21), hd(self.U12), ptr(self.invL22),
-            ptr(self.invU22), pr.ctypes.data_as(C.c_void_p), pc.ctypes.data_as(C.c_void_p),
-            current_stream_ptr(), C.byref(h)), 'psb_splitlu_create')
-        super().__init__(h, n, keep=(self.L11, self.U11, self.L21, self.U12, self.invL22, self.invU22))
-        self.n1, self.n2 = n1, n2
-
-    def levels(self):
-        """(levels of L11, levels of U11): what is left for the sparse triangular solves."""
-        if self.L11 is None:
-            return 0, 0
-        return self.L11.info()['levels'], self.U11.info()['levels']
 
 
 class DeviceAMG:

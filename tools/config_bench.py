@@ -81,7 +81,7 @@ def c2():
         v = to_device(b)
         z = torch.empty_like(v)
         apply_s = time_gpu(lambda: dev.apply(v, z), reps=20)
-        infoL, infoU = pre._dL.info(), pre._dU.info()
+        lvL, lvU = dev.levels()
         s = GMRES(CommonSolverArgs(maxiter=30, tau=1e-8), precond=RightILUT()).makeSolver()
         run(s, A, b)
         st, hist, dt = run(s, A, b)
@@ -97,8 +97,8 @@ def c2():
         out.append(dict(config='C2: GMRES(30)+RightILUT, DH-Matrix-%d (n=%d)' % (lev, A.shape[0]),
                         iters=st.iters(), ref_iters=ref['iters'], ilut_setup_cpu_s=setup,
                         gpu_solve_incl_setup_s=dt, gpu_ilut_apply_s=apply_s, cpu_ilut_apply_s=cpu_apply,
-                        levels_L=infoL['levels'], levels_U=infoU['levels'],
-                        us_per_level=1e6 * apply_s / (infoL['levels'] + infoU['levels']),
+                        levels_L11=lvL, levels_U11=lvU, dense_tail_rows=dev.n2,
+                        us_per_level=1e6 * apply_s / max(lvL + lvU, 1),
                         cpu_solve_excl_setup_s=cpu,
                         hist_max_rel_err=float(np.max(np.abs(hist[:k] - ref['hist'][:k]) / ref['hist'][:k]))))
     return out
