@@ -304,6 +304,15 @@ def run_single_gpu(args):
     cpu_rate, cpu_s = cpu_oracle_rate(A, b, cpu_iters)
     cores = blas_threads()
 
+    # ---- configs[2] as named: PCG + incomplete Cholesky (RightIC defaults), at the largest size
+    # whose SuperLU setup fits a bench run (m = 1024; at m = 4096 spilu alone takes ~1.7 h on the host)
+    ic_line = None
+    if os.environ.get('PSB_BENCH_SKIP_IC', '0') != '1':
+        try:
+            ic_line = ic_pcg_leg(int(os.environ.get('PSB_BENCH_IC_M', '1024')))
+        except Exception as exc:                       # never lose the headline line over the side leg
+            ic_line = {'error': repr(exc)[:200]}
+
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1,
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': dev_ms / args.steps,
@@ -344,8 +353,63 @@ def run_single_gpu(args):
                                    % (cpu_iters, n, cpu_s, cores, os.cpu_count())},
         'final_residual': hist_last,
     }
+    if ic_line is not None:
+        line['ic_pcg'] = ic_line
     print(json.dumps(line))
     return 0
+
+
+def ic_pcg_leg(m):
+    """IC-preconditioned PCG to tau = 1e-8 through the public API on the m x m Laplacian; the
+    preconditioner application is timed alone on the device and with scipy on the host."""
+    import torch
+    from oracle import precond
+    from pysolvers_b200 import CommonSolverArgs
+    from pysolvers_b200.Linear import PCG, RightIC
+    from pysolvers_b200.device import to_device
+    from pysolvers_b200.problems import fd_laplacian_2d
+    A = -fd_laplacian_2d(0.0, 1.0, m)
+    n = A.shape[0]
+    b = np.ones(n)
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        pre = RightIC().form(A)
+    setup_s = time.perf_counter() - t0
+    dev = pre.device_prec()
+    v, z = to_device(b), torch.empty(n, dtype=torch.float64, device='cuda')
+    for _ in range(2):
+        dev.apply(v, z)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        dev.apply(v, z)
+    e1.record()
+    torch.cuda.synchronize()
+    apply_ms = e0.elapsed_time(e1) / 5
+    iL, iLt = pre._dL.info(), pre._dLt.info()
+    t0 = time.perf_counter()
+    ref = precond.ic_apply(pre._L, pre._Lt, b)
+    cpu_apply_s = time.perf_counter() - t0
+    err = float(np.linalg.norm(z.cpu().numpy() - ref) / np.linalg.norm(ref))
+    s = PCG(CommonSolverArgs(maxiter=2000, tau=1e-8, showIters=False, showFinal=False), precond=RightIC()).makeSolver()
+    s.precond = pre
+    s.freezePrec()                                    # reuse the factor formed above (PCGSolver.py:92-94)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        st = s.solve(A, b)
+    torch.cuda.synchronize()
+    solve_s = time.perf_counter() - t0
+    levels = iL['levels'] + iLt['levels']
+    return {'workload': 'IC-PCG (RightIC defaults), 2-D 5-point Laplacian m=%d (n=%d), tau=1e-8' % (m, n),
+            'iterations': int(st.iters()), 'success': bool(st.success()),
+            'iter_per_s_e2e': st.iters() / solve_s, 'solve_s': solve_s,
+            'ic_setup_host_s': setup_s, 'nnz_L': int(pre._L.nnz), 'levels_L_plus_Lt': int(levels),
+            'ic_apply_ms': apply_ms, 'us_per_level': 1e3 * apply_ms / levels,
+            'ic_apply_kernel': pre._dL.info2()['kernel'],
+            'ic_apply_algorithmic_GBps': (12 * (iL['nnz_packed'] + iLt['nnz_packed']) + 48 * n) / (apply_ms * 1e-3) / 1e9,
+            'cpu_ic_apply_s': cpu_apply_s, 'apply_rel_err_vs_scipy': err}
 
 
 def main():

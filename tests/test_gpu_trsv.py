@@ -113,6 +113,8 @@ def test_both_kernels_bit_identical(cuda):
                     [-1, -9000, -15000, 0]).tocsr()          # a chain with far dependencies on it
     cases.append((band, True, False))
     cases.append((band.T.tocsr(), False, False))
+    lu2 = spla.splu(sp.csc_matrix(_lap(132)))                 # 17 424 rows: long rows AND a wrapping window
+    cases += [(lu2.L.tocsr(), True, True), (lu2.U.tocsr(), False, False)]
     lu = spla.splu(sp.csc_matrix(_lap(48)))                   # long rows (warp per row)
     cases += [(lu.L.tocsr(), True, True), (lu.U.tocsr(), False, False)]
     for T, lower, unit in cases:
@@ -120,7 +122,7 @@ def test_both_kernels_bit_identical(cuda):
         dT, x = _both_kernels(T, lower, unit, v)
         i2 = dT.info2()
         assert T.shape[0] <= i2['wslots'] <= 16384 or i2['wslots'] in (8192, 16384)
-        if T.shape[0] <= 20000 and T is not cases[-1][0] and T is not cases[-2][0]:
+        if T.shape[0] <= 20000 and all(T is not c[0] for c in cases[-4:]):
             # thread-per-row chunks follow the row-wise restatement bit for bit (a long row summed by
             # a whole warp does not: shuffle tree)
             assert np.array_equal(x, precond.trsv_rowwise(T, v, lower=lower, unit_diagonal=unit))
