@@ -64,6 +64,11 @@ long long   psb_launch_count(void);
 int psb_csr_create(int64_t n_rows, int64_t n_cols, int64_t nnz,
                    const int32_t* d_rowptr, const int32_t* d_colind,
                    const double* d_vals, void* stream, psb_csr_t* out);
+/* Process-wide option for the matrices created afterwards: keep a second copy of the column
+ * indices of banded matrices as 16-bit distances from the diagonal (10 instead of 12 bytes per
+ * entry in the STREAM kernels; bit-identical results).  Off by default: measured gain 4 % on the
+ * stand-alone SpMV, none in the persistent PCG kernel (profiles/round1f_notes.md). */
+int psb_csr_set_cols16(int enable);
 int psb_csr_destroy(psb_csr_t A);
 /* info[0]=kernel kind, [1]=max row length, [2]=max nnz per 256-row tile,
  * [3]=rows per tile, [4]=vector width (VECTOR kind), [5]=max grid size,
@@ -94,6 +99,16 @@ int psb_jacobi_sweep(psb_csr_t A, const double* d_dinv, double omega,
  * PCGSolver.py:86,102,125,134) */
 int psb_dot(int64_t n, const double* d_x, const double* d_y, double* d_out,
             void* stream);
+
+/* --------------------------------------------- input generators (device) -- */
+/* The finite-difference Laplacians of the benchmark configurations assembled directly in HBM
+ * (examples/FDLaplacian2D.py:5-23 and its 7-point 3-D extension): CSR rows [row_lo, row_hi) of the
+ * m^dim grid matrix with the reference's stored column order and global column numbers; values
+ * `diag` on the diagonal and `off` elsewhere.  psb_stencil_nnz sizes colind / vals (rowptr needs
+ * row_hi - row_lo + 1 entries); -1 on bad arguments. */
+int64_t psb_stencil_nnz(int dim, int64_t m, int64_t row_lo, int64_t row_hi);
+int psb_stencil_fill(int dim, int64_t m, int64_t row_lo, int64_t row_hi, double diag, double off,
+                     int32_t* d_rowptr, int32_t* d_colind, double* d_vals, void* stream);
 
 /* ---------------------------------------------- sparse triangular solves -- */
 /* Level analysis + repacking of a triangular CSR factor given in HOST memory (the

@@ -40,6 +40,7 @@ SIGNATURES = {
     'psb_last_error': (C.c_char_p, []),
     'psb_launch_count': (C.c_longlong, []),
     'psb_csr_create': (C.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    'psb_csr_set_cols16': (C.c_int, [C.c_int]),
     'psb_csr_destroy': (C.c_int, [_vp]),
     'psb_csr_info': (C.c_int, [_vp, C.POINTER(_i64)]),
     'psb_csr_set_kind': (C.c_int, [_vp, C.c_int]),
@@ -49,6 +50,8 @@ SIGNATURES = {
     'psb_spmv_add': (C.c_int, [_vp, _vp, _vp, _vp]),
     'psb_jacobi_sweep': (C.c_int, [_vp, _vp, _dbl, _vp, _vp, _vp, _vp]),
     'psb_dot': (C.c_int, [_i64, _vp, _vp, _vp, _vp]),
+    'psb_stencil_nnz': (_i64, [C.c_int, _i64, _i64, _i64]),
+    'psb_stencil_fill': (C.c_int, [C.c_int, _i64, _i64, _i64, _dbl, _dbl, _vp, _vp, _vp, _vp]),
     'psb_trsv_create': (C.c_int, [_i64, _vp, _vp, _vp, C.c_int, C.c_int, _vp, C.POINTER(_vp)]),
     'psb_trsv_destroy': (C.c_int, [_vp]),
     'psb_trsv_info': (C.c_int, [_vp, C.POINTER(_i64)]),

@@ -76,7 +76,7 @@ __device__ __forceinline__ void mega_push_r(const MegaParams& P, long long i, do
       P.push_r[k][i - P.push_off[k]] = v;
 }
 
-template <int MINB>
+template <int MINB, bool C16>
 __global__ void __launch_bounds__(kBlock, MINB)
 pcg_mega_kernel(const MegaParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -125,7 +125,7 @@ pcg_mega_kernel(const MegaParams P) {
         ea.pp_off[k] = P.push_off[k]; ea.pp_cnt[k] = P.push_cnt[k]; ea.pp_remote[k] = P.push_p[it & 1][k];
       }
       acc = 0.0;
-      bulk_pass<EPI_DOT_PUP, 1>(P.A, P.r, P.Ap, ea, beta, pipe, acc);
+      bulk_pass<EPI_DOT_PUP, 1, C16>(P.A, P.r, P.Ap, ea, beta, pipe, acc);
       const double pAp = mega_allreduce(P, acc, e++, scratch, false, 0ull);
       if (pAp == 0.0) { status = PSB_BREAKDOWN_PAP; k_final = it; break; }     // :114-115
       const double alpha = rr_old / pAp;                                         // :118
@@ -195,7 +195,7 @@ void pcg_mega_caps(const psb_csr* A, int* cap_v, int* cap_c, size_t* smem) {
   *smem = 2 * ((size_t)*cap_v * 8 + (size_t)*cap_c * 4 + (size_t)(kBlock + 4) * 4);
 }
 
-template <int MINB>
+template <int MINB, bool C16>
 static int mega_launch_t(const MegaParams& P, cudaStream_t stream) {
   int cv, cc;
   size_t smem;
@@ -204,8 +204,8 @@ static int mega_launch_t(const MegaParams& P, cudaStream_t stream) {
   static thread_local size_t cached_smem = 0;
   if (per_sm == 0 || cached_smem != smem) {
     if (smem > 48 * 1024)
-      PSB_CUDA(cudaFuncSetAttribute(pcg_mega_kernel<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_mega_kernel<MINB>, kBlock, smem));
+      PSB_CUDA(cudaFuncSetAttribute(pcg_mega_kernel<MINB, C16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_mega_kernel<MINB, C16>, kBlock, smem));
     if (per_sm < 1) { set_error("pcg_mega_launch: kernel does not fit on an SM"); return PSB_ERR_UNSUPP; }
     cached_smem = smem;
   }
@@ -215,7 +215,7 @@ static int mega_launch_t(const MegaParams& P, cudaStream_t stream) {
   grid = std::min<long long>(grid, (long long)sm_count() * 16);       // partial buffers hold this many
   MegaParams Q = P;
   void* args[] = {(void*)&Q};
-  PSB_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_mega_kernel<MINB>, dim3((unsigned)grid), dim3(kBlock),
+  PSB_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_mega_kernel<MINB, C16>, dim3((unsigned)grid), dim3(kBlock),
                                        args, smem, stream));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return PSB_OK;
@@ -229,9 +229,14 @@ int pcg_mega_launch(const MegaParams& P, cudaStream_t stream) {
     minb = env ? atoi(env) : 5;       // measured best on B200: 5 CTAs/SM, 48 registers, no spills
     if (minb < 4 || minb > 6) minb = 5;
   }
-  if (minb == 6) return mega_launch_t<6>(P, stream);
-  if (minb == 4) return mega_launch_t<4>(P, stream);
-  return mega_launch_t<5>(P, stream);
+  if (P.A.colind16 != nullptr) {
+    if (minb == 6) return mega_launch_t<6, true>(P, stream);
+    if (minb == 4) return mega_launch_t<4, true>(P, stream);
+    return mega_launch_t<5, true>(P, stream);
+  }
+  if (minb == 6) return mega_launch_t<6, false>(P, stream);
+  if (minb == 4) return mega_launch_t<4, false>(P, stream);
+  return mega_launch_t<5, false>(P, stream);
 }
 
 }  // namespace psb

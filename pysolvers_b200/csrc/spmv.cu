@@ -60,6 +60,24 @@ __global__ void csr_stats_kernel(const int* __restrict__ rowptr, int64_t n_rows,
   atomicMax(&stats[2], m_t512);
 }
 
+static int g_cols16 = -1;     // 16-bit column distances for banded matrices: -1 ask PSB_SPMV_C16, 0 off, 1 on
+
+// colind[k] - row as int16 for every entry; *fail is raised when one does not fit
+__global__ void csr_delta16_kernel(const int* __restrict__ rowptr, const int* __restrict__ colind,
+                                   int64_t n_rows, short* __restrict__ out, int* __restrict__ fail) {
+  bool bad = false;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_rows;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int a = rowptr[i], b = rowptr[i + 1];
+    for (int k = a; k < b; ++k) {
+      const long long d = (long long)colind[k] - i;
+      if (d < -32768 || d > 32767) bad = true;
+      out[k] = (short)d;
+    }
+  }
+  if (bad) *fail = 1;
+}
+
 template <int EPI>
 __device__ __forceinline__ void finish_dot(double acc, const psb_csr A, const EpiArgs& ea,
                                            double* scratch) {
@@ -176,7 +194,7 @@ spmv_stream_kernel(const psb_csr A, const double* __restrict__ x, double* __rest
 // ---------------------------------------------------------------------------
 // STREAM kernel, bulk-async staged (default): thin wrapper over bulk_pass (spmv_bulk.cuh)
 // ---------------------------------------------------------------------------
-template <int EPI, int RPT>
+template <int EPI, int RPT, bool C16>
 __global__ void __launch_bounds__(kBlock)
 spmv_bulk_kernel(const psb_csr A, const double* x, double* y, const EpiArgs ea,
                  const int* __restrict__ d_skip, int cap_v, int cap_c) {
@@ -189,7 +207,7 @@ spmv_bulk_kernel(const psb_csr A, const double* x, double* y, const EpiArgs ea,
   BulkPipe P;
   bulk_pipe_init(P, smem_raw, full, cap_v, cap_c);
   double acc = 0.0;
-  bulk_pass<EPI, RPT>(A, x, y, ea, beta, P, acc);
+  bulk_pass<EPI, RPT, C16>(A, x, y, ea, beta, P, acc);
   finish_dot<EPI>(acc, A, ea, scratch);
 }
 
@@ -272,9 +290,9 @@ static inline void bulk_caps(const psb_csr* A, int rpt, int* cap_v, int* cap_c, 
   *smem = 2 * stage;
 }
 
-template <int EPI, int RPT>
-static int launch_bulk(const psb_csr* A, const double* x, double* y, const EpiArgs& ea,
-                       const int* d_skip, cudaStream_t st) {
+template <int EPI, int RPT, bool C16>
+static int launch_bulk_t(const psb_csr* A, const double* x, double* y, const EpiArgs& ea,
+                         const int* d_skip, cudaStream_t st) {
   constexpr int R = kBlock * RPT;
   int cap_v, cap_c;
   size_t smem;
@@ -283,14 +301,21 @@ static int launch_bulk(const psb_csr* A, const double* x, double* y, const EpiAr
   static thread_local size_t cached_smem = 0;
   const int64_t tiles = (A->n_rows + R - 1) / R;
   if (per_sm == 0 || cached_smem != smem) {
-    int rc = occupancy_per_sm(spmv_bulk_kernel<EPI, RPT>, smem, &per_sm);
+    int rc = occupancy_per_sm(spmv_bulk_kernel<EPI, RPT, C16>, smem, &per_sm);
     if (rc != PSB_OK) return rc;
     cached_smem = smem;
   }
-  spmv_bulk_kernel<EPI, RPT><<<grid_for(per_sm, tiles, A->max_grid), kBlock, smem, st>>>(
+  spmv_bulk_kernel<EPI, RPT, C16><<<grid_for(per_sm, tiles, A->max_grid), kBlock, smem, st>>>(
       *A, x, y, ea, d_skip, cap_v, cap_c);
   PSB_LAUNCH_CHECK();
   return PSB_OK;
+}
+
+template <int EPI, int RPT>
+static int launch_bulk(const psb_csr* A, const double* x, double* y, const EpiArgs& ea,
+                       const int* d_skip, cudaStream_t st) {
+  if (A->colind16 != nullptr) return launch_bulk_t<EPI, RPT, true>(A, x, y, ea, d_skip, st);
+  return launch_bulk_t<EPI, RPT, false>(A, x, y, ea, d_skip, st);
 }
 
 template <int EPI, int W>
@@ -405,8 +430,8 @@ extern "C" int psb_csr_create(int64_t n_rows, int64_t n_cols, int64_t nnz,
   A->rowptr = d_rowptr; A->colind = d_colind; A->vals = d_vals;
   A->vec_loads = aligned16(d_colind) && aligned16(d_vals);
   A->max_grid = sm_count() * 16;
-  A->partials = nullptr; A->ticket = nullptr;
-  int h_stats[3] = {0, 0, 0};
+  A->partials = nullptr; A->ticket = nullptr; A->colind16 = nullptr;
+  int h_stats[4] = {0, 0, 0, 0};        // longest row, fullest 256- / 512-row tile, "a column delta does not fit 16 bits"
   int* d_stats = nullptr;
   cudaError_t e = cudaMalloc(&A->partials, sizeof(double) * A->max_grid);
   if (e == cudaSuccess) e = cudaMalloc(&A->ticket, sizeof(unsigned int));
@@ -418,6 +443,27 @@ extern "C" int psb_csr_create(int64_t n_rows, int64_t n_cols, int64_t nnz,
     csr_stats_kernel<<<grid, kBlock, 0, st>>>(d_rowptr, n_rows, d_stats);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     e = cudaPeekAtLastError();
+    // OPTIONAL (psb_csr_set_cols16 / PSB_SPMV_C16=1, off by default).  Banded matrices
+    // (|col - row| < 2^15, e.g. every 2-D stencil up to 32 767 columns per grid line): a second
+    // copy of the column indices as 16-bit distances from the diagonal lets the STREAM kernels
+    // move 10 instead of 12 bytes per entry.  Built speculatively in the same stream, judged with
+    // the statistics (one synchronisation), dropped if a distance does not fit or another kernel
+    // is chosen.  Measured at C3 (profiles/round1f_notes.md): 12.5 % fewer bytes buy 4 % on the
+    // stand-alone SpMV and nothing in the persistent PCG kernel, and the extra pass costs 0.8 %
+    // end to end -- at 93 - 97 % of the copy bandwidth the kernels are no longer purely DRAM-bound.
+    if (g_cols16 < 0) { const char* v = getenv("PSB_SPMV_C16"); g_cols16 = (v && atoi(v) != 0) ? 1 : 0; }
+    if (e == cudaSuccess && g_cols16 > 0 && n_rows == n_cols && nnz >= (1 << 16) && A->vec_loads &&
+        nnz <= 32 * n_rows) {
+      short* d16 = nullptr;
+      if (cudaMalloc(&d16, sizeof(short) * (size_t)nnz) == cudaSuccess) {
+        csr_delta16_kernel<<<grid, kBlock, 0, st>>>(d_rowptr, d_colind, n_rows, d16, d_stats + 3);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaPeekAtLastError();
+        A->colind16 = d16;
+      } else {
+        (void)cudaGetLastError();      // no memory for the copy: carry on with 32-bit indices
+      }
+    }
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -426,6 +472,7 @@ extern "C" int psb_csr_create(int64_t n_rows, int64_t n_cols, int64_t nnz,
     set_error("psb_csr_create: %s", cudaGetErrorString(e));
     if (A->partials) cudaFree(A->partials);
     if (A->ticket) cudaFree(A->ticket);
+    if (A->colind16) cudaFree((void*)A->colind16);
     delete A;
     return PSB_ERR_CUDA;
   }
@@ -433,7 +480,16 @@ extern "C" int psb_csr_create(int64_t n_rows, int64_t n_cols, int64_t nnz,
   A->max_tile_nnz[0] = h_stats[1];
   A->max_tile_nnz[1] = h_stats[2];
   choose_kernel(A);
+  if (A->colind16 != nullptr && (h_stats[3] != 0 || A->kind != PSB_SPMV_STREAM)) {
+    cudaFree((void*)A->colind16);
+    A->colind16 = nullptr;
+  }
   *out = A;
+  return PSB_OK;
+}
+
+extern "C" int psb_csr_set_cols16(int enable) {
+  g_cols16 = enable ? 1 : 0;
   return PSB_OK;
 }
 
@@ -441,6 +497,7 @@ extern "C" int psb_csr_destroy(psb_csr_t A) {
   if (A == nullptr) return PSB_OK;
   if (A->partials) cudaFree(A->partials);
   if (A->ticket) cudaFree(A->ticket);
+  if (A->colind16) cudaFree((void*)A->colind16);
   delete A;
   return PSB_OK;
 }
@@ -453,7 +510,7 @@ extern "C" int psb_csr_info(psb_csr_t A, int64_t info[8]) {
   info[3] = (int64_t)kBlock * A->rpt;
   info[4] = A->vec_width;
   info[5] = A->max_grid;
-  info[6] = A->vec_loads ? 1 : 0;
+  info[6] = (A->vec_loads ? 1 : 0) | (A->colind16 ? 2 : 0);
   info[7] = A->max_tile_nnz[1];
   return PSB_OK;
 }

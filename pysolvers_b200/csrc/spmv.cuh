@@ -7,6 +7,8 @@ struct psb_csr {
   int64_t row_off;      // row-range views: vectors are indexed at row_off + row (rowptr is pre-offset)
   const int*    rowptr;
   const int*    colind;
+  const short*  colind16;   // owned, nullable: colind[k] - (row_off + row) as int16 when every |delta| fits
+                            // (banded matrices): the STREAM kernels then stream 10 instead of 12 bytes per entry
   const double* vals;
   int  kind;            // PSB_SPMV_STREAM | PSB_SPMV_VECTOR
   int  max_row;         // longest row

@@ -105,7 +105,7 @@ __device__ __forceinline__ void bulk_pipe_init(BulkPipe& P, unsigned char* smem,
 // One pass over all tiles of A assigned to this CTA (grid-stride).  `beta` is used by
 // EPI_DOT_PUP only.  x may have been written earlier by this same kernel (persistent PCG):
 // it is read through the coherent path.
-template <int EPI, int RPT>
+template <int EPI, int RPT, bool C16 = false>
 __device__ __forceinline__ void bulk_pass(const psb_csr& A, const double* x, double* y,
                                           const EpiArgs& ea, const double beta, BulkPipe& P,
                                           double& acc) {
@@ -124,7 +124,8 @@ __device__ __forceinline__ void bulk_pass(const psb_csr& A, const double* x, dou
   };
   bool waited = (ea.wait_n == 0);
   const int nnz_v_lim = (int)(A.nnz & ~(int64_t)1);          // bulk copies stop at the last
-  const int nnz_c_lim = (int)(A.nnz & ~(int64_t)3);          // whole 16-byte chunk of each array
+  constexpr int kCA = C16 ? 7 : 3;                           // column entries per 16 bytes, minus 1
+  const int nnz_c_lim = (int)(A.nnz & ~(int64_t)kCA);        // whole 16-byte chunk of each array
   const int rp_lim = (int)((A.n_rows + 1) & ~(int64_t)3);
 
   auto stage_vals = [&](int st) { return reinterpret_cast<double*>(smem_raw + st * stage_bytes); };
@@ -138,17 +139,20 @@ __device__ __forceinline__ void bulk_pass(const psb_csr& A, const double* x, dou
   auto issue = [&](int64_t lt, int st, int s, int e) {
     const int64_t row0 = phys(lt) * R;
     const int nr = (int)min((int64_t)R, A.n_rows - row0);
-    const int v0 = s & ~1, c0 = s & ~3;
+    const int v0 = s & ~1, c0 = s & ~kCA;
     const int v1 = min((e + 1) & ~1, nnz_v_lim);
-    const int c1 = min((e + 3) & ~3, nnz_c_lim);
+    const int c1 = min((e + kCA) & ~kCA, nnz_c_lim);
     const int r1 = (int)min((int64_t)((nr + 1 + 3) & ~3), (int64_t)rp_lim - row0);
     const uint32_t bv = v1 > v0 ? (uint32_t)(v1 - v0) * 8u : 0u;
-    const uint32_t bc = c1 > c0 ? (uint32_t)(c1 - c0) * 4u : 0u;
+    const uint32_t bc = c1 > c0 ? (uint32_t)(c1 - c0) * (C16 ? 2u : 4u) : 0u;
     const uint32_t br = r1 > 0 ? (uint32_t)r1 * 4u : 0u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&full[st], bv + bc + br);
     if (bv) bulk_g2s(stage_vals(st), A.vals + v0, bv, &full[st], pol);
-    if (bc) bulk_g2s(stage_cols(st), A.colind + c0, bc, &full[st], pol);
+    if (bc) {
+      if (C16) bulk_g2s(stage_cols(st), A.colind16 + c0, bc, &full[st], pol);
+      else     bulk_g2s(stage_cols(st), A.colind + c0, bc, &full[st], pol);
+    }
     if (br) bulk_g2s(stage_rp(st), A.rowptr + row0, br, &full[st], pol);
   };
   auto tile_bounds = [&](int64_t lt, int& s, int& e) {
@@ -200,14 +204,20 @@ __device__ __forceinline__ void bulk_pass(const psb_csr& A, const double* x, dou
         double* svw = stage_vals(st);
         int*    scw = stage_cols(st);
         for (int i = max(s0, nnz_v_lim) + tid; i < e0; i += kBlock) svw[i - (s0 & ~1)] = A.vals[i];
-        for (int i = max(s0, nnz_c_lim) + tid; i < e0; i += kBlock) scw[i - (s0 & ~3)] = A.colind[i];
+        if (C16) {
+          short* scw16 = reinterpret_cast<short*>(scw);
+          for (int i = max(s0, nnz_c_lim) + tid; i < e0; i += kBlock) scw16[i - (s0 & ~kCA)] = A.colind16[i];
+        } else {
+          for (int i = max(s0, nnz_c_lim) + tid; i < e0; i += kBlock) scw[i - (s0 & ~kCA)] = A.colind[i];
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
       }
     }
 
     const int s = rp[0];
-    const int offv = s & ~1, offc = s & ~3;
+    const int offv = s & ~1, offc = s & ~kCA;
+    const short* sc16 = reinterpret_cast<const short*>(sc);
     // EPI_DOT_PUP: the tile's own rows of p = x + beta * pold are formed once, kept in shared
     // memory and stored; gathers that fall inside the tile's row window (the k, k-1, k+1 entries
     // of a stencil) read them back instead of two global gathers each.
@@ -247,8 +257,10 @@ __device__ __forceinline__ void bulk_pass(const psb_csr& A, const double* x, dou
         const int a = rp[lr], b = rp[lr + 1];
         double sum = 0.0;
         int k = a;
+        const int rabs = (int)(A.row_off + row0 + lr);  // C16: columns are stored relative to the row
+        auto col = [&](int kk) -> int { return C16 ? rabs + (int)sc16[kk - offc] : sc[kk - offc]; };
         for (; k + 4 <= b; k += 4) {                   // 4 independent gathers in flight
-          const int c0 = sc[k - offc], c1 = sc[k + 1 - offc], c2 = sc[k + 2 - offc], c3 = sc[k + 3 - offc];
+          const int c0 = col(k), c1 = col(k + 1), c2 = col(k + 2), c3 = col(k + 3);
           const double x0 = gather(c0), x1 = gather(c1), x2 = gather(c2), x3 = gather(c3);
           sum += sv[k - offv] * x0;
           sum += sv[k + 1 - offv] * x1;
@@ -256,7 +268,7 @@ __device__ __forceinline__ void bulk_pass(const psb_csr& A, const double* x, dou
           sum += sv[k + 3 - offv] * x3;
         }
         for (; k < b; ++k) {
-          sum += sv[k - offv] * gather(sc[k - offc]);
+          sum += sv[k - offv] * gather(col(k));
         }
         if constexpr (EPI == EPI_DOT_PUP) {
           y[win0 + lr] = sum;

@@ -112,7 +112,7 @@ class DeviceCSR:
         nat.check(nat.lib().psb_csr_info(self._h, buf), 'psb_csr_info')
         return dict(kind=int(buf[0]), max_row=int(buf[1]), max_tile_nnz=int(buf[2]),
                     rows_per_tile=int(buf[3]), vec_width=int(buf[4]),
-                    max_grid=int(buf[5]), vec_loads=bool(buf[6]),
+                    max_grid=int(buf[5]), vec_loads=bool(buf[6] & 1), cols16=bool(buf[6] & 2),
                     max_tile_nnz_512=int(buf[7]))
 
     def set_kind(self, kind):

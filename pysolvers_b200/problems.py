@@ -77,6 +77,34 @@ def fd_laplacian_3d(a, b, m, row_lo=0, row_hi=None):
     return _stencil_csr(n, k, cols, vals, valid)
 
 
+def device_fd_laplacian(dim, a, b, m, negate=False, row_lo=0, row_hi=None):
+    """The same matrices as ``fd_laplacian_2d`` (dim = 2; ``negate`` gives the SPD
+    ``-FDLaplacian2D`` of examples/FDBratu2D.py:15) and ``fd_laplacian_3d`` (dim = 3),
+    bit for bit, assembled directly in HBM (psb_stencil_fill): returns a DeviceCSR that the
+    solvers accept in place of the scipy matrix -- no host assembly, no upload."""
+    import torch
+    from . import _native as nat
+    from .device import DeviceCSR, current_stream_ptr, ptr, require_cuda
+    require_cuda()
+    n = m ** dim
+    row_hi = n if row_hi is None else row_hi
+    h = np.abs(b - a) / np.double(m + 1)
+    if dim == 2:
+        diag, off = -4.0 / h / h, 1.0 / h / h
+    else:
+        diag, off = 6.0 / h / h, -1.0 / h / h
+    if negate:
+        diag, off = -diag, -off
+    nnz = int(nat.lib().psb_stencil_nnz(dim, m, row_lo, row_hi))
+    assert nnz >= 0
+    indptr = torch.empty(row_hi - row_lo + 1, dtype=torch.int32, device='cuda')
+    indices = torch.empty(nnz, dtype=torch.int32, device='cuda')
+    data = torch.empty(nnz, dtype=torch.float64, device='cuda')
+    nat.check(nat.lib().psb_stencil_fill(dim, m, row_lo, row_hi, float(diag), float(off), ptr(indptr),
+                                         ptr(indices), ptr(data), current_stream_ptr()), 'psb_stencil_fill')
+    return DeviceCSR(indptr=indptr, indices=indices, data=data, shape=(row_hi - row_lo, n))
+
+
 class FDBratu2D:
     """-Lap(u) - alpha*exp(-u) = 0 on (-1,1)^2 (examples/FDBratu2D.py:10-29)."""
 

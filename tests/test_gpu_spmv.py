@@ -136,3 +136,82 @@ def test_spmv_3d_slab_full_width(cuda):
     dA = DeviceCSR(A)
     y = dA.matvec(to_device(x)).cpu().numpy()
     assert np.array_equal(y, A @ x)
+
+
+def test_spmv_16bit_column_deltas(cuda):
+    """Banded matrices get a second copy of the column indices as 16-bit distances from the
+    diagonal (10 instead of 12 bytes per entry in the STREAM kernels); the result stays
+    bit-identical to scipy.  Distances of -32768 ... 32767 fit, 32768 does not."""
+    from pysolvers_b200 import _native as nat
+    from pysolvers_b200.device import DeviceCSR, to_device
+    rng = np.random.default_rng(21)
+    n = 120000
+    nat.check(nat.lib().psb_csr_set_cols16(1), 'psb_csr_set_cols16')      # optional path, off by default
+    try:
+        _cols16_cases(rng, n, DeviceCSR, to_device)
+    finally:
+        nat.check(nat.lib().psb_csr_set_cols16(0), 'psb_csr_set_cols16')
+    A = sp.diags([np.ones(n - 1), np.ones(n)], [-1, 0], shape=(n, n), format='csr')
+    assert not DeviceCSR(A).info()['cols16']
+
+
+def _cols16_cases(rng, n, DeviceCSR, to_device):
+
+    def banded(offsets):
+        diags = [rng.standard_normal(n - abs(o)) for o in offsets]
+        return sp.diags(diags, offsets, shape=(n, n), format='csr')
+
+    for offsets, want in (((0, -1, 1, -300, 300), True),
+                          ((0, -32768, 32767, 5), True),
+                          ((0, 32768, -7), False),
+                          ((0, -32769, 2), False)):
+        A = banded(offsets)
+        dA = DeviceCSR(A)
+        assert dA.info()['kind'] == 1
+        assert dA.info()['cols16'] == want, offsets
+        x = rng.standard_normal(n)
+        y = dA.matvec(to_device(x)).cpu().numpy()
+        assert np.array_equal(y, A @ x), offsets
+    # odd sizes / unaligned tails of the 16-bit staging: n and nnz not multiples of 8
+    for n2 in (65537, 70001):
+        A = sp.diags([rng.standard_normal(n2 - 3), rng.standard_normal(n2), rng.standard_normal(n2 - 1)],
+                     [-3, 0, 1], shape=(n2, n2), format='csr')
+        dA = DeviceCSR(A)
+        assert dA.info()['cols16']
+        x = rng.standard_normal(n2)
+        assert np.array_equal(dA.matvec(to_device(x)).cpu().numpy(), A @ x)
+
+
+def test_device_generators_bit_identical(cuda):
+    """The Laplacians assembled in HBM (psb_stencil_fill) are the host generators' matrices bit for
+    bit -- row pointers, stored column order, values -- for whole grids and row slabs, and a solver
+    takes the DeviceCSR in place of the scipy matrix."""
+    import contextlib
+    import io
+    from pysolvers_b200 import CommonSolverArgs
+    from pysolvers_b200.Linear import PCG
+    from pysolvers_b200.problems import device_fd_laplacian, fd_laplacian_2d, fd_laplacian_3d
+
+    def same(dA, A):
+        B = dA.to_scipy()
+        assert B.shape == A.shape
+        assert np.array_equal(B.indptr, A.indptr) and np.array_equal(B.indices, A.indices)
+        assert np.array_equal(B.data, A.data)
+
+    for m in (1, 2, 7, 300):
+        same(device_fd_laplacian(2, 0.0, 1.0, m), fd_laplacian_2d(0.0, 1.0, m))
+    same(device_fd_laplacian(2, -1.0, 1.0, 33, negate=True), -fd_laplacian_2d(-1.0, 1.0, 33))
+    same(device_fd_laplacian(2, 0.0, 1.0, 50, row_lo=1203, row_hi=2077), fd_laplacian_2d(0.0, 1.0, 50, 1203, 2077))
+    for m in (1, 2, 20):
+        same(device_fd_laplacian(3, 0.0, 1.0, m), fd_laplacian_3d(0.0, 1.0, m))
+    same(device_fd_laplacian(3, 0.0, 1.0, 16, row_lo=777, row_hi=3001), fd_laplacian_3d(0.0, 1.0, 16, 777, 3001))
+
+    A = -fd_laplacian_2d(0.0, 1.0, 48)
+    dA = device_fd_laplacian(2, 0.0, 1.0, 48, negate=True)
+    b = np.ones(48 * 48)
+    out = []
+    for M in (A, dA):
+        s = PCG(CommonSolverArgs(maxiter=500, tau=1e-8)).makeSolver()
+        with contextlib.redirect_stdout(io.StringIO()):
+            out.append(s.solve(M, b))
+    assert out[0].iters() == out[1].iters() and np.array_equal(out[0].soln(), out[1].soln())

@@ -57,3 +57,20 @@ def test_product_does_not_import_oracle():
             if f.endswith(('.py', '.cu', '.cuh')):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
+
+
+def test_stencil_prefix_matches_host_generators():
+    """psb_stencil_nnz (host arithmetic of the device generator) against the row pointers of the
+    numpy generators, which are pinned bit-exactly to the reference's (test_oracle_golden)."""
+    from pysolvers_b200 import _native as nat
+    from pysolvers_b200.problems import fd_laplacian_2d, fd_laplacian_3d
+    lib = nat.lib()
+    for dim, m, gen in ((2, 1, fd_laplacian_2d), (2, 2, fd_laplacian_2d), (2, 9, fd_laplacian_2d),
+                        (2, 40, fd_laplacian_2d), (3, 1, fd_laplacian_3d), (3, 2, fd_laplacian_3d),
+                        (3, 6, fd_laplacian_3d), (3, 11, fd_laplacian_3d)):
+        A = gen(0.0, 1.0, m)
+        n = m ** dim
+        for k in range(n + 1):
+            assert lib.psb_stencil_nnz(dim, m, 0, k) == A.indptr[k]
+        assert lib.psb_stencil_nnz(dim, m, n // 3, n) == A.indptr[n] - A.indptr[n // 3]
+    assert lib.psb_stencil_nnz(4, 3, 0, 1) == -1 and lib.psb_stencil_nnz(2, 3, 5, 2) == -1
