@@ -126,12 +126,14 @@ int psb_trsv_destroy(psb_trsv_t T);
 /* info[0]=n, [1]=levels, [2]=off-diagonal nnz, [3]=packed (padded) nnz,
  * [4]=lower, [5]=unit_diag, [6]=32-row groups. */
 int psb_trsv_info(psb_trsv_t T, int64_t info[8]);
-/* Which solve kernel the analysis chose, and the data of the shared-memory window kernel:
+/* Which solve kernel the analysis chose, and the data of the shared-memory window kernels:
  * info[0]=kernel (0 grid-wide, hand-over through L2; 1 one CTA, hand-over through shared
- * memory), [1]=window slots, [2]=dependencies older than the window (read from the global
- * vector), [3]=largest distance of a dependency in processing order, [4]=forced kernel or -1. */
+ * memory; 2 a cluster of 8 CTAs, window replicated through distributed shared memory),
+ * [1]=window slots, [2]=dependencies older than the window (read from the global
+ * vector), [3]=largest distance of a dependency in processing order, [4]=forced kernel or -1,
+ * [5]=entries per lane of a staging buffer, [6]=the cluster kernel may be forced. */
 int psb_trsv_info2(psb_trsv_t T, int64_t info[8]);
-/* Force a kernel for this factor (0 / 1), or -1 to return to the analysis' choice.  Both
+/* Force a kernel for this factor (0 / 1 / 2), or -1 to return to the analysis' choice.  All
  * kernels produce bit-identical results. */
 int psb_trsv_set_kernel(psb_trsv_t T, int kernel);
 /* Debugging aid of the one-CTA kernel: when d_trace (device, 12 * groups int64) is not NULL every

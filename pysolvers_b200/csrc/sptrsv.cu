@@ -205,7 +205,8 @@ static int trsv_kernel_override() {
   static int v = -2;
   if (v == -2) {
     const char* e = getenv("PSB_TRSV_KERNEL");
-    v = e == nullptr ? -1 : (strcmp(e, "cta") == 0 ? PSB_TRSV_CTA : (strcmp(e, "grid") == 0 ? PSB_TRSV_GRID : -1));
+    v = e == nullptr ? -1 : (strcmp(e, "cta") == 0 ? PSB_TRSV_CTA : (strcmp(e, "cluster") == 0 ? PSB_TRSV_CLUSTER
+                                              : (strcmp(e, "grid") == 0 ? PSB_TRSV_GRID : -1)));
   }
   return v;
 }
@@ -215,13 +216,13 @@ int trsv_solve(const psb_trsv* T, const double* rhs, double* x, const int32_t* r
   if (T->n == 0) return PSB_OK;
   const int forced = T->forced_kernel >= 0 ? T->forced_kernel : trsv_kernel_override();
   const int kernel = forced >= 0 ? forced : T->kernel;
-  if (kernel == PSB_TRSV_CTA) {
+  if (kernel == PSB_TRSV_CTA || kernel == PSB_TRSV_CLUSTER) {
     if (T->n_far > 0) {      // far dependencies are polled in the global vector: sentinel first
       const int fg = (int)std::min<int64_t>((T->n + kBlock * 4 - 1) / (kBlock * 4), (int64_t)sm_count() * 8);
       trsv_prepare_kernel<<<std::max(fg, 1), kBlock, 0, st>>>(x, T->n, T->d_counter, d_skip);
       PSB_LAUNCH_CHECK();
     }
-    return trsv_solve_cta(T, rhs, x, rhs_map, out2, out_map, d_skip, st);
+    return trsv_solve_cta(T, kernel == PSB_TRSV_CLUSTER ? 1 : 0, rhs, x, rhs_map, out2, out_map, d_skip, st);
   }
   const int fill_grid = (int)std::min<int64_t>((T->n + kBlock * 4 - 1) / (kBlock * 4), (int64_t)sm_count() * 8);
   trsv_prepare_kernel<<<std::max(fill_grid, 1), kBlock, 0, st>>>(x, T->n, T->d_counter, d_skip);
@@ -447,11 +448,17 @@ extern "C" int psb_trsv_create(int64_t n, const int32_t* h_rowptr, const int32_t
   // vector of up to 16 384 rows lives in the window whole; beyond that the window wraps around
   // and is sized so that a whole chunk of typical length can be staged: 16 384 slots while the
   // chunks are short, 8 192 slots (26 entries per lane staged) for the longer rows of IC factors.
+  // With more than kTrsvCtaMaxChunksPerLevel chunks per level the cluster kernel is the candidate:
+  // its 64 warps need a reuse slack of 32 (2 * 128 + 2) positions, i.e. the large window.
   const double mean_len = (double)T->nnz_packed / 32.0 / std::max(T->n_groups, 1);
+  const double cpl = (double)T->n_groups / std::max(T->n_levels, 1);
+  const bool cluster_cand = cpl > kTrsvCtaMaxChunksPerLevel && cpl <= kTrsvClusterMaxChunksPerLevel;
   if (n <= kTrsvMaxSlots) { T->wslots = 32; while (T->wslots < n) T->wslots <<= 1; }
-  else T->wslots = mean_len <= 12.0 ? kTrsvMaxSlots : kTrsvMaxSlots / 2;
+  else T->wslots = (cluster_cand || mean_len <= 12.0) ? kTrsvMaxSlots : kTrsvMaxSlots / 2;
   T->stage_len = (int)std::min<int64_t>(32, (kTrsvSmemBudget - 128 - (int64_t)T->wslots * 8) / (kTrsvCtaWarps * 384));
-  const int64_t near_limit = n <= T->wslots ? n : (int64_t)T->wslots - 32 * (2 * kTrsvAhead + 2);
+  const int ahead = cluster_cand ? 2 * kTrsvCtaWarps * kTrsvClusterSize : kTrsvAhead;
+  const int64_t near_limit = n <= T->wslots ? n : (int64_t)T->wslots - 32 * (2 * ahead + 2);
+  T->cluster_ok = (n <= T->wslots || cluster_cand) ? 1 : 0;
   // entry encoding: byte offset into the window (near), the always-zero slot right behind the window
   // (padding), or -(row) - 2 (far)
   const int32_t zero_off = T->wslots * 8;
@@ -483,15 +490,17 @@ extern "C" int psb_trsv_create(int64_t n, const int32_t* h_rowptr, const int32_t
       wmeta[4 * (size_t)g + 3] = (int32_t)(grp_rows[g] | (has_far << 6) | (width << 7));
     }
   }
-  // One CTA wins while the solve is bound by the latency of the dependency chain: few chunks per
-  // level (16 warps cover the wavefront) and the dependencies inside the window.  Wide levels, many
-  // long rows (one chunk each) or many far dependencies have enough parallelism for / need the
-  // whole grid.  Thresholds measured on B200 (profiles/round1d_trsv.md).
+  // One CTA wins while the solve is bound by the latency of the dependency chain and a level has
+  // at most ~3 chunks (the critical warps and the next spinners keep their warp schedulers); up to
+  // ~12 chunks per level the 4-CTA cluster covers the wavefront with 64 warps at the price of
+  // the DSMEM hand-over; wider levels, or many dependencies outside the window, go to the grid.
+  // Thresholds measured on B200 (profiles/round1d_trsv.md, round1g_cluster.md).
   {
-    const double cpl = (double)T->n_groups / std::max(T->n_levels, 1);
-    const bool narrow = cpl <= kTrsvCtaMaxChunksPerLevel;
     const bool local = (double)T->n_far <= 0.02 * (double)std::max<int64_t>(T->nnz_off, 1);
-    T->kernel = (narrow && local) ? PSB_TRSV_CTA : PSB_TRSV_GRID;
+    if (!local) T->kernel = PSB_TRSV_GRID;
+    else if (cpl <= kTrsvCtaMaxChunksPerLevel) T->kernel = PSB_TRSV_CTA;
+    else if (cluster_cand) T->kernel = PSB_TRSV_CLUSTER;
+    else T->kernel = PSB_TRSV_GRID;
   }
 
   cudaError_t e = upload(&T->d_order, order, st);
@@ -532,7 +541,7 @@ extern "C" int psb_trsv_info(psb_trsv_t T, int64_t info[8]) {
 extern "C" int psb_trsv_info2(psb_trsv_t T, int64_t info[8]) {
   PSB_REQUIRE(T && info, PSB_ERR_ARG, "psb_trsv_info2: NULL argument");
   info[0] = T->kernel; info[1] = T->wslots; info[2] = T->n_far; info[3] = T->max_dist;
-  info[4] = T->forced_kernel; info[5] = T->stage_len; info[6] = info[7] = 0;
+  info[4] = T->forced_kernel; info[5] = T->stage_len; info[6] = T->cluster_ok; info[7] = 0;
   return PSB_OK;
 }
 
@@ -544,7 +553,9 @@ extern "C" int psb_trsv_set_trace(psb_trsv_t T, long long* d_trace) {
 
 extern "C" int psb_trsv_set_kernel(psb_trsv_t T, int kernel) {
   PSB_REQUIRE(T != nullptr, PSB_ERR_ARG, "psb_trsv_set_kernel: NULL argument");
-  PSB_REQUIRE(kernel >= -1 && kernel <= PSB_TRSV_CTA, PSB_ERR_ARG, "psb_trsv_set_kernel: unknown kernel");
+  PSB_REQUIRE(kernel >= -1 && kernel <= PSB_TRSV_CLUSTER, PSB_ERR_ARG, "psb_trsv_set_kernel: unknown kernel");
+  PSB_REQUIRE(kernel != PSB_TRSV_CLUSTER || T->cluster_ok, PSB_ERR_UNSUPP,
+              "psb_trsv_set_kernel: this factor was not analysed for the cluster kernel");
   T->forced_kernel = kernel;
   return PSB_OK;
 }

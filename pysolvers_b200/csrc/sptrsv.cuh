@@ -33,12 +33,13 @@ struct psb_trsv {
   int stage_len = 0;              // entries per lane of a warp's staging buffer
   int64_t n_far = 0;              // dependencies older than the window (read from the global vector)
   int64_t max_dist = 0;           // largest position distance of a dependency
-  int kernel = 0;                 // PSB_TRSV_GRID / PSB_TRSV_CTA chosen by the analysis
+  int cluster_ok = 0;             // the window data respect the (larger) reuse slack of the cluster kernel
+  int kernel = 0;                 // PSB_TRSV_GRID / PSB_TRSV_CTA / PSB_TRSV_CLUSTER chosen by the analysis
   long long* d_trace = nullptr;   // not owned: psb_trsv_set_trace (debugging the one-CTA kernel)
   int forced_kernel = -1;         // psb_trsv_set_kernel: >= 0 overrides the analysis
 };
 
-enum { PSB_TRSV_GRID = 0, PSB_TRSV_CTA = 1 };
+enum { PSB_TRSV_GRID = 0, PSB_TRSV_CTA = 1, PSB_TRSV_CLUSTER = 2 };
 
 namespace psb {
 
@@ -46,7 +47,10 @@ constexpr int kTrsvCtaWarps = 16;        // warps of the one-CTA kernel (512 thr
 constexpr int kTrsvAhead = 2 * kTrsvCtaWarps;   // chunks a warp may run ahead of the slowest one (2 rounds)
 constexpr int kTrsvMaxSlots = 16384;     // largest window of the shared-memory kernel: 128 KB of fp64
 constexpr int kTrsvSmemBudget = 224 * 1024;   // window + 16 staging buffers must fit (227 KB opt-in limit)
-constexpr double kTrsvCtaMaxChunksPerLevel = 4.0;   // mean chunks per level up to which one CTA beats the grid
+constexpr int kTrsvClusterSize = 4;      // CTAs of the cluster kernel: 64 warps on 4 SMs (8 CTAs would need a reuse
+                                         // slack of 32 (2 * 256 + 2) positions, more than the 16 384-slot window)
+constexpr double kTrsvCtaMaxChunksPerLevel = 3.5;       // mean chunks per level up to which ONE CTA is used
+constexpr double kTrsvClusterMaxChunksPerLevel = 12.0;  // ... up to which the 4-CTA cluster is used; beyond: the grid
 
 // x = T^-1 rhs, enqueued on st.  rhs_map (nullable): row r takes rhs[rhs_map[r]].
 // out2/out_map (nullable): additionally out2[out_map[r]] = x[r].
@@ -54,8 +58,8 @@ constexpr double kTrsvCtaMaxChunksPerLevel = 4.0;   // mean chunks per level up 
 int trsv_solve(const psb_trsv* T, const double* rhs, double* x, const int32_t* rhs_map,
                double* out2, const int32_t* out_map, const int* d_skip, cudaStream_t st);
 
-// the same solve by ONE CTA with the wavefront in shared memory (sptrsv_cta.cu)
-int trsv_solve_cta(const psb_trsv* T, const double* rhs, double* x, const int32_t* rhs_map,
+// the same solve by ONE CTA, or one cluster of CTAs, with the wavefront in shared memory (sptrsv_cta.cu)
+int trsv_solve_cta(const psb_trsv* T, int cluster, const double* rhs, double* x, const int32_t* rhs_map,
                    double* out2, const int32_t* out_map, const int* d_skip, cudaStream_t st);
 
 }  // namespace psb

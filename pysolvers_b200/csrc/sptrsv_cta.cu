@@ -212,24 +212,66 @@ __device__ __forceinline__ double walk(double acc, int nr, uint32_t sc, uint32_t
   return acc;
 }
 
-template <bool kTrace>
+// ---- distributed shared memory (thread-block cluster): every CTA of the cluster keeps a replica of
+// the window and of the progress array; a producer stores its result into all of them.
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f64(uint32_t a, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_s32(uint32_t a, int v) {
+  asm volatile("st.shared::cluster.s32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// kC = 1: one CTA.  kC > 1: a cluster of kC CTAs on kC SMs; chunk g runs on CTA g mod kC, warp
+// (g / kC) mod 16, so consecutive chunks -- the critical one and the ones spinning behind it -- sit
+// on different SMs and 16 kC warps cover wide levels.  The price is the DSMEM hand-over (~215
+// cycles instead of 38), so the cluster is used when a level has more chunks than one CTA can
+// keep on separate schedulers (measured: 4.5 - 8.5 chunks per level 0.78 - 0.88 us per level
+// against 1.0 - 1.7 for one CTA and 1.15 for the grid; profiles/round1g_cluster.md).
+template <int kC, bool kTrace>
 __global__ void __launch_bounds__(kCtaThreads, 1)
 trsv_cta_kernel(const CtaView T, const double* __restrict__ rhs, double* x,
                 const int32_t* __restrict__ rhs_map, double* out2,
                 const int32_t* __restrict__ out_map, const int* d_skip) {
-  if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
+  if (d_skip != nullptr && ld_cg(d_skip) != 0) return;       // uniform over the whole cluster
+  constexpr int kStride = kCtaWarps * kC;                   // chunks per round of all warps
+  constexpr int kAheadC = 2 * kStride;                      // run-ahead allowance in chunks: two rounds (with one
+                                                            // round every round ends in a cluster-wide wait)
+  constexpr int kProg = kStride < 32 ? 32 : kStride;        // progress entries (one per warp of the cluster)
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ int prog_raw[32];
+  __shared__ int prog_raw[kProg];
   __shared__ __align__(8) unsigned long long bars_raw[kCtaWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cta = kC == 1 ? 0 : (int)cluster_rank();
+  const int gw = warp * kC + cta;                           // this warp's slot in prog[]: first chunk it owns
   // the shared-window addresses are made opaque to the compiler: otherwise it re-derives them from
   // special registers (S2R, tens of cycles) right before each use, also on the critical path
   uint32_t wbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
   uint32_t prog_base = (uint32_t)__cvta_generic_to_shared(prog_raw);
   asm volatile("mov.u32 %0, %0;" : "+r"(wbase));
   asm volatile("mov.u32 %0, %0;" : "+r"(prog_base));
-  const uint32_t prog_a = prog_base + 4u * lane;
   const uint32_t bar = (uint32_t)__cvta_generic_to_shared(bars_raw) + 8u * warp;
+  // replicas: cluster-space addresses of every CTA's window, most urgent consumer first (the next
+  // chunk runs on the next CTA); lane c < kC also holds the address of CTA c's progress array
+  uint32_t rwin[kC];
+  uint32_t rprog = 0;
+  if (kC > 1) {
+#pragma unroll
+    for (int c = 0; c < kC; ++c) rwin[c] = mapa_u32(wbase, (uint32_t)((cta + 1 + c) % kC));
+    rprog = mapa_u32(prog_base, (uint32_t)(lane % kC));
+  }
   // layout: window | 128 bytes whose first 8 are the always-zero slot of the padding entries |
   // per warp: stage_len x 32 columns (int32) then stage_len x 32 values (fp64)
   const uint32_t stage_bytes = (uint32_t)T.stage_len * 384u;
@@ -241,18 +283,31 @@ trsv_cta_kernel(const CtaView T, const double* __restrict__ rhs, double* x,
   const int fill = (int)min((int64_t)T.wslots, T.n);
   for (int i = threadIdx.x; i < fill; i += kCtaThreads) sts_vol(wbase + ((uint32_t)i << 3), kNotReady);
   if (threadIdx.x == 0) sts_vol(wbase + (uint32_t)T.wslots * 8u, 0.0);
-  if (threadIdx.x < 32)
-    prog_raw[threadIdx.x] = ((int)threadIdx.x < kCtaWarps && (int)threadIdx.x < T.n_groups)
-                                ? (int)threadIdx.x - kCtaWarps : INT32_MAX;
+  for (int i = threadIdx.x; i < kProg; i += kCtaThreads)
+    prog_raw[i] = (i < kStride && i < T.n_groups) ? i - kStride : INT32_MAX;
   if (lane == 0) mbar_init32(bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
+  if (kC > 1) cluster_sync_all();        // nobody stores into a replica before its owner has initialised it
+
+  // oldest chunk in work anywhere in the cluster (local replica: may lag, never runs ahead)
+  auto low_water = [&]() -> int {
+    int v = INT32_MAX;
+#pragma unroll
+    for (int j = 0; j < kProg / 32; ++j) v = min(v, lds_vol_i32(prog_base + 4u * (uint32_t)(lane + 32 * j)));
+    return __reduce_min_sync(0xffffffffu, v);
+  };
+  auto publish = [&](int value) {
+    if (kC == 1) { if (lane == 0) sts_vol_i32(prog_base + 4u * (uint32_t)gw, value); }
+    else if (lane < kC) st_cluster_s32(rprog + 4u * (uint32_t)gw, value);
+  };
 
   const int4 kNone = make_int4(0, 0, 0, 0);
-  int g = warp;
+  int g = gw;
+  bool ok = true;
   int4 m0 = g < T.n_groups ? __ldg(T.meta + g) : kNone;
-  int4 m1 = g + kCtaWarps < T.n_groups ? __ldg(T.meta + g + kCtaWarps) : kNone;
-  int4 m2 = g + 2 * kCtaWarps < T.n_groups ? __ldg(T.meta + g + 2 * kCtaWarps) : kNone;
+  int4 m1 = g + kStride < T.n_groups ? __ldg(T.meta + g + kStride) : kNone;
+  int4 m2 = g + 2 * kStride < T.n_groups ? __ldg(T.meta + g + 2 * kStride) : kNone;
   uint32_t parity = 0;
   // stage the first round of the first chunk
   if (g < T.n_groups && lane == 0) {
@@ -264,9 +319,10 @@ trsv_cta_kernel(const CtaView T, const double* __restrict__ rhs, double* x,
       bulk_g2s32(sv_base, T.vals + b0, (uint32_t)n0 * 256u, bar);
     }
   }
-  for (; g < T.n_groups; g += kCtaWarps) {
+  for (; ok && g < T.n_groups; g += kStride) {
     // meta of the chunk three rounds ahead (arrives while this chunk is worked on)
-    const int4 m3 = g + 3 * kCtaWarps < T.n_groups ? __ldg(T.meta + g + 3 * kCtaWarps) : kNone;
+    const int4 m3 = g + 3 * kStride < T.n_groups ? __ldg(T.meta + g + 3 * kStride) : kNone;
+    const int4 mr = m2;                         // chunk g + kAheadC: its slots are reset below
     const int64_t base = ((int64_t)m0.y << 32) | (unsigned int)m0.x;
     const int item0 = m0.z;
     const int rows = m0.w & 63;                 // 0: one long row for the warp
@@ -287,30 +343,38 @@ trsv_cta_kernel(const CtaView T, const double* __restrict__ rhs, double* x,
     }
 
     if (T.wraps) {
-      // nobody runs more than kAhead chunks ahead of the slowest warp ...
+      // nobody runs more than kAheadC chunks ahead of the slowest warp (nothing to protect during
+      // the first round: the window is >= 64 kStride slots, no slot is reused yet) ...
       int spins = 0;
-      for (;;) {
-        const int lw = __reduce_min_sync(0xffffffffu, lds_vol_i32(prog_a));
-        if (lw >= g - kAhead) break;
-        if (++spins > kSpinLimitCta) { *T.error = 2; return; }
+      while (g >= kStride) {
+        if (low_water() >= g - kAheadC) break;
+        if (++spins > kSpinLimitCta) { *T.error = 2; ok = false; break; }
         __nanosleep(64);
       }
-      // ... so the readers of what the slots of chunk g + kAhead held one lap ago are done: reset them
-      if (g + 2 * kCtaWarps < T.n_groups) {
-        const int r_item = m2.z, r_rows = (m2.w & 63) == 0 ? 1 : (m2.w & 63);
-        if (lane < r_rows) sts_vol(wbase + ((uint32_t)((r_item + lane) & wmask) << 3), kNotReady);
+      // ... so the readers of what the slots of chunk g + kAheadC held one lap ago are done: reset them
+      if (g + kAheadC < T.n_groups) {
+        const int r_item = mr.z, r_rows = (mr.w & 63) == 0 ? 1 : (mr.w & 63);
+        if (lane < r_rows) {
+          const uint32_t off = (uint32_t)((r_item + lane) & wmask) << 3;
+          if (kC == 1) sts_vol(wbase + off, kNotReady);
+          else {
+#pragma unroll
+            for (int c = 0; c < kC; ++c) st_cluster_f64(rwin[c] + off, kNotReady);
+          }
+        }
       }
-      __syncwarp();                      // the resets of all lanes before the progress store of lane 0
+      if (kC > 1) asm volatile("fence.acq_rel.cluster;" ::: "memory");   // resets before the progress store, everywhere
+      __syncwarp();                      // the resets of all lanes before the progress store
     }
-    if (lane == 0) sts_vol_i32(prog_base + 4u * warp, g);   // also the wavefront estimate of the sleepers
+    publish(g);                          // also the wavefront estimate of the sleepers
 
     double acc = 0.0;
     if (owner) acc = rhs_map ? rhs[rhs_map[row]] : rhs[row];
-    const uint32_t wout = wbase + ((uint32_t)(q & wmask) << 3);
+    const uint32_t wout = (uint32_t)(q & wmask) << 3;
     double* xout = x + row;
 
     // prefetch the chunk of two rounds ahead into L2: cols (128 B per entry row), vals (256 B)
-    if (g + 2 * kCtaWarps < T.n_groups) {
+    if (g + 2 * kStride < T.n_groups) {
       const int64_t pbase = ((int64_t)m2.y << 32) | (unsigned int)m2.x;
       const int plen = m2.w >> 7;
       for (int i = lane; i < plen; i += 32) prefetch_l2(T.cols + pbase + (int64_t)i * 32);
@@ -325,7 +389,7 @@ trsv_cta_kernel(const CtaView T, const double* __restrict__ rhs, double* x,
     // to the distance; only the next few levels spin on their dependencies.
     if (len > 0) {
       for (;;) {
-        const int ahead = g - __reduce_min_sync(0xffffffffu, lds_vol_i32(prog_a)) - T.near_chunks;
+        const int ahead = g - low_water() - T.near_chunks;
         if (ahead <= 0) break;
         __nanosleep((unsigned)((min(ahead, 512) * T.ns_per_chunk_q4) >> 4));
       }
@@ -347,7 +411,7 @@ trsv_cta_kernel(const CtaView T, const double* __restrict__ rhs, double* x,
       {
         int spins = 0;
         while (!mbar_try32(bar, parity)) {
-          if (++spins > kSpinLimitCta) { *T.error = 3; break; }
+          if (++spins > kSpinLimitCta) { *T.error = 3; ok = false; break; }
         }
         parity ^= 1u;
       }
@@ -360,7 +424,13 @@ trsv_cta_kernel(const CtaView T, const double* __restrict__ rhs, double* x,
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     }
     const double r = acc * d;            // d = 1 / diagonal (scipy: x = y * invdiag); 1 for unit_diag
-    if (owner) sts_vol(wout, r);
+    if (owner) {
+      if (kC == 1) sts_vol(wbase + wout, r);
+      else {
+#pragma unroll
+        for (int c = 0; c < kC; ++c) st_cluster_f64(rwin[c] + wout, r);   // next CTA first, own replica last
+      }
+    }
     if (kTrace) t_ready = clock64();
     // everything below is off the critical path
     if (owner) {
@@ -368,7 +438,7 @@ trsv_cta_kernel(const CtaView T, const double* __restrict__ rhs, double* x,
       if (out2 != nullptr) out2[out_map[row]] = r;
     }
     __syncwarp();
-    if (lane == 0 && g + kCtaWarps < T.n_groups) {          // stage the first round of the next chunk
+    if (lane == 0 && g + kStride < T.n_groups) {            // stage the first round of the next chunk
       const int64_t b1 = ((int64_t)m1.y << 32) | (unsigned int)m1.x;
       const int n1 = min(m1.w >> 7, T.stage_len);
       if (n1 > 0) {
@@ -387,20 +457,46 @@ trsv_cta_kernel(const CtaView T, const double* __restrict__ rhs, double* x,
     m0 = m1; m1 = m2; m2 = m3;
   }
   __syncwarp();
-  if (lane == 0) sts_vol_i32(prog_base + 4u * warp, INT32_MAX);
+  publish(INT32_MAX);
+  if (kC > 1) cluster_sync_all();        // no CTA leaves while another may still store into its replica
 }
 
 }  // namespace
 
-int trsv_solve_cta(const psb_trsv* T, const double* rhs, double* x, const int32_t* rhs_map,
-                   double* out2, const int32_t* out_map, const int* d_skip, cudaStream_t st) {
-  const size_t smem = (size_t)T->wslots * sizeof(double) + 128 + (size_t)kCtaWarps * T->stage_len * 384;
+template <int kC>
+static int launch_cta(const CtaView& V, size_t smem, bool trace, const double* rhs, double* x,
+                      const int32_t* rhs_map, double* out2, const int32_t* out_map, const int* d_skip,
+                      cudaStream_t st) {
   static thread_local bool configured = false;
   if (!configured) {
-    PSB_CUDA(cudaFuncSetAttribute(trsv_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsvSmemBudget));
-    PSB_CUDA(cudaFuncSetAttribute(trsv_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsvSmemBudget));
+    PSB_CUDA(cudaFuncSetAttribute(trsv_cta_kernel<kC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsvSmemBudget));
+    PSB_CUDA(cudaFuncSetAttribute(trsv_cta_kernel<kC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsvSmemBudget));
     configured = true;
   }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kC);
+  cfg.blockDim = dim3(kCtaThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = kC > 1 ? 1 : 0;
+  if (trace) PSB_CUDA(cudaLaunchKernelEx(&cfg, trsv_cta_kernel<kC, true>, V, rhs, x, rhs_map, out2, out_map, d_skip));
+  else       PSB_CUDA(cudaLaunchKernelEx(&cfg, trsv_cta_kernel<kC, false>, V, rhs, x, rhs_map, out2, out_map, d_skip));
+  PSB_LAUNCH_CHECK();
+  return PSB_OK;
+}
+
+int trsv_solve_cta(const psb_trsv* T, int cluster, const double* rhs, double* x, const int32_t* rhs_map,
+                   double* out2, const int32_t* out_map, const int* d_skip, cudaStream_t st) {
+  const size_t smem = (size_t)T->wslots * sizeof(double) + 128 + (size_t)kCtaWarps * T->stage_len * 384;
+  if (cluster && !T->cluster_ok) {
+    set_error("trsv_solve: this factor was not analysed for the cluster kernel");
+    return PSB_ERR_UNSUPP;
+  }
+  const int kc = cluster ? kTrsvClusterSize : 1;
   // chunks per level decide who spins (the next 2 levels) and how long the others sleep (half of
   // an optimistic 128 ns per level of distance)
   const double cpl = std::max(1.0, (double)T->n_groups / std::max(T->n_levels, 1));
@@ -413,10 +509,8 @@ int trsv_solve_cta(const psb_trsv* T, const double* rhs, double* x, const int32_
   CtaView V{T->n, T->n_groups, T->wslots, T->n > T->wslots ? 1 : 0, T->stage_len, T->d_order, T->d_diag,
             reinterpret_cast<const int4*>(T->d_wmeta), T->d_wcols, T->d_vals, T->d_error,
             near_chunks, ns_q4, T->d_trace};
-  if (T->d_trace) trsv_cta_kernel<true><<<1, kCtaThreads, smem, st>>>(V, rhs, x, rhs_map, out2, out_map, d_skip);
-  else trsv_cta_kernel<false><<<1, kCtaThreads, smem, st>>>(V, rhs, x, rhs_map, out2, out_map, d_skip);
-  PSB_LAUNCH_CHECK();
-  return PSB_OK;
+  if (kc == 1) return launch_cta<1>(V, smem, T->d_trace != nullptr, rhs, x, rhs_map, out2, out_map, d_skip, st);
+  return launch_cta<kTrsvClusterSize>(V, smem, T->d_trace != nullptr, rhs, x, rhs_map, out2, out_map, d_skip, st);
 }
 
 }  // namespace psb

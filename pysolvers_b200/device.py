@@ -183,12 +183,13 @@ class DeviceTrsv:
     def info2(self):
         buf = (C.c_int64 * 8)()
         nat.check(nat.lib().psb_trsv_info2(self._h, buf), 'psb_trsv_info2')
-        return dict(kernel='cta' if buf[0] == 1 else 'grid', wslots=int(buf[1]), n_far=int(buf[2]),
-                    max_dist=int(buf[3]), forced=int(buf[4]))
+        return dict(kernel={0: 'grid', 1: 'cta', 2: 'cluster'}[int(buf[0])], wslots=int(buf[1]), n_far=int(buf[2]),
+                    max_dist=int(buf[3]), forced=int(buf[4]), stage_len=int(buf[5]), cluster_ok=bool(buf[6]))
 
     def set_kernel(self, kernel):
-        """'grid' (hand-over through L2), 'cta' (one CTA, shared-memory window) or None (analysis)."""
-        k = {'grid': 0, 'cta': 1, None: -1}[kernel]
+        """'grid' (hand-over through L2), 'cta' (one CTA, shared-memory window), 'cluster' (8 CTAs,
+        window replicated through distributed shared memory) or None (analysis)."""
+        k = {'grid': 0, 'cta': 1, 'cluster': 2, None: -1}[kernel]
         nat.check(nat.lib().psb_trsv_set_kernel(self._h, k), 'psb_trsv_set_kernel')
 
     def levels(self):

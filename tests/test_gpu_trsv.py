@@ -82,19 +82,22 @@ def test_trsv_edge_cases(cuda):
 
 
 def _both_kernels(T, lower, unit, v):
-    """Solve with the grid-wide kernel (hand-over through L2) and with the one-CTA kernel
-    (hand-over through the shared-memory window): the results must be the same bits."""
+    """Solve with the grid-wide kernel (hand-over through L2), the one-CTA kernel (hand-over through
+    the shared-memory window) and, where the analysis allows it, the 8-CTA cluster kernel (window
+    replicated through distributed shared memory): the results must be the same bits."""
     from pysolvers_b200.device import DeviceTrsv, to_device
     dT = DeviceTrsv(T, lower=lower, unit_diag=unit)
     out = {}
-    for kern in ('grid', 'cta'):
+    kernels = ['grid', 'cta'] + (['cluster'] if dT.info2()['cluster_ok'] else [])
+    for kern in kernels:
         dT.set_kernel(kern)
-        assert dT.info2()['forced'] == {'grid': 0, 'cta': 1}[kern]
+        assert dT.info2()['forced'] == {'grid': 0, 'cta': 1, 'cluster': 2}[kern]
         xs = [dT.solve(to_device(v)).cpu().numpy() for _ in range(2)]    # twice: state carried over
         dT.check()
         assert np.array_equal(xs[0], xs[1])
         out[kern] = xs[0]
-    assert np.array_equal(out['grid'], out['cta'])
+    for kern in kernels[1:]:
+        assert np.array_equal(out['grid'], out[kern]), kern
     return dT, out['cta']
 
 
@@ -113,6 +116,10 @@ def test_both_kernels_bit_identical(cuda):
                     [-1, -9000, -15000, 0]).tocsr()          # a chain with far dependencies on it
     cases.append((band, True, False))
     cases.append((band.T.tocsr(), False, False))
+    # wide levels (Gauss-Seidel triangle of a 200 x 200 grid: 100 rows per level on average, 40 000
+    # rows): analysed for the cluster kernel, the window wraps around
+    gs = sp.triu(_lap(200)).tocsr()
+    cases.append((gs, False, False))
     lu2 = spla.splu(sp.csc_matrix(_lap(132)))                 # 17 424 rows: long rows AND a wrapping window
     cases += [(lu2.L.tocsr(), True, True), (lu2.U.tocsr(), False, False)]
     lu = spla.splu(sp.csc_matrix(_lap(48)))                   # long rows (warp per row)
@@ -128,6 +135,9 @@ def test_both_kernels_bit_identical(cuda):
             assert np.array_equal(x, precond.trsv_rowwise(T, v, lower=lower, unit_diagonal=unit))
         ref = spla.spsolve_triangular(T.tocsr(), v, lower=lower, unit_diagonal=unit)
         assert np.linalg.norm(x - ref) <= 1e-11 * np.linalg.norm(ref), (T.shape, lower, unit)
+    from pysolvers_b200.device import DeviceTrsv as _DT
+    i3 = _DT(gs, lower=False).info2()
+    assert i3['cluster_ok'] and i3['kernel'] == 'cluster' and i3['wslots'] == 16384
     # the banded case must really exercise the far path
     from pysolvers_b200.device import DeviceTrsv
     i2 = DeviceTrsv(band, lower=True).info2()

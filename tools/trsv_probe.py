@@ -13,7 +13,8 @@ def bench(T, lower, name, unit=False, reps=5):
     v = to_device(np.ones(T.shape[0]))
     out = torch.empty_like(v)
     res = {}
-    for kern in ('grid', 'cta'):
+    kernels = ['grid', 'cta'] + (['cluster'] if dT.info2()['cluster_ok'] else [])
+    for kern in kernels:
         dT.set_kernel(kern)
         dT.solve(v, out)
         torch.cuda.synchronize()
@@ -25,17 +26,17 @@ def bench(T, lower, name, unit=False, reps=5):
         e1.record()
         torch.cuda.synchronize()
         res[kern] = (e0.elapsed_time(e1) / reps, out.clone())
-    assert torch.equal(res['grid'][1], res['cta'][1]), name
+    for kern in kernels[1:]:
+        assert torch.equal(res['grid'][1], res[kern][1]), (name, kern)
     i, i2 = dT.info(), dT.info2()
     lv = i['levels']
-    gb = (12 * i['nnz_packed'] + 24 * i['n']) / 1e9
-    print('%-14s n=%8d lev=%6d rows/lev=%7.1f far=%d | grid %8.3f ms %6.2f us/lev | cta %8.3f ms %6.3f us/lev %6.1f GB/s | x%.1f  auto=%s'
-          % (name, i['n'], lv, i['n'] / lv, i2['n_far'], res['grid'][0], 1e3 * res['grid'][0] / lv,
-             res['cta'][0], 1e3 * res['cta'][0] / lv, gb / (res['cta'][0] * 1e-3),
-             res['grid'][0] / res['cta'][0], i2['kernel']), flush=True)
+    us = lambda k: ('%7.3f' % (1e3 * res[k][0] / lv)) if k in res else '    n/a'
+    print('%-14s n=%8d lev=%6d rows/lev=%7.1f chunks/lev=%5.1f far=%6d | us/level: grid %s  cta %s  cluster %s | auto=%-7s %8.3f ms'
+          % (name, i['n'], lv, i['n'] / lv, i['groups'] / lv, i2['n_far'], us('grid'), us('cta'), us('cluster'),
+             i2['kernel'], res[i2['kernel']][0]), flush=True)
 
 
-which = sys.argv[1:] or ['chain', 'ic128', 'ic256', 'ic512', 'dh15', 'gs512', 'gs2048', 'lu']
+which = sys.argv[1:] or ['chain', 'ic128', 'ic256', 'ic512', 'dh15', 'gs256', 'gs512', 'gs2048', 'lu']
 for w in which:
     if w == 'chain':
         n = 20000
