@@ -128,6 +128,18 @@ class DistCSR:
 
     def __init__(self, comm, indptr, indices, data, lo, hi, n):
         import torch.distributed as dist
+        import time as _time
+        _timing = os.environ.get('PSB_DIST_TIMING', '0') == '1'
+        _t = [_time.perf_counter()]
+
+        def _mark(what):
+            if _timing:
+                torch.cuda.synchronize()
+                now = _time.perf_counter()
+                if comm.rank == 0:
+                    print('[DistCSR] %-28s %7.2f ms' % (what, 1e3 * (now - _t[0])), flush=True)
+                _t[0] = now
+        self._mark = _mark
         self.comm = comm
         self.lo, self.hi, self.n = int(lo), int(hi), int(n)
         self.n_loc = self.hi - self.lo
@@ -136,7 +148,9 @@ class DistCSR:
         dev = torch.device('cuda', torch.cuda.current_device())
         ip = torch.as_tensor(indptr).to(dev)
         ix = torch.as_tensor(indices).to(dev)
+        _mark('upload indptr, indices')
         loc = localize(ip, ix, self.lo, self.hi, self.starts)
+        _mark('localize (halo lists)')
         self.recv = loc['recv'].cpu().numpy()
         self.recv_owner = loc['recv_owner'].cpu().numpy()
         self.n_halo = int(self.recv.size)
@@ -144,10 +158,12 @@ class DistCSR:
         gathered = [None] * comm.world
         dist.all_gather_object(gathered, (self.recv, self.recv_owner))
         self.send = send_lists(comm.rank, self.lo, gathered)
+        _mark('all_gather halo lists')
         self.A = DeviceCSR(indptr=ip.to(torch.int32), indices=loc['local_indices'],
                            data=torch.as_tensor(data).to(dev),
                            shape=(self.n_loc, self.n_loc + self.n_halo))
         del ix
+        _mark('upload data, csr_create')
         # peers: union of the ranks we send to / receive from
         peers = sorted(set(self.send) | set(int(o) for o in np.unique(self.recv_owner)))
         k = len(peers)
@@ -180,9 +196,11 @@ class DistCSR:
             peer_rank, send_off, send_cnt, idx_ptrs, recv_off, recv_cnt, C.byref(self._h)),
             'psb_dist_create')
 
+        _mark('psb_dist_create')
         self.p2p = False
         if os.environ.get('PSB_DIST_MODE', 'p2p') != 'nccl':
             self._enable_p2p(gathered)
+        _mark('peer-memory mapping')
 
     def _enable_p2p(self, all_recv):
         """Map every rank's exported region (NVLink peer memory) so that the solve
@@ -410,9 +428,12 @@ def bench_multi_gpu(args, bench):
     nnz = int(nnz_t.item())
     mode = 'nvlink-p2p' if D.p2p else 'nccl'
     if not skip_e2e:
-        ip_h, dt_h = indptr.cpu().numpy(), data.cpu().numpy()
-        cols_h = laplacian_block_device(dim, 0.0, 1.0, m, lo, hi, dev)[1].cpu().numpy()
-        b_h = np.ones(n_loc)
+        # host operands in page-locked memory, as in the single-GPU bench (the e2e leg copies from
+        # pinned memory; pageable arrays cost 2 - 4 x in the upload)
+        pin = lambda t: t.cpu().pin_memory().numpy()
+        ip_h, dt_h = pin(indptr), pin(data)
+        cols_h = pin(laplacian_block_device(dim, 0.0, 1.0, m, lo, hi, dev)[1])
+        b_h = torch.ones(n_loc, dtype=torch.float64).pin_memory().numpy()
         solver = DistributedPCG(CommonSolverArgs(maxiter=iters, tau=0.0, failOnMaxiter=False,
                                                  showIters=False, showFinal=False))
         del D
