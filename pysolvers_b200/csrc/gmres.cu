@@ -19,6 +19,7 @@
 // row-major array makes every basis vector a strided column).  The Hessenberg column, the
 // rotations, g, the iteration counter and the flags live in device memory; the host polls a
 // pinned copy one iteration behind.
+#include <cstdlib>
 #include "prec.cuh"
 #include "spmv.cuh"
 
@@ -176,7 +177,7 @@ gmres_multidot_kernel(const GmresState* st, int64_t n, const double* __restrict_
 }
 
 // batched axpy: w = (init ? 0 : w) + sign * sum_c coef[j0 + c] q_{j0+c}; optional w.w
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 4)
 gmres_multiaxpy_kernel(GmresState* st, int64_t n, const double* __restrict__ Q, int64_t ldq,
                        double* __restrict__ w, const double* coef, int j0, int cnt, double sign,
                        int init_zero, int want_norm, int check_done, ReduceBuf rb) {
@@ -297,7 +298,17 @@ gmres_norm_kernel(GmresState* st, int64_t n, const double* __restrict__ r, Reduc
   }
 }
 
+constexpr int64_t kBasisPad = 288;   // elements; see basis_ld
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// Leading dimension of the Krylov basis.  The batched CGS2 kernels stream 8 basis vectors and w at
+// the same offset; with n a power of two the nine streams are exactly 2^k bytes apart and collide in
+// the memory system, so consecutive vectors are staggered by a pad (multiple of 32 elements).
+static int64_t basis_ld(int64_t n) {
+  static int64_t pad = -1;
+  if (pad < 0) { const char* e = getenv("PSB_GMRES_PAD"); pad = e ? align_up(atoll(e), 32) : kBasisPad; }
+  return align_up(n, 32) + pad;
+}
 
 struct GmresWork {
   GmresState* st;
@@ -327,7 +338,7 @@ static GmresWork carve(void* d_work, int64_t n, int64_t m) {
   w.sm.sn = s;              s += m;
   w.sm.g = s;               s += m + 1;
   w.sm.y = s;
-  w.ldq = align_up(n, 32);
+  w.ldq = basis_ld(n);
   char* v = base + 4096 + reduce_bytes() + small_bytes(m);
   const int64_t vec = w.ldq * (int64_t)sizeof(double);
   w.Q = (double*)v;                         v += (m + 1) * vec;
@@ -357,7 +368,7 @@ using namespace psb;
 extern "C" int64_t psb_gmres_workspace_bytes(int64_t n, int32_t maxiter) {
   if (n < 0 || maxiter < 1) return PSB_ERR_ARG;
   const int64_t m = maxiter;
-  return 4096 + reduce_bytes() + small_bytes(m) + (m + 4) * align_up(n, 32) * (int64_t)sizeof(double);
+  return 4096 + reduce_bytes() + small_bytes(m) + (m + 4) * basis_ld(n) * (int64_t)sizeof(double);
 }
 
 extern "C" int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, double* d_x,
@@ -389,6 +400,22 @@ extern "C" int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, 
   PSB_CUDA(cudaStreamSynchronize(st));
 
   const int grid = stream_grid(n, w.rb.max_grid);
+  // The basis kernels run as exactly ONE wave of resident CTAs (grid-stride inside): with the
+  // generic 8 CTAs per SM and 3 - 5 resident ones the second wave left 40 % of the slots empty
+  // (ncu: 53 % of the DRAM peak, profiles/round1h_gmres.md).
+  auto one_wave = [&](const void* kernel, int* cache) -> int {
+    if (*cache == 0) {
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+      *cache = per_sm * sm_count();
+    }
+    const int64_t need = ((n >> 1) + kBlock - 1) / kBlock;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(*cache, need), w.rb.max_grid));
+  };
+  static thread_local int wave_dot = 0, wave_axpy = 0, wave_mgs = 0;
+  const int grid_dot = one_wave((const void*)gmres_multidot_kernel, &wave_dot);
+  const int grid_axpy = one_wave((const void*)gmres_multiaxpy_kernel, &wave_axpy);
+  const int grid_mgs = one_wave((const void*)gmres_mgs_kernel, &wave_mgs);
   gmres_init_kernel<<<grid, kBlock, 0, st>>>(w.st, w.sm, n, d_b, w.rb);
   PSB_LAUNCH_CHECK();
   // q_0 = b / beta   (GMRESSolver.py:90-91); harmless when b == 0 (result unused)
@@ -410,7 +437,7 @@ extern "C" int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, 
     if (rc != PSB_OK) return rc;
     if (orth == PSB_ORTH_MGS) {
       for (int j = 0; j <= k + 1; ++j) {
-        gmres_mgs_kernel<<<grid, kBlock, 0, st>>>(w.st, w.sm, n, w.Q, w.ldq, w.w, j, k, w.rb);
+        gmres_mgs_kernel<<<grid_mgs, kBlock, 0, st>>>(w.st, w.sm, n, w.Q, w.ldq, w.w, j, k, w.rb);
         PSB_LAUNCH_CHECK();
       }
     } else {
@@ -418,13 +445,13 @@ extern "C" int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, 
         double* hout = round == 0 ? w.sm.hcol : w.sm.hcol2;
         for (int j0 = 0; j0 <= k; j0 += kCh) {
           const int cnt = std::min(kCh, k + 1 - j0);
-          gmres_multidot_kernel<<<grid, kBlock, 0, st>>>(w.st, n, w.Q, w.ldq, w.w, j0, cnt, hout, w.rb);
+          gmres_multidot_kernel<<<grid_dot, kBlock, 0, st>>>(w.st, n, w.Q, w.ldq, w.w, j0, cnt, hout, w.rb);
           PSB_LAUNCH_CHECK();
         }
         for (int j0 = 0; j0 <= k; j0 += kCh) {
           const int cnt = std::min(kCh, k + 1 - j0);
           const int want_norm = (round == 1 && j0 + kCh > k) ? 1 : 0;
-          gmres_multiaxpy_kernel<<<grid, kBlock, 0, st>>>(w.st, n, w.Q, w.ldq, w.w, hout, j0, cnt, -1.0,
+          gmres_multiaxpy_kernel<<<grid_axpy, kBlock, 0, st>>>(w.st, n, w.Q, w.ldq, w.w, hout, j0, cnt, -1.0,
                                                           0, want_norm, 1, w.rb);
           PSB_LAUNCH_CHECK();
         }
@@ -466,7 +493,7 @@ extern "C" int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, 
   double* tvec = has_prec ? w.t : d_x;
   for (int j0 = 0; j0 <= kf; j0 += kCh) {
     const int cnt = std::min(kCh, kf + 1 - j0);
-    gmres_multiaxpy_kernel<<<grid, kBlock, 0, st>>>(w.st, n, w.Q, w.ldq, tvec, w.sm.y, j0, cnt, 1.0,
+    gmres_multiaxpy_kernel<<<grid_axpy, kBlock, 0, st>>>(w.st, n, w.Q, w.ldq, tvec, w.sm.y, j0, cnt, 1.0,
                                                     j0 == 0 ? 1 : 0, 0, 0, w.rb);
     PSB_LAUNCH_CHECK();
   }

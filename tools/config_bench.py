@@ -190,6 +190,39 @@ def c5(m, gmres_too=False):
     return out
 
 
+def gmres_large(m, maxiter=30):
+    """The GMRES kernels at the headline size: un-preconditioned GMRES(maxiter) on the m x m
+    Laplacian, matrix and right-hand side resident in HBM, both orthogonalisation orders.
+    Algorithmic bytes of iteration k (k = 0 .. maxiter-1, k+1 basis vectors):
+      SpMV 12 nnz + 4(n+1) + 16 n;  CGS2: two passes of (k+1) dots + (k+1) axpys over the basis,
+      i.e. 2 * [2 (k+1) + 3] * 8n;  MGS (axpy of step j-1 fused with the dot of step j: read
+      q_{j-1}, q_j, w, write w): (k+1) * 32 n;  norm + scale: 24 n."""
+    from pysolvers_b200.problems import device_fd_laplacian
+    dA = device_fd_laplacian(2, 0.0, 1.0, m, negate=True)
+    n, nnz = dA.shape[0], dA.nnz
+    b = torch.ones(n, dtype=torch.float64, device='cuda')
+    out = {'config': 'GMRES(%d), no preconditioner, 2-D 5-point Laplacian m=%d (n=%d), device-resident' % (maxiter, m, n)}
+    spmv = 12 * nnz + 4 * (n + 1) + 16 * n
+    for orth in ('cgs2', 'mgs'):
+        s = GMRES(CommonSolverArgs(maxiter=maxiter, tau=1e-300, failOnMaxiter=False, showIters=False, showFinal=False),
+                  orth=orth).makeSolver()
+        quiet(s.solve, dA, b)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st = quiet(s.solve, dA, b)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        iters = maxiter
+        if orth == 'cgs2':
+            byts = sum(spmv + 2 * (2 * (k + 1) + 3) * 8 * n + 24 * n for k in range(iters))
+        else:
+            byts = sum(spmv + (k + 1) * 32 * n + 24 * n for k in range(iters))
+        out[orth] = {'solve_s': dt, 'iters_reported': int(st.iters()), 'ms_per_iteration': 1e3 * dt / iters,
+                     'algorithmic_GB': byts / 1e9, 'achieved_GBps': byts / dt / 1e9,
+                     'final_resid': float(st.resid()) if st.resid() is not None else None}
+    return out
+
+
 def main():
     which = sys.argv[1:] or ['c1', 'c2', 'ic512', 'c5_512']
     res = {}
@@ -201,6 +234,8 @@ def main():
             res[w] = c2()
         elif w.startswith('ic'):
             res[w] = ic(int(w[2:]))
+        elif w.startswith('gmres'):
+            res[w] = gmres_large(int(w[5:]))
         elif w.startswith('c5_'):
             res[w] = c5(int(w[3:]), gmres_too=(int(w[3:]) <= 512))
         print('%s done in %.1f s' % (w, time.perf_counter() - t0), file=sys.stderr, flush=True)
