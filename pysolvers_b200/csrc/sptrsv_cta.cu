@@ -1,4 +1,5 @@
-// Sparse triangular solve with the wavefront kept in SHARED memory (one CTA).
+// Sparse triangular solve with the wavefront kept in SHARED memory: one CTA, or one thread-block
+// cluster of 4 CTAs with the window replicated through distributed shared memory.
 //
 // Why: the factors the reference produces (SuperLU IC / ILUT / LU, ICPreconditioner.py:45-63,
 // ILUTPreconditioner.py:51-78, VCycleManager.py:34-37) have thousands of dependency levels
@@ -25,14 +26,18 @@
 //  * the (col, val) pairs of a chunk are copied into a per-warp staging buffer by the TMA engine
 //    (cp.async.bulk + mbarrier) as soon as the previous chunk of the warp is done -- two rounds
 //    after an L2 prefetch of the same bytes -- so that the critical window touches shared memory
-//    only: four polls in flight, entries consumed in stored order, and after a row's last
+//    only: four polls in flight, entries consumed in the order in which they become available
+//    (oldest dependency level first, rows right-aligned in their chunk), and after a row's last
 //    dependency arrives only multiply, subtract, scale and the shared-memory store remain.
-//  * a warp that finds a dependency missing looks where the wavefront is (oldest chunk in work
-//    = min prog[]) and sleeps in proportion to the distance; only the next chunks spin.
-//  * arithmetic identical to the grid-wide kernel: b_i - sum L_ij x_j accumulated in stored
-//    column order, product rounded first, times the reciprocal of the diagonal last (invdiag is
-//    formed once, as scipy's spsolve_triangular does) -> bit-identical results, and no fp64
-//    division on the critical path.
+//  * a warp whose chunk is far behind the wavefront (oldest chunk in work = min prog[]) sleeps
+//    in proportion to the distance; only the next chunks spin, each on its own warp scheduler.
+//  * arithmetic identical to the grid-wide kernel: b_i - sum L_ij x_j accumulated in
+//    dependency-level order, product rounded first, times the reciprocal of the diagonal last
+//    (invdiag is formed once, as scipy's spsolve_triangular does) -> bit-identical results, and
+//    no fp64 division on the critical path.
+//  * cluster variant (kC = 4): every CTA keeps a replica of the window and of prog[]; results,
+//    resets and progress are stored into all replicas with st.shared::cluster; chunk g runs on
+//    CTA g mod 4 (profiles/round1g_cluster.md).
 #include "sptrsv.cuh"
 
 #include <algorithm>
