@@ -193,3 +193,44 @@ def test_split_lu_matches_superlu(cuda, tail):
     if S.n1 > 0:
         full = DeviceSplitLU(lu, tail=1).levels()
         assert S.levels()[0] <= full[0] and S.levels()[1] <= full[1]
+
+
+@pytest.mark.parametrize('m', [24, 40])
+@pytest.mark.parametrize('orth', ['mgs', 'cgs2'])
+@pytest.mark.parametrize('device', [False, True])
+def test_newton_gmres_amg_vs_reference_golden(cuda, m, orth, device):
+    """configs[4] as BASELINE.json names it: Newton with inexact, non-restarted GMRES and the AMG
+    V-cycle preconditioner (damped Jacobi) on FDBratu2D, against the run of the reference itself
+    (tests/golden/make_golden_newton_gmres.py): same Newton and GMRES iteration counts, same
+    ||F|| history, same solution -- with host operands and with u, F, J resident in HBM."""
+    import os
+    from pysolvers_b200 import CommonSolverArgs
+    from pysolvers_b200.Linear import GMRES, AMG
+    from pysolvers_b200.Nonlinear import NewtonSolver
+    from pysolvers_b200.problems import FDBratu2D, DeviceFDBratu2D
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'newton_gmres_golden.npz'))
+    func = DeviceFDBratu2D(m=m) if device else FDBratu2D(m=m)
+    lin_iters = []
+    newton = NewtonSolver(control=CommonSolverArgs(tau=1.0e-12, maxiter=10),
+                          solver=GMRES(control=CommonSolverArgs(maxiter=60), orth=orth,
+                                       precond=AMG(numIters=5, smoother=_smoother('djac'))),
+                          fixLinTol=False, minLinTol=1.0e-6, freezePrec=True)
+    inner = newton.solver
+    orig = inner.solve
+
+    def spy(J, rhs):
+        r = orig(J, rhs)
+        lin_iters.append(r.iters())
+        return r
+    inner.solve = spy
+    st, hist = _run(newton, func, func.initialU())
+    key = 'newton_gmres/bratu_m%d_djac' % m
+    assert st.success() and st.iters() == int(g[key + '/iters'])
+    assert lin_iters == g[key + '/lin_iters'].tolist()
+    gh = g[key + '/hist']
+    sel = gh > 1e-9 * gh[0]        # below that the Newton residual is the linear solver's noise
+    assert rel_err(np.asarray(hist)[sel], gh[sel]) < 1e-6
+    x = st.soln()
+    x = x.cpu().numpy() if hasattr(x, 'cpu') else x
+    gx = g[key + '/x']
+    assert np.linalg.norm(x - gx) <= 1e-8 * np.linalg.norm(gx)
