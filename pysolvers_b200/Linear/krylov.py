@@ -112,19 +112,23 @@ class PCGSolver(IterativeLinearSolver):
 
 
 class GMRES(IterativeLinearSolverType):
-    """Factory for GMRESSolver (GMRESSolver.py:27-40).  ``orth`` is an added,
-    optional knob: 'cgs2' (default, batched) or 'mgs' (the reference's
-    orthogonalisation order)."""
+    """Factory for GMRESSolver (GMRESSolver.py:27-40).  Added, optional knobs:
+    ``orth`` = 'cgs2' (default, batched) or 'mgs' (the reference's
+    orthogonalisation order); ``honorFreeze`` = keep the preconditioner while
+    ``freezePrec()`` is in force (default False: rebuilt on every solve like the
+    reference)."""
 
     def __init__(self, control=CommonSolverArgs(),
-                 precond=IdentityPreconditionerType(), name='GMRES', orth='cgs2'):
+                 precond=IdentityPreconditionerType(), name='GMRES', orth='cgs2',
+                 honorFreeze=False):
         super().__init__(control=control, precond=precond, name=name)
         self.orth = orth
+        self.honorFreeze = honorFreeze
 
     def makeSolver(self, name=None):
         return GMRESSolver(self.control(), precond=self.precond(),
                            name=self.name() if name is None else name,
-                           orth=self.orth)
+                           orth=self.orth, honorFreeze=self.honorFreeze)
 
 
 class GMRESSolver(IterativeLinearSolver):
@@ -142,10 +146,15 @@ class GMRESSolver(IterativeLinearSolver):
     """
 
     def __init__(self, control=CommonSolverArgs(),
-                 precond=IdentityPreconditionerType(), name='GMRES', orth='cgs2'):
+                 precond=IdentityPreconditionerType(), name='GMRES', orth='cgs2',
+                 honorFreeze=False):
         super().__init__(control=control, precond=precond, name=name)
         self.precond = None
         self.orth = orth
+        # added, optional: keep the formed preconditioner while ``freezePrec()`` is in force, as
+        # PCGSolver does (PCGSolver.py:92-94) -- what "AMG V-cycle preconditioner reuse" in
+        # configs[4] intends.  Default False = the reference's behaviour (rebuild on every solve).
+        self.honorFreeze = honorFreeze
         self.last_history = None
 
     def solve(self, A, b):
@@ -160,7 +169,12 @@ class GMRESSolver(IterativeLinearSolver):
         if n == 0 or _device_norm(b_d) == 0.0:
             return self.handleConvergence(0, zeros(), 0, 0)
 
-        precond = self.precondType().form(A)          # always rebuilt, see class doc
+        if self.honorFreeze and self.precond is not None and self.precFrozen():
+            precond = self.precond
+        else:
+            precond = self.precondType().form(A)      # always rebuilt by default, see class doc
+            if self.honorFreeze:
+                self.precond = precond
         prec_h = right_handle_of(precond)
         orth = {'cgs2': nat.ORTH_CGS2, 'mgs': nat.ORTH_MGS}[self.orth]
 

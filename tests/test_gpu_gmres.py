@@ -117,3 +117,31 @@ def test_gmres_preconditioner_always_rebuilt(cuda):
     _run(s, A, b)
     _run(s, A, b)
     assert Counting.built == 2
+
+
+def test_gmres_honor_freeze_is_opt_in(cuda):
+    """The reference's GMRES rebuilds its preconditioner on every solve (freezePrec has no effect,
+    GMRESSolver.py:71-72) and so does ours by default; ``honorFreeze=True`` keeps it while frozen,
+    like PCGSolver (PCGSolver.py:92-94)."""
+    import contextlib
+    import io
+    from pysolvers_b200 import CommonSolverArgs
+    from pysolvers_b200.Linear import GMRES, RightILUT
+    from pysolvers_b200.problems import load_dh_matrix
+    A = load_dh_matrix(8)
+    b = A @ np.ones(A.shape[0])
+    built = []
+    ptype = RightILUT()
+    form0 = ptype.form
+    ptype.form = lambda M: built.append(1) or form0(M)
+    for honor, want in ((False, 3), (True, 1)):
+        del built[:]
+        s = GMRES(CommonSolverArgs(maxiter=30, tau=1e-8), precond=ptype, honorFreeze=honor).makeSolver()
+        s.freezePrec()
+        outs = []
+        for _ in range(3):
+            with contextlib.redirect_stdout(io.StringIO()):
+                outs.append(s.solve(A, b))
+        assert len(built) == want
+        assert all(o.success() and o.iters() == outs[0].iters() for o in outs)
+        assert np.array_equal(outs[0].soln(), outs[2].soln())
