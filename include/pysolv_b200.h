@@ -169,6 +169,20 @@ int psb_splitlu_create(int64_t n, int64_t n1, psb_trsv_t L11, psb_trsv_t U11, ps
                        psb_csr_t U12, const double* d_invL22, const double* d_invU22,
                        const int32_t* h_perm_r, const int32_t* h_perm_c, void* stream,
                        psb_prec_t* out);
+/* General form: L and U are split independently, each in its own symmetric permutation chosen
+ * by the host (the dense block of L = the rows of its last dependency levels, the one of U = the
+ * rows of its first ones).  L-stage position p takes v[h_map_in[p]] (n1L sparse rows, then
+ * n - n1L dense ones); U-stage element p takes the L-stage result at h_map_mid[p] (NULL: same
+ * order); result[h_map_out[p]] = x[p].  Maps: HOST int32[n]. */
+int psb_splitlu2_create(int64_t n, int64_t n1L, int64_t n1U, psb_trsv_t L11, psb_trsv_t U11,
+                        psb_csr_t L21, psb_csr_t U12, const double* d_invL22,
+                        const double* d_invU22, const int32_t* h_map_in,
+                        const int32_t* h_map_mid, const int32_t* h_map_out, void* stream,
+                        psb_prec_t* out);
+/* Dependency levels of a triangular CSR matrix in HOST memory (no device work): level(i) = 1 + max
+ * level of the rows row i depends on, 0 if none. */
+int psb_tri_levels(int64_t n, const int32_t* h_rowptr, const int32_t* h_colind, int lower,
+                   int32_t* h_level);
 /* z = M^-1 r (z must not alias r).  Preconditioner.applyRight / applyLeft. */
 int psb_prec_apply(psb_prec_t P, const double* d_r, double* d_z, void* stream);
 int psb_prec_destroy(psb_prec_t P);

@@ -16,6 +16,11 @@
 //     y2 = inv(L22) (w2 - L21 y1)  SpMV + triangular GEMV
 //     x2 = inv(U22) y2             triangular GEMV
 //     x1 = U11^-1 (y1 - U12 x2)    SpMV + sparse triangular solve
+// The dense blocks are chosen by dependency LEVEL, not by position: for L the rows of its last
+// levels (level >= l*), for U the rows of its first levels, each moved to the end by a symmetric
+// permutation that keeps the factor triangular (a row of a late level never feeds an earlier one).
+// At Bratu 1024^2 (175 104 coarse rows, 3 494 levels) a dense block of 8 192 rows leaves 218 levels
+// for the sparse solves when chosen by level, 1 079 when it is simply the trailing rows.
 // Agreement with SuperLU.solve: 5e-16 relative (tests/test_gpu_amg.py).
 #include "prec.cuh"
 #include "spmv.cuh"
@@ -84,17 +89,23 @@ scatter_kernel(const double* __restrict__ v, const int32_t* __restrict__ map, in
 }
 
 struct SplitLuPrec : psb_prec {
-  int64_t n1 = 0, n2 = 0;
-  psb_trsv* L11 = nullptr;      // not owned (null when n1 == 0)
-  psb_trsv* U11 = nullptr;
-  const psb_csr* L21 = nullptr; // n2 x n1, not owned
-  const psb_csr* U12 = nullptr; // n1 x n2
-  const double* invL22 = nullptr;   // n2 x n2 row-major, not owned
-  const double* invU22 = nullptr;
-  int32_t* iperm_r = nullptr;   // owned: row r of the L solve takes v[iperm_r[r]]
-  int32_t* iperm_c = nullptr;   // owned: result[iperm_c[r]] = z[r]
-  double* buf = nullptr;        // owned: y1 (n1) | s1 (n1) | w2 (n2) | t2 (n2) | y2 (n2)
-  ~SplitLuPrec() override { cudaFree(iperm_r); cudaFree(iperm_c); cudaFree(buf); }
+  // L and U are split independently (each in its own symmetric permutation, chosen by the host:
+  // the dense block of L holds its LAST dependency levels, the one of U its FIRST ones):
+  //   L-stage works on positions p: row p takes v[map_in[p]];  n1L sparse + n2L dense rows
+  //   U-stage element p takes ycat[map_mid[p]];                 n1U sparse + n2U dense rows
+  //   result[map_out[p]] = x[p]
+  int64_t n1L = 0, n2L = 0, n1U = 0, n2U = 0;
+  psb_trsv* L11 = nullptr;      // not owned (null when n1L == 0)
+  psb_trsv* U11 = nullptr;      // not owned (null when n1U == 0)
+  const psb_csr* L21 = nullptr; // n2L x n1L, not owned
+  const psb_csr* U12 = nullptr; // n1U x n2U
+  const double* invL22 = nullptr;   // n2L x n2L row-major, not owned
+  const double* invU22 = nullptr;   // n2U x n2U
+  int32_t* map_in = nullptr;    // owned
+  int32_t* map_mid = nullptr;   // owned (null: identity, same split for L and U)
+  int32_t* map_out = nullptr;   // owned
+  double* buf = nullptr;        // owned: ycat (n) | yU (n) | w2 (max n2) | t2 (max n2) | s1 (n1U)
+  ~SplitLuPrec() override { cudaFree(map_in); cudaFree(map_mid); cudaFree(map_out); cudaFree(buf); }
   const char* kind() const override { return "splitlu"; }
   int check_error() override {
     int a = 0, b = 0;
@@ -103,39 +114,55 @@ struct SplitLuPrec : psb_prec {
     return a | b;
   }
   int apply(const double* r, double* z, const int* d_skip, cudaStream_t st) override {
-    double* y1 = buf;
-    double* s1 = buf + n1;
-    double* w2 = buf + 2 * n1;
-    double* t2 = w2 + n2;
-    double* y2 = t2 + n2;
-    const int g2 = (int)std::max<int64_t>(1, std::min<int64_t>((n2 + kBlock - 1) / kBlock, (int64_t)sm_count() * 4));
-    const int gg = (int)std::max<int64_t>(1, std::min<int64_t>((n2 + kGemvWarps - 1) / kGemvWarps, (int64_t)sm_count() * 8));
+    const int64_t n2max = std::max(n2L, n2U);
+    double* ycat = buf;                 // [y1 (n1L) | y2 (n2L)] in L order
+    double* yU = buf + n;               // the same vector in U order (aliases ycat when map_mid is null)
+    double* w2 = buf + 2 * n;
+    double* t2 = w2 + n2max;
+    double* s1 = t2 + n2max;
+    auto grid_of = [&](int64_t cnt) {
+      return (int)std::max<int64_t>(1, std::min<int64_t>((cnt + kBlock - 1) / kBlock, (int64_t)sm_count() * 4));
+    };
+    auto gemv_grid = [&](int64_t rows) {
+      return (int)std::max<int64_t>(1, std::min<int64_t>((rows + kGemvWarps - 1) / kGemvWarps, (int64_t)sm_count() * 8));
+    };
     int rc = PSB_OK;
-    if (n1 > 0) {
-      rc = trsv_solve(L11, r, y1, iperm_r, nullptr, nullptr, d_skip, st);          // y1 = L11^-1 (Pr v)_1
+    // ---- L stage: y1 = L11^-1 w1 ; y2 = inv(L22) (w2 - L21 y1) ------------------------------
+    double* y1 = ycat;
+    double* y2 = ycat + n1L;
+    if (n1L > 0) {
+      rc = trsv_solve(L11, r, y1, map_in, nullptr, nullptr, d_skip, st);
       if (rc != PSB_OK) return rc;
     }
-    gather_kernel<<<g2, kBlock, 0, st>>>(r, iperm_r, n1, n2, w2, d_skip);            // w2 = (Pr v)_2
+    gather_kernel<<<grid_of(n2L), kBlock, 0, st>>>(r, map_in, n1L, n2L, w2, d_skip);
     PSB_LAUNCH_CHECK();
     const double* rhs2 = w2;
-    if (n1 > 0) {
+    if (n1L > 0) {
       EpiArgs ea; ea.f = w2;
-      rc = spmv_launch(L21, EPI_RESID, y1, t2, ea, d_skip, st);                      // t2 = w2 - L21 y1
+      rc = spmv_launch(L21, EPI_RESID, y1, t2, ea, d_skip, st);
       if (rc != PSB_OK) return rc;
       rhs2 = t2;
     }
-    tri_gemv_kernel<true><<<gg, kGemvWarps * 32, 0, st>>>(invL22, (int)n2, rhs2, y2, d_skip);   // y2 = L22^-1 .
+    tri_gemv_kernel<true><<<gemv_grid(n2L), kGemvWarps * 32, 0, st>>>(invL22, (int)n2L, rhs2, y2, d_skip);
     PSB_LAUNCH_CHECK();
-    double* x2 = w2;                                                                 // w2 is free again
-    tri_gemv_kernel<false><<<gg, kGemvWarps * 32, 0, st>>>(invU22, (int)n2, y2, x2, d_skip);    // x2 = U22^-1 y2
+    // ---- the same vector in the order of the U split ------------------------------------------
+    const double* yu = ycat;
+    if (map_mid != nullptr) {
+      gather_kernel<<<grid_of(n), kBlock, 0, st>>>(ycat, map_mid, 0, n, yU, d_skip);
+      PSB_LAUNCH_CHECK();
+      yu = yU;
+    }
+    // ---- U stage: x2 = inv(U22) y2 ; x1 = U11^-1 (y1 - U12 x2) --------------------------------
+    double* x2 = w2;
+    tri_gemv_kernel<false><<<gemv_grid(n2U), kGemvWarps * 32, 0, st>>>(invU22, (int)n2U, yu + n1U, x2, d_skip);
     PSB_LAUNCH_CHECK();
-    scatter_kernel<<<g2, kBlock, 0, st>>>(x2, iperm_c, n1, n2, z, d_skip);           // result[iperm_c[n1 + i]] = x2[i]
+    scatter_kernel<<<grid_of(n2U), kBlock, 0, st>>>(x2, map_out, n1U, n2U, z, d_skip);
     PSB_LAUNCH_CHECK();
-    if (n1 > 0) {
-      EpiArgs ea; ea.f = y1;
-      rc = spmv_launch(U12, EPI_RESID, x2, s1, ea, d_skip, st);                      // s1 = y1 - U12 x2
+    if (n1U > 0) {
+      EpiArgs ea; ea.f = yu;
+      rc = spmv_launch(U12, EPI_RESID, x2, s1, ea, d_skip, st);          // s1 = y1 - U12 x2
       if (rc != PSB_OK) return rc;
-      rc = trsv_solve(U11, s1, y1, nullptr, z, iperm_c, d_skip, st);                 // x1 = U11^-1 s1, scattered
+      rc = trsv_solve(U11, s1, ycat, nullptr, z, map_out, d_skip, st);   // x1, scattered into z; ycat is free again
       if (rc != PSB_OK) return rc;
     }
     return PSB_OK;
@@ -148,43 +175,90 @@ struct SplitLuPrec : psb_prec {
 
 using namespace psb;
 
+static int upload_map(int32_t** d, const int32_t* h, int64_t n, cudaStream_t st) {
+  PSB_CUDA(cudaMalloc((void**)d, (size_t)n * sizeof(int32_t)));
+  PSB_CUDA(cudaMemcpyAsync(*d, h, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  return PSB_OK;
+}
+
+extern "C" int psb_splitlu2_create(int64_t n, int64_t n1L, int64_t n1U, psb_trsv_t L11, psb_trsv_t U11,
+                                   psb_csr_t L21, psb_csr_t U12, const double* d_invL22,
+                                   const double* d_invU22, const int32_t* h_map_in,
+                                   const int32_t* h_map_mid, const int32_t* h_map_out, void* stream,
+                                   psb_prec_t* out) {
+  PSB_REQUIRE(out && h_map_in && h_map_out && d_invL22 && d_invU22, PSB_ERR_ARG, "psb_splitlu2_create: NULL argument");
+  PSB_REQUIRE(n >= 1 && n1L >= 0 && n1L < n && n1U >= 0 && n1U < n, PSB_ERR_ARG,
+              "psb_splitlu2_create: need 0 <= n1 < n for both factors");
+  const int64_t n2L = n - n1L, n2U = n - n1U;
+  PSB_REQUIRE(n2L < (int64_t)46000 && n2U < (int64_t)46000, PSB_ERR_UNSUPP,
+              "psb_splitlu2_create: dense block too large for int32 indexing");
+  if (n1L > 0) {
+    PSB_REQUIRE(L11 && L21, PSB_ERR_ARG, "psb_splitlu2_create: leading blocks of L missing");
+    PSB_REQUIRE(L11->n == n1L && L11->lower && L21->n_rows == n2L && L21->n_cols == n1L, PSB_ERR_ARG,
+                "psb_splitlu2_create: L11 must be a lower factor of order n1L and L21 n2L x n1L");
+  }
+  if (n1U > 0) {
+    PSB_REQUIRE(U11 && U12, PSB_ERR_ARG, "psb_splitlu2_create: leading blocks of U missing");
+    PSB_REQUIRE(U11->n == n1U && !U11->lower && U12->n_rows == n1U && U12->n_cols == n2U, PSB_ERR_ARG,
+                "psb_splitlu2_create: U11 must be an upper factor of order n1U and U12 n1U x n2U");
+  }
+  for (int64_t i = 0; i < n; ++i) {
+    const bool bad = h_map_in[i] < 0 || h_map_in[i] >= n || h_map_out[i] < 0 || h_map_out[i] >= n ||
+                     (h_map_mid && (h_map_mid[i] < 0 || h_map_mid[i] >= n));
+    PSB_REQUIRE(!bad, PSB_ERR_ARG, "psb_splitlu2_create: map entry out of range");
+  }
+  SplitLuPrec* P = new (std::nothrow) SplitLuPrec();
+  PSB_REQUIRE(P != nullptr, PSB_ERR_ARG, "psb_splitlu2_create: out of host memory");
+  P->n = n; P->n1L = n1L; P->n2L = n2L; P->n1U = n1U; P->n2U = n2U;
+  P->L11 = n1L > 0 ? L11 : nullptr; P->L21 = n1L > 0 ? L21 : nullptr;
+  P->U11 = n1U > 0 ? U11 : nullptr; P->U12 = n1U > 0 ? U12 : nullptr;
+  P->invL22 = d_invL22; P->invU22 = d_invU22;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = upload_map(&P->map_in, h_map_in, n, st);
+  if (rc == PSB_OK) rc = upload_map(&P->map_out, h_map_out, n, st);
+  if (rc == PSB_OK && h_map_mid) rc = upload_map(&P->map_mid, h_map_mid, n, st);
+  if (rc == PSB_OK) {
+    const int64_t n2max = std::max(n2L, n2U);
+    cudaError_t e = cudaMalloc((void**)&P->buf, (size_t)(2 * n + 2 * n2max + n1U + 1) * sizeof(double));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error("psb_splitlu2_create: %s", cudaGetErrorString(e)); rc = PSB_ERR_CUDA; }
+  }
+  if (rc != PSB_OK) { delete P; return rc; }
+  *out = P;
+  return PSB_OK;
+}
+
+// the same split position for both factors, permutations as SuperLU reports them
 extern "C" int psb_splitlu_create(int64_t n, int64_t n1, psb_trsv_t L11, psb_trsv_t U11, psb_csr_t L21,
                                   psb_csr_t U12, const double* d_invL22, const double* d_invU22,
                                   const int32_t* h_perm_r, const int32_t* h_perm_c, void* stream,
                                   psb_prec_t* out) {
-  PSB_REQUIRE(out && h_perm_r && h_perm_c && d_invL22 && d_invU22, PSB_ERR_ARG, "psb_splitlu_create: NULL argument");
-  PSB_REQUIRE(n >= 1 && n1 >= 0 && n1 < n, PSB_ERR_ARG, "psb_splitlu_create: need 0 <= n1 < n");
-  const int64_t n2 = n - n1;
-  PSB_REQUIRE(n2 < (int64_t)46000, PSB_ERR_UNSUPP, "psb_splitlu_create: trailing block too large for int32 indexing");
-  if (n1 > 0) {
-    PSB_REQUIRE(L11 && U11 && L21 && U12, PSB_ERR_ARG, "psb_splitlu_create: leading blocks missing");
-    PSB_REQUIRE(L11->n == n1 && U11->n == n1 && L11->lower && !U11->lower, PSB_ERR_ARG,
-                "psb_splitlu_create: L11 / U11 must be lower / upper factors of order n1");
-    PSB_REQUIRE(L21->n_rows == n2 && L21->n_cols == n1 && U12->n_rows == n1 && U12->n_cols == n2, PSB_ERR_ARG,
-                "psb_splitlu_create: L21 must be n2 x n1 and U12 n1 x n2");
-  }
-  SplitLuPrec* P = new (std::nothrow) SplitLuPrec();
-  PSB_REQUIRE(P != nullptr, PSB_ERR_ARG, "psb_splitlu_create: out of host memory");
-  P->n = n; P->n1 = n1; P->n2 = n2;
-  P->L11 = n1 > 0 ? L11 : nullptr; P->U11 = n1 > 0 ? U11 : nullptr;
-  P->L21 = n1 > 0 ? L21 : nullptr; P->U12 = n1 > 0 ? U12 : nullptr;
-  P->invL22 = d_invL22; P->invU22 = d_invU22;
+  PSB_REQUIRE(h_perm_r && h_perm_c && n >= 1, PSB_ERR_ARG, "psb_splitlu_create: NULL argument");
   std::vector<int32_t> ipr((size_t)n), ipc((size_t)n);
   for (int64_t i = 0; i < n; ++i) {
-    if (h_perm_r[i] < 0 || h_perm_r[i] >= n || h_perm_c[i] < 0 || h_perm_c[i] >= n) {
-      delete P; set_error("psb_splitlu_create: permutation entry out of range"); return PSB_ERR_ARG;
-    }
+    PSB_REQUIRE(h_perm_r[i] >= 0 && h_perm_r[i] < n && h_perm_c[i] >= 0 && h_perm_c[i] < n, PSB_ERR_ARG,
+                "psb_splitlu_create: permutation entry out of range");
     ipr[h_perm_r[i]] = (int32_t)i;     // (Pr v)[perm_r[i]] = v[i]
     ipc[h_perm_c[i]] = (int32_t)i;     // (Pc z)[i] = z[perm_c[i]]
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMalloc((void**)&P->iperm_r, (size_t)n * sizeof(int32_t));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&P->iperm_c, (size_t)n * sizeof(int32_t));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&P->buf, (size_t)(2 * n1 + 3 * n2) * sizeof(double));
-  if (e == cudaSuccess) e = cudaMemcpyAsync(P->iperm_r, ipr.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(P->iperm_c, ipc.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) { delete P; set_error("psb_splitlu_create: %s", cudaGetErrorString(e)); return PSB_ERR_CUDA; }
-  *out = P;
+  return psb_splitlu2_create(n, n1, n1, L11, U11, L21, U12, d_invL22, d_invU22, ipr.data(), nullptr, ipc.data(),
+                             stream, out);
+}
+
+// dependency levels of a triangular CSR matrix in host memory (level = 1 + max level of the rows a
+// row depends on): the host uses them to choose the dense blocks
+extern "C" int psb_tri_levels(int64_t n, const int32_t* h_rowptr, const int32_t* h_colind, int lower,
+                              int32_t* h_level) {
+  PSB_REQUIRE(n >= 0 && h_rowptr && h_level && (n == 0 || h_colind), PSB_ERR_ARG, "psb_tri_levels: NULL argument");
+  auto visit = [&](int64_t i) {
+    int32_t lv = 0;
+    for (int32_t p = h_rowptr[i]; p < h_rowptr[i + 1]; ++p) {
+      const int32_t j = h_colind[p];
+      if (lower ? (j < i) : (j > i)) lv = std::max(lv, h_level[j] + 1);
+    }
+    h_level[i] = lv;
+  };
+  if (lower) for (int64_t i = 0; i < n; ++i) visit(i);
+  else       for (int64_t i = n - 1; i >= 0; --i) visit(i);
   return PSB_OK;
 }

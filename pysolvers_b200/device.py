@@ -268,51 +268,113 @@ DENSE_TAIL_LARGE = 16384
 DENSE_TAIL_LARGE_N = 300000
 
 
-class DeviceSplitLU(DevicePrec):
-    """x = Pc U^-1 L^-1 Pr v for a SuperLU factorisation, with the trailing ``tail`` rows of L
-    and U as dense, explicitly inverted blocks (psb_splitlu_create).  With a fill-reducing
-    ordering those rows are the top separators of the elimination tree: an almost dense
-    triangle, one dependency level per row for a sparse triangular solve (at Bratu 1024^2 the
-    leading blocks keep 1 079 of 3 494 levels).  The blocks are well conditioned (cond 20 - 60,
-    measured), the result agrees with SuperLU.solve to 5e-16.  The inverses are formed once
-    on the device (setup; torch.linalg.solve_triangular); the apply is our own kernels."""
+def tri_levels(T, lower):
+    """Dependency levels of a triangular scipy CSR matrix (host arithmetic in the library)."""
+    T = sp.csr_matrix(T)
+    n = T.shape[0]
+    ip = np.ascontiguousarray(T.indptr, dtype=np.int32)
+    ix = np.ascontiguousarray(T.indices, dtype=np.int32)
+    lev = np.zeros(n, dtype=np.int32)
+    nat.check(nat.lib().psb_tri_levels(n, ip.ctypes.data_as(C.c_void_p), ix.ctypes.data_as(C.c_void_p),
+                                       1 if lower else 0, lev.ctypes.data_as(C.c_void_p)), 'psb_tri_levels')
+    return lev
 
-    def __init__(self, lu, tail=None):
+
+def _dense_block_by_level(T, lower, tail):
+    """Symmetric permutation q (new position -> old row) that moves the dense block of a
+    triangular factor to the end, and the number n1 of rows left in front.  The block holds the
+    rows at the thin top of the elimination tree, chosen by HEIGHT: h(i) = length of the longest
+    chain of rows below i that lead to it -- the dependency level of row i for a lower factor, the
+    level of row i in the transposed (lower) matrix for an upper factor (the rows that the backward
+    solve needs first and on which the longest chains of dependents hang).  Block = {h >= h*} with
+    the smallest h* that keeps it within ``tail`` rows.  Such a set contains everything its members
+    feed (lower) / need (upper), so moving it to the end keeps the factor triangular, and the
+    sparse triangular solve on the rest has h* levels -- not the levels of an arbitrary trailing
+    index range (Bratu 1024^2 coarse L, 8 192 dense rows: 218 instead of 1 079)."""
+    n = T.shape[0]
+    h = tri_levels(T, True) if lower else tri_levels(sp.csr_matrix(T.T), True)
+    counts = np.bincount(h)
+    above = np.cumsum(counts[::-1])[::-1]                     # rows with h >= level
+    ok = np.flatnonzero(above <= tail)
+    dense = h >= (int(ok[0]) if ok.size else len(counts))
+    if not dense.any():             # the top level alone exceeds the budget: just the last row (it feeds
+        dense[n - 1] = True         # nobody in a lower factor and needs nobody in an upper one)
+    q = np.concatenate([np.flatnonzero(~dense), np.flatnonzero(dense)])
+    return q, int((~dense).sum())
+
+
+class DeviceSplitLU(DevicePrec):
+    """x = Pc U^-1 L^-1 Pr v for a SuperLU factorisation, with up to ``tail`` rows of L and of U
+    as dense, explicitly inverted blocks (psb_splitlu2_create).  With a fill-reducing ordering the
+    top separators of the elimination tree form an almost dense triangle in which every row is
+    a dependency level of its own for a sparse triangular solve.  The blocks are chosen by level
+    (``_dense_block_by_level``), independently for L and U; they are well conditioned (cond
+    20 - 60, measured), the result agrees with SuperLU.solve to 5e-16.  The inverses are formed
+    once on the device (setup; torch.linalg.solve_triangular); the apply is our own kernels.
+    ``by_level=False`` takes the trailing ``tail`` rows instead (the first version; kept for
+    comparison)."""
+
+    def __init__(self, lu, tail=None, by_level=True):
         require_cuda()
         n = int(lu.shape[0])
         if tail is None:
             tail = DENSE_TAIL_LARGE if n >= DENSE_TAIL_LARGE_N else DENSE_TAIL
-        n2 = min(n, int(tail))
-        n1 = n - n2
+        tail = max(1, min(n, int(tail)))
         L = lu.L.tocsr()
         U = lu.U.tocsr()
+        if by_level and tail < n:
+            qL, n1L = _dense_block_by_level(L, True, tail)
+            qU, n1U = _dense_block_by_level(U, False, tail)
+        else:
+            qL = qU = np.arange(n)
+            n1L = n1U = n - tail
+        ident_L = bool(np.array_equal(qL, np.arange(n)))
+        ident_U = bool(np.array_equal(qU, np.arange(n)))
+        if not ident_L:
+            L = L[qL][:, qL].tocsr()
+        if not ident_U:
+            U = U[qU][:, qU].tocsr()
         dev = torch.device('cuda', torch.cuda.current_device())
-        eye = torch.eye(n2, dtype=torch.float64, device=dev)
-        L22 = torch.from_numpy(L[n1:, n1:].toarray()).to(dev)
-        self.invL22 = torch.linalg.solve_triangular(L22, eye, upper=False, unitriangular=True).contiguous()
-        del L22
-        U22 = torch.from_numpy(U[n1:, n1:].toarray()).to(dev)
-        self.invU22 = torch.linalg.solve_triangular(U22, eye, upper=True).contiguous()
-        del U22, eye
+
+        def inverse(block, upper, unit):
+            k = block.shape[0]
+            eye = torch.eye(k, dtype=torch.float64, device=dev)
+            d = torch.from_numpy(block.toarray()).to(dev)
+            return torch.linalg.solve_triangular(d, eye, upper=upper, unitriangular=unit).contiguous()
+        self.invL22 = inverse(L[n1L:, n1L:], False, True)
+        self.invU22 = inverse(U[n1U:, n1U:], True, False)
         self.L11 = self.U11 = self.L21 = self.U12 = None
-        if n1 > 0:
-            self.L11 = DeviceTrsv(L[:n1, :n1].tocsr(), lower=True, unit_diag=True)
-            self.U11 = DeviceTrsv(U[:n1, :n1].tocsr(), lower=False)
-            self.L21 = DeviceCSR(L[n1:, :n1].tocsr())
-            self.U12 = DeviceCSR(U[:n1, n1:].tocsr())
-        pr = np.ascontiguousarray(lu.perm_r, dtype=np.int32)
-        pc = np.ascontiguousarray(lu.perm_c, dtype=np.int32)
+        if n1L > 0:
+            self.L11 = DeviceTrsv(L[:n1L, :n1L].tocsr(), lower=True, unit_diag=True)
+            self.L21 = DeviceCSR(L[n1L:, :n1L].tocsr())
+        if n1U > 0:
+            self.U11 = DeviceTrsv(U[:n1U, :n1U].tocsr(), lower=False)
+            self.U12 = DeviceCSR(U[:n1U, n1U:].tocsr())
+        # (Pr v)[perm_r[i]] = v[i]  ->  L position p (row qL[p]) takes v[iperm_r[qL[p]]]
+        # (Pc z)[i] = z[perm_c[i]]  ->  U position p (row qU[p]) goes to result[iperm_c[qU[p]]]
+        ipr = np.empty(n, dtype=np.int64)
+        ipr[np.asarray(lu.perm_r)] = np.arange(n)
+        ipc = np.empty(n, dtype=np.int64)
+        ipc[np.asarray(lu.perm_c)] = np.arange(n)
+        map_in = np.ascontiguousarray(ipr[qL], dtype=np.int32)
+        map_out = np.ascontiguousarray(ipc[qU], dtype=np.int32)
+        map_mid = None
+        if not (ident_L and ident_U) or n1L != n1U:
+            posL = np.empty(n, dtype=np.int64)
+            posL[qL] = np.arange(n)
+            map_mid = np.ascontiguousarray(posL[qU], dtype=np.int32)
         h = C.c_void_p()
         hd = lambda o: None if o is None else o.handle
-        nat.check(nat.lib().psb_splitlu_create(
-            n, n1, hd(self.L11), hd(self.U11), hd(self.L21), hd(self.U12), ptr(self.invL22),
-            ptr(self.invU22), pr.ctypes.data_as(C.c_void_p), pc.ctypes.data_as(C.c_void_p),
-            current_stream_ptr(), C.byref(h)), 'psb_splitlu_create')
+        nat.check(nat.lib().psb_splitlu2_create(
+            n, n1L, n1U, hd(self.L11), hd(self.U11), hd(self.L21), hd(self.U12), ptr(self.invL22),
+            ptr(self.invU22), map_in.ctypes.data_as(C.c_void_p),
+            None if map_mid is None else map_mid.ctypes.data_as(C.c_void_p),
+            map_out.ctypes.data_as(C.c_void_p), current_stream_ptr(), C.byref(h)), 'psb_splitlu2_create')
         super().__init__(h, n, keep=(self.L11, self.U11, self.L21, self.U12, self.invL22, self.invU22))
-        self.n1, self.n2 = n1, n2
+        self.n1, self.n2 = n1L, n - n1L
+        self.n1U, self.n2U = n1U, n - n1U
 
     def levels(self):
         """(levels of L11, levels of U11): what is left for the sparse triangular solves."""
-        if self.L11 is None:
-            return 0, 0
-        return self.L11.info()['levels'], self.U11.info()['levels']
+        return (0 if self.L11 is None else self.L11.info()['levels'],
+                0 if self.U11 is None else self.U11.info()['levels'])

@@ -170,8 +170,9 @@ def test_newton_bratu_device_resident(cuda, golden, sm):
     assert np.linalg.norm(st.soln().cpu().numpy() - gx) <= 1e-8 * np.linalg.norm(gx)
 
 
+@pytest.mark.parametrize('by_level', [True, False])
 @pytest.mark.parametrize('tail', [0, 7, 300, 100000])
-def test_split_lu_matches_superlu(cuda, tail):
+def test_split_lu_matches_superlu(cuda, tail, by_level):
     """The coarse-level solve: x = Pc U^-1 L^-1 Pr v with the trailing rows of L and U as dense,
     explicitly inverted blocks must agree with SuperLU.solve (what spsolve does in
     VCycleManager.py:34-37) to rounding, for every split position incl. all-dense and tail = 1."""
@@ -183,16 +184,22 @@ def test_split_lu_matches_superlu(cuda, tail):
     rng = np.random.default_rng(4)
     A = sp.csc_matrix(-fd_laplacian_2d(0.0, 1.0, 40)) + sp.random(1600, 1600, density=0.002, random_state=rng, format='csc')
     lu = spla.splu(A, permc_spec=COARSE_PERMC_SPEC)
-    S = DeviceSplitLU(lu, tail=max(tail, 1))
-    assert S.n2 == min(max(tail, 1), 1600) and S.n1 + S.n2 == 1600
+    S = DeviceSplitLU(lu, tail=max(tail, 1), by_level=by_level)
+    assert 1 <= S.n2 <= min(max(tail, 1), 1600) and S.n1 + S.n2 == 1600 and S.n1U + S.n2U == 1600
+    if not by_level:
+        assert S.n2 == min(max(tail, 1), 1600) and S.n2U == S.n2
     for _ in range(2):
         v = rng.standard_normal(1600)
         x = S.apply(to_device(v)).cpu().numpy()
         ref = lu.solve(v)
         assert np.linalg.norm(x - ref) <= 1e-12 * np.linalg.norm(ref)
     if S.n1 > 0:
-        full = DeviceSplitLU(lu, tail=1).levels()
+        full = DeviceSplitLU(lu, tail=1, by_level=False).levels()
         assert S.levels()[0] <= full[0] and S.levels()[1] <= full[1]
+    if by_level and tail == 300:
+        # choosing the dense rows by level leaves fewer levels than the same number of trailing rows
+        other = DeviceSplitLU(lu, tail=300, by_level=False).levels()
+        assert S.levels()[0] <= other[0] and S.levels()[1] <= other[1]
 
 
 @pytest.mark.parametrize('m', [24, 40])
