@@ -57,3 +57,17 @@ def test_hierarchy_irregular_matrices(golden, tag, nlev):
     for k in range(nlev - 1):
         _same_csr(ups[k], golden_csr(golden, '%s/P%d' % (tag, k)), 'P%d' % k)
         _same_csr(downs[k], golden_csr(golden, '%s/R%d' % (tag, k)), 'R%d' % k)
+
+
+def test_restriction_fast_path_equals_literal():
+    """restriction_of's transpose short cut gives the arrays of the reference's lil route."""
+    import scipy.sparse as sp
+    from pysolvers_b200.Linear import amg_setup
+    from pysolvers_b200.problems import FDBratu2D
+    for m in (9, 40):
+        J = sp.csr_matrix(FDBratu2D(m, 0.5).evalJ(np.ones(m * m)))
+        P, _ = amg_setup.sa_coarsen(J, lvl=1)
+        fast = amg_setup.restriction_of(P, True)
+        lit = amg_setup._restriction_literal(P, not amg_setup._normalisation_is_noop())
+        assert np.array_equal(fast.indptr, lit.indptr) and np.array_equal(fast.indices, lit.indices)
+        assert np.array_equal(fast.data, lit.data)
