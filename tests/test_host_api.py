@@ -172,3 +172,45 @@ def test_backtracking_line_search():
     ls.setNorm(npla.norm)
     ok, x, F, nF = ls.search(np.array([10.0]), abs(np.arctan(10.0)), np.array([-10.0 * 101 * np.arctan(10.0) / 10.0]), _ArcTan())
     assert ok and nF < abs(np.arctan(10.0))
+
+
+def test_dense_block_by_height_keeps_factors_triangular():
+    """Host logic of the split LU (no GPU): psb_tri_levels equals the numpy level analysis; moving the
+    rows at the top of the elimination tree to the end keeps L and U triangular; the rest has no more
+    levels than the same number of trailing rows would leave; the permuted solve is the same solve."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from oracle import precond
+    from pysolvers_b200.device import _dense_block_by_level, tri_levels
+    from pysolvers_b200.problems import fd_laplacian_2d
+    rng = np.random.default_rng(8)
+    n = 30 * 30
+    A = sp.csc_matrix(-fd_laplacian_2d(0.0, 1.0, 30)) + sp.random(n, n, density=0.003, random_state=rng, format='csc')
+    lu = spla.splu(A, permc_spec='MMD_AT_PLUS_A')
+    L, U = lu.L.tocsr(), lu.U.tocsr()
+    assert np.array_equal(tri_levels(L, True), precond.level_sets(L, lower=True)[0])
+    assert np.array_equal(tri_levels(U, False), precond.level_sets(U, lower=False)[0])
+    ipr = np.empty(n, dtype=np.int64)
+    ipr[lu.perm_r] = np.arange(n)
+    ipc = np.empty(n, dtype=np.int64)
+    ipc[lu.perm_c] = np.arange(n)
+    for tail in (1, 5, 120, n - 1):
+        qL, n1L = _dense_block_by_level(L, True, tail)
+        qU, n1U = _dense_block_by_level(U, False, tail)
+        assert sorted(qL.tolist()) == list(range(n)) and sorted(qU.tolist()) == list(range(n))
+        assert 1 <= n - n1L <= tail and 1 <= n - n1U <= tail
+        Lp, Up = L[qL][:, qL].tocsr(), U[qU][:, qU].tocsr()
+        assert sp.triu(Lp, 1).nnz == 0 and sp.tril(Up, -1).nnz == 0
+        if n1L > 0 and n - n1L > 1:
+            by_height = tri_levels(Lp[:n1L, :n1L], True).max() + 1
+            trailing = tri_levels(L[:n1L, :n1L], True).max() + 1
+            assert by_height <= trailing
+        v = rng.standard_normal(n)
+        y = spla.spsolve_triangular(Lp, v[ipr[qL]], lower=True, unit_diagonal=True)
+        posL = np.empty(n, dtype=np.int64)
+        posL[qL] = np.arange(n)
+        x = spla.spsolve_triangular(Up, y[posL[qU]], lower=False)
+        out = np.empty(n)
+        out[ipc[qU]] = x
+        ref = lu.solve(v)
+        assert np.linalg.norm(out - ref) <= 1e-12 * np.linalg.norm(ref)
