@@ -179,6 +179,15 @@ int psb_splitlu2_create(int64_t n, int64_t n1L, int64_t n1U, psb_trsv_t L11, psb
                         const double* d_invU22, const int32_t* h_map_in,
                         const int32_t* h_map_mid, const int32_t* h_map_out, void* stream,
                         psb_prec_t* out);
+/* Optional block-diagonal stage of a split LU whose sparse leading blocks had their supernodes
+ * collapsed on the host (L11 = L~ blockdiag(D), U11 = blockdiag(D) U~ with identity diagonal blocks in
+ * L~ / U~; pysolvers_b200/Linear/supernodes.py): y = B x with B = identity outside the supernodes;
+ * row r reads x[h_row0[r] + c] for c in [h_c_lo[r], h_c_hi[r]) with the weights
+ * h_vals[h_off[r] + c - h_c_lo[r]].  upper = 0: applied after the L11 solve; 1: before the U11 solve.
+ * All arrays HOST, one entry per row of the leading block. */
+int psb_splitlu_set_blockdiag(psb_prec_t P, int upper, int64_t n_rows, const int32_t* h_row0,
+                              const int32_t* h_c_lo, const int32_t* h_c_hi, const int64_t* h_off,
+                              const double* h_vals, int64_t n_vals, void* stream);
 /* Dependency levels of a triangular CSR matrix in HOST memory (no device work): level(i) = 1 + max
  * level of the rows row i depends on, 0 if none. */
 int psb_tri_levels(int64_t n, const int32_t* h_rowptr, const int32_t* h_colind, int lower,

@@ -27,6 +27,7 @@
 #include "sptrsv.cuh"
 
 #include <algorithm>
+#include <cstring>
 #include <new>
 #include <vector>
 
@@ -88,6 +89,36 @@ scatter_kernel(const double* __restrict__ v, const int32_t* __restrict__ map, in
     out[map[off + i]] = v[i];
 }
 
+// Block-diagonal stage of the supernodal collapse (Linear/supernodes.py): y = B x where B is the
+// identity outside the collapsed supernodes and a small dense triangle inside; row r reads
+// x[row0[r] + c], c in [c_lo[r], c_hi[r]), with the weights vals[off[r] + c - c_lo[r]] in that order.
+struct BlockDiag {
+  int64_t n = 0;
+  int32_t* row0 = nullptr;
+  int32_t* c_lo = nullptr;
+  int32_t* c_hi = nullptr;
+  int64_t* off = nullptr;
+  double* vals = nullptr;
+  void release() { cudaFree(row0); cudaFree(c_lo); cudaFree(c_hi); cudaFree(off); cudaFree(vals); n = 0; }
+};
+
+__global__ void __launch_bounds__(kBlock)
+blockdiag_kernel(int64_t n, const int32_t* __restrict__ row0, const int32_t* __restrict__ c_lo,
+                 const int32_t* __restrict__ c_hi, const int64_t* __restrict__ off,
+                 const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+                 const int* d_skip) {
+  if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
+  for (int64_t r = blockIdx.x * (int64_t)kBlock + threadIdx.x; r < n; r += (int64_t)gridDim.x * kBlock) {
+    const int lo = c_lo[r], hi = c_hi[r];
+    if (hi <= lo) { y[r] = x[r]; continue; }
+    const double* xv = x + row0[r];
+    const double* w = vals + off[r];
+    double acc = 0.0;
+    for (int c = lo; c < hi; ++c) acc += w[c - lo] * xv[c];
+    y[r] = acc;
+  }
+}
+
 struct SplitLuPrec : psb_prec {
   // L and U are split independently (each in its own symmetric permutation, chosen by the host:
   // the dense block of L holds its LAST dependency levels, the one of U its FIRST ones):
@@ -104,8 +135,12 @@ struct SplitLuPrec : psb_prec {
   int32_t* map_in = nullptr;    // owned
   int32_t* map_mid = nullptr;   // owned (null: identity, same split for L and U)
   int32_t* map_out = nullptr;   // owned
-  double* buf = nullptr;        // owned: ycat (n) | yU (n) | w2 (max n2) | t2 (max n2) | s1 (n1U)
-  ~SplitLuPrec() override { cudaFree(map_in); cudaFree(map_mid); cudaFree(map_out); cudaFree(buf); }
+  double* buf = nullptr;        // owned: ycat (n) | yU (n) | w2 (max n2) | t2 (max n2) | s1 (n1U) | tmp (max n1)
+  BlockDiag bdL, bdU;           // owned: block-diagonal stages of collapsed supernodes (n == 0: none)
+  ~SplitLuPrec() override {
+    cudaFree(map_in); cudaFree(map_mid); cudaFree(map_out); cudaFree(buf);
+    bdL.release(); bdU.release();
+  }
   const char* kind() const override { return "splitlu"; }
   int check_error() override {
     int a = 0, b = 0;
@@ -120,6 +155,7 @@ struct SplitLuPrec : psb_prec {
     double* w2 = buf + 2 * n;
     double* t2 = w2 + n2max;
     double* s1 = t2 + n2max;
+    double* tmp = s1 + n1U;
     auto grid_of = [&](int64_t cnt) {
       return (int)std::max<int64_t>(1, std::min<int64_t>((cnt + kBlock - 1) / kBlock, (int64_t)sm_count() * 4));
     };
@@ -131,8 +167,13 @@ struct SplitLuPrec : psb_prec {
     double* y1 = ycat;
     double* y2 = ycat + n1L;
     if (n1L > 0) {
-      rc = trsv_solve(L11, r, y1, map_in, nullptr, nullptr, d_skip, st);
+      // with collapsed supernodes: z1 = L~11^-1 w1, then y1 = blockdiag(D^-1) z1
+      rc = trsv_solve(L11, r, bdL.n ? tmp : y1, map_in, nullptr, nullptr, d_skip, st);
       if (rc != PSB_OK) return rc;
+      if (bdL.n) {
+        blockdiag_kernel<<<grid_of(n1L), kBlock, 0, st>>>(n1L, bdL.row0, bdL.c_lo, bdL.c_hi, bdL.off, bdL.vals, tmp, y1, d_skip);
+        PSB_LAUNCH_CHECK();
+      }
     }
     gather_kernel<<<grid_of(n2L), kBlock, 0, st>>>(r, map_in, n1L, n2L, w2, d_skip);
     PSB_LAUNCH_CHECK();
@@ -162,7 +203,13 @@ struct SplitLuPrec : psb_prec {
       EpiArgs ea; ea.f = yu;
       rc = spmv_launch(U12, EPI_RESID, x2, s1, ea, d_skip, st);          // s1 = y1 - U12 x2
       if (rc != PSB_OK) return rc;
-      rc = trsv_solve(U11, s1, ycat, nullptr, z, map_out, d_skip, st);   // x1, scattered into z; ycat is free again
+      const double* rhs1 = s1;
+      if (bdU.n) {                                                         // s1' = blockdiag(D^-1) s1, then U~11
+        blockdiag_kernel<<<grid_of(n1U), kBlock, 0, st>>>(n1U, bdU.row0, bdU.c_lo, bdU.c_hi, bdU.off, bdU.vals, s1, tmp, d_skip);
+        PSB_LAUNCH_CHECK();
+        rhs1 = tmp;
+      }
+      rc = trsv_solve(U11, rhs1, ycat, nullptr, z, map_out, d_skip, st);   // x1, scattered into z; ycat is free again
       if (rc != PSB_OK) return rc;
     }
     return PSB_OK;
@@ -219,12 +266,45 @@ extern "C" int psb_splitlu2_create(int64_t n, int64_t n1L, int64_t n1U, psb_trsv
   if (rc == PSB_OK && h_map_mid) rc = upload_map(&P->map_mid, h_map_mid, n, st);
   if (rc == PSB_OK) {
     const int64_t n2max = std::max(n2L, n2U);
-    cudaError_t e = cudaMalloc((void**)&P->buf, (size_t)(2 * n + 2 * n2max + n1U + 1) * sizeof(double));
+    cudaError_t e = cudaMalloc((void**)&P->buf, (size_t)(2 * n + 2 * n2max + n1U + std::max(n1L, n1U) + 1) * sizeof(double));
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { set_error("psb_splitlu2_create: %s", cudaGetErrorString(e)); rc = PSB_ERR_CUDA; }
   }
   if (rc != PSB_OK) { delete P; return rc; }
   *out = P;
+  return PSB_OK;
+}
+
+extern "C" int psb_splitlu_set_blockdiag(psb_prec_t P_, int upper, int64_t n_rows, const int32_t* h_row0,
+                                         const int32_t* h_c_lo, const int32_t* h_c_hi, const int64_t* h_off,
+                                         const double* h_vals, int64_t n_vals, void* stream) {
+  PSB_REQUIRE(P_ && h_row0 && h_c_lo && h_c_hi && h_off && (n_vals == 0 || h_vals), PSB_ERR_ARG,
+              "psb_splitlu_set_blockdiag: NULL argument");
+  PSB_REQUIRE(strcmp(P_->kind(), "splitlu") == 0, PSB_ERR_ARG, "psb_splitlu_set_blockdiag: not a split LU");
+  SplitLuPrec* P = static_cast<SplitLuPrec*>(P_);
+  PSB_REQUIRE(n_rows == (upper ? P->n1U : P->n1L) && n_rows > 0, PSB_ERR_ARG,
+              "psb_splitlu_set_blockdiag: one entry per row of the sparse leading block");
+  for (int64_t r = 0; r < n_rows; ++r) {
+    const bool bad = h_c_lo[r] < 0 || h_c_hi[r] < h_c_lo[r] || h_row0[r] < 0 || h_row0[r] + h_c_hi[r] > n_rows ||
+                     (h_c_hi[r] > h_c_lo[r] && (h_off[r] < 0 || h_off[r] + (h_c_hi[r] - h_c_lo[r]) > n_vals));
+    PSB_REQUIRE(!bad, PSB_ERR_ARG, "psb_splitlu_set_blockdiag: row descriptor out of range");
+  }
+  BlockDiag& B = upper ? P->bdU : P->bdL;
+  B.release();
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMalloc((void**)&B.row0, (size_t)n_rows * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&B.c_lo, (size_t)n_rows * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&B.c_hi, (size_t)n_rows * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&B.off, (size_t)n_rows * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&B.vals, (size_t)std::max<int64_t>(n_vals, 1) * 8);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(B.row0, h_row0, (size_t)n_rows * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(B.c_lo, h_c_lo, (size_t)n_rows * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(B.c_hi, h_c_hi, (size_t)n_rows * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(B.off, h_off, (size_t)n_rows * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n_vals) e = cudaMemcpyAsync(B.vals, h_vals, (size_t)n_vals * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { B.release(); set_error("psb_splitlu_set_blockdiag: %s", cudaGetErrorString(e)); return PSB_ERR_CUDA; }
+  B.n = n_rows;
   return PSB_OK;
 }
 

@@ -8,6 +8,7 @@ stored (possibly unsorted) column order is kept, because the STREAM SpMV sums
 each row in that order to stay bit-identical to scipy's csr_matvec.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import scipy.sparse as sp
@@ -259,12 +260,15 @@ class DevicePrec:
             pass
 
 
-# trailing rows of an LU factor pair handled as explicitly inverted dense blocks: doubling the tail
-# roughly halves the levels left for the sparse triangular solves (0.85 us each, twice per solve)
-# and quadruples the GEMV bytes (8 192 rows: 0.27 GB per factor, 45 us) -- 16 384 pays off once
-# the factors have several thousand levels
+# rows of an LU factor pair handled as explicitly inverted dense blocks: doubling the block roughly
+# halves the levels left for the sparse triangular solves (~1 us each, twice per solve) and
+# quadruples the GEMV bytes (8 192 rows: 0.27 GB per factor, 60 us).  With the supernodes of the
+# sparse part collapsed (below) 8 192 rows are the better choice at every size measured (Bratu 2048^2
+# coarse LU: 16 384 rows -> 65 levels, 1.30 ms per solve; 8 192 rows -> 82 levels, 1.16 ms).
 DENSE_TAIL = 8192
-DENSE_TAIL_LARGE = 16384
+COLLAPSE_MIN_LEVELS = 150     # collapse the supernodes of a sparse leading block only if it has this many levels
+COLLAPSE_MIN_ROWS = 8         # ... and only supernodes of at least this many rows (host cost against levels)
+DENSE_TAIL_LARGE = int(os.environ.get('PSB_DENSE_TAIL_LARGE', '8192'))     # n >= DENSE_TAIL_LARGE_N
 DENSE_TAIL_LARGE_N = 300000
 
 
@@ -312,9 +316,11 @@ class DeviceSplitLU(DevicePrec):
     20 - 60, measured), the result agrees with SuperLU.solve to 5e-16.  The inverses are formed
     once on the device (setup; torch.linalg.solve_triangular); the apply is our own kernels.
     ``by_level=False`` takes the trailing ``tail`` rows instead (the first version; kept for
-    comparison)."""
+    comparison).  ``collapse``: supernodal collapse of the sparse leading blocks
+    (Linear/supernodes.py) -- None: when they still have >= COLLAPSE_MIN_LEVELS levels; True / False:
+    always / never."""
 
-    def __init__(self, lu, tail=None, by_level=True):
+    def __init__(self, lu, tail=None, by_level=True, collapse=None):
         require_cuda()
         n = int(lu.shape[0])
         if tail is None:
@@ -344,12 +350,21 @@ class DeviceSplitLU(DevicePrec):
         self.invL22 = inverse(L[n1L:, n1L:], False, True)
         self.invU22 = inverse(U[n1U:, n1U:], True, False)
         self.L11 = self.U11 = self.L21 = self.U12 = None
+        bd_L = bd_U = None
+        self.collapsed = (0, 0)
         if n1L > 0:
-            self.L11 = DeviceTrsv(L[:n1L, :n1L].tocsr(), lower=True, unit_diag=True)
+            L11 = L[:n1L, :n1L].tocsr()
+            if collapse is not False:
+                L11, bd_L = self._collapse(L11, True, collapse)
+            self.L11 = DeviceTrsv(L11, lower=True, unit_diag=True)
             self.L21 = DeviceCSR(L[n1L:, :n1L].tocsr())
         if n1U > 0:
-            self.U11 = DeviceTrsv(U[:n1U, :n1U].tocsr(), lower=False)
+            U11 = U[:n1U, :n1U].tocsr()
+            if collapse is not False:
+                U11, bd_U = self._collapse(U11, False, collapse)
+            self.U11 = DeviceTrsv(U11, lower=False)
             self.U12 = DeviceCSR(U[:n1U, n1U:].tocsr())
+        self.collapsed = (0 if bd_L is None else bd_L[5], 0 if bd_U is None else bd_U[5])
         # (Pr v)[perm_r[i]] = v[i]  ->  L position p (row qL[p]) takes v[iperm_r[qL[p]]]
         # (Pc z)[i] = z[perm_c[i]]  ->  U position p (row qU[p]) goes to result[iperm_c[qU[p]]]
         ipr = np.empty(n, dtype=np.int64)
@@ -373,6 +388,36 @@ class DeviceSplitLU(DevicePrec):
         super().__init__(h, n, keep=(self.L11, self.U11, self.L21, self.U12, self.invL22, self.invU22))
         self.n1, self.n2 = n1L, n - n1L
         self.n1U, self.n2U = n1U, n - n1U
+        for upper, bd in ((0, bd_L), (1, bd_U)):
+            if bd is not None:
+                row0, c_lo, c_hi, off, vals, _ = bd
+                nat.check(nat.lib().psb_splitlu_set_blockdiag(
+                    h, upper, row0.shape[0], row0.ctypes.data_as(C.c_void_p), c_lo.ctypes.data_as(C.c_void_p),
+                    c_hi.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
+                    vals.ctypes.data_as(C.c_void_p), vals.shape[0], current_stream_ptr()),
+                    'psb_splitlu_set_blockdiag')
+
+    @staticmethod
+    def _collapse(T11, lower, collapse):
+        """Supernodal collapse of a sparse leading block (Linear/supernodes.py) when it still has many
+        dependency levels: (transformed block, packed block-diagonal stage) or (T11, None)."""
+        from .Linear import supernodes as SN
+        n1 = T11.shape[0]
+        if collapse is None and (n1 < 2 or int(tri_levels(T11, lower).max()) + 1 < COLLAPSE_MIN_LEVELS):
+            return T11, None
+        M = sp.csc_matrix(T11) if lower else sp.csr_matrix(T11)       # line-major: columns of L, rows of U
+        M.sort_indices()
+        line = np.repeat(np.arange(n1), np.diff(M.indptr))
+        if not np.array_equal(M.indices[M.indptr[:-1]], np.arange(n1)):
+            return T11, None                                            # a line without its diagonal first: leave it
+        ptr2, idx2, dat2, blocks = SN.collapse(M.indptr, M.indices, M.data, n1, s_min=COLLAPSE_MIN_ROWS)
+        del line
+        if not blocks:
+            return T11, None
+        cls = sp.csc_matrix if lower else sp.csr_matrix
+        T2 = cls((dat2, idx2, ptr2), shape=(n1, n1)).tocsr()
+        row0, c_lo, c_hi, off, vals = SN.pack_blocks(blocks, n1, transpose=lower)
+        return T2, (row0, c_lo, c_hi, np.ascontiguousarray(off, dtype=np.int64), vals, len(blocks))
 
     def levels(self):
         """(levels of L11, levels of U11): what is left for the sparse triangular solves."""

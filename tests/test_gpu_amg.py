@@ -241,3 +241,33 @@ def test_newton_gmres_amg_vs_reference_golden(cuda, m, orth, device):
     x = x.cpu().numpy() if hasattr(x, 'cpu') else x
     gx = g[key + '/x']
     assert np.linalg.norm(x - gx) <= 1e-8 * np.linalg.norm(gx)
+
+
+@pytest.mark.parametrize('tail', [1, 40, 400])
+def test_split_lu_supernodal_collapse(cuda, tail):
+    """Supernodes of the sparse leading blocks collapsed (identity diagonal blocks + a block-diagonal
+    stage): the same solve as SuperLU to rounding, with fewer levels left for the triangular solves."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from pysolvers_b200.Linear.multigrid import COARSE_PERMC_SPEC
+    from pysolvers_b200.device import DeviceSplitLU, to_device
+    from pysolvers_b200.problems import fd_laplacian_2d
+    import pysolvers_b200.device as dev
+    rng = np.random.default_rng(14)
+    A = sp.csc_matrix(-fd_laplacian_2d(0.0, 1.0, 60))
+    lu = spla.splu(A, permc_spec=COARSE_PERMC_SPEC)
+    old = dev.COLLAPSE_MIN_ROWS
+    dev.COLLAPSE_MIN_ROWS = 2
+    try:
+        S = DeviceSplitLU(lu, tail=tail, collapse=True)
+    finally:
+        dev.COLLAPSE_MIN_ROWS = old
+    plain = DeviceSplitLU(lu, tail=tail, collapse=False)
+    assert S.collapsed[0] > 0 and S.collapsed[1] > 0 and plain.collapsed == (0, 0)
+    assert S.levels()[0] < plain.levels()[0] and S.levels()[1] < plain.levels()[1]
+    for _ in range(2):
+        v = rng.standard_normal(3600)
+        ref = lu.solve(v)
+        for P in (S, plain):
+            x = P.apply(to_device(v)).cpu().numpy()
+            assert np.linalg.norm(x - ref) <= 1e-12 * np.linalg.norm(ref)
