@@ -71,3 +71,51 @@ def test_restriction_fast_path_equals_literal():
         lit = amg_setup._restriction_literal(P, not amg_setup._normalisation_is_noop())
         assert np.array_equal(fast.indptr, lit.indptr) and np.array_equal(fast.indices, lit.indices)
         assert np.array_equal(fast.data, lit.data)
+
+
+@pytest.mark.parametrize('s_min', [2, 8])
+def test_supernodal_collapse_is_the_same_solve(s_min):
+    """Linear/supernodes.py on the host: L = L~ blockdiag(D), U = blockdiag(D) U~ with identity
+    diagonal blocks in L~ / U~ and unchanged panel structure; solving with the collapsed factors plus
+    the block-diagonal stage equals the original triangular solves to rounding, and the collapsed
+    factors have fewer dependency levels."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from oracle import precond
+    from pysolvers_b200.Linear import supernodes as SN
+    rng = np.random.default_rng(3)
+    A = sp.csc_matrix(-fd_laplacian_2d(0.0, 1.0, 36))
+    lu = spla.splu(A, permc_spec='MMD_AT_PLUS_A')
+    n = A.shape[0]
+
+    def block_stage(blocks, x, transpose):
+        row0, c_lo, c_hi, off, vals = SN.pack_blocks(blocks, n, transpose)
+        y = x.copy()
+        for r in np.flatnonzero(c_hi > c_lo):
+            y[r] = vals[off[r]:off[r] + c_hi[r] - c_lo[r]] @ x[row0[r] + c_lo[r]:row0[r] + c_hi[r]]
+        return y
+
+    L = sp.csc_matrix(lu.L)
+    L.sort_indices()
+    first, size = SN.find_supernodes(L.indptr, L.indices, n)
+    assert first[0] == 0 and size.sum() == n and size.max() >= 8
+    ptr2, idx2, dat2, blocks = SN.collapse(L.indptr, L.indices, L.data, n, s_min=s_min)
+    Lt = sp.csc_matrix((dat2, idx2, ptr2), shape=(n, n)).tocsr()
+    assert blocks and Lt.nnz < L.nnz and sp.triu(Lt, 1).nnz == 0
+    lv0 = len(precond.level_sets(sp.csr_matrix(L), lower=True)[1]) - 1
+    lv1 = len(precond.level_sets(Lt, lower=True)[1]) - 1
+    assert lv1 < lv0
+    w = rng.standard_normal(n)
+    ref = spla.spsolve_triangular(sp.csr_matrix(L), w, lower=True, unit_diagonal=True)
+    got = block_stage(blocks, spla.spsolve_triangular(Lt, w, lower=True, unit_diagonal=True), True)
+    assert np.linalg.norm(got - ref) <= 1e-13 * np.linalg.norm(ref)
+
+    U = sp.csr_matrix(lu.U)
+    U.sort_indices()
+    ptr2, idx2, dat2, blocks = SN.collapse(U.indptr, U.indices, U.data, n, s_min=s_min)
+    Ut = sp.csr_matrix((dat2, idx2, ptr2), shape=(n, n))
+    assert blocks and sp.tril(Ut, -1).nnz == 0
+    assert len(precond.level_sets(Ut, lower=False)[1]) < len(precond.level_sets(U, lower=False)[1])
+    ref = spla.spsolve_triangular(U, w, lower=False)
+    got = spla.spsolve_triangular(Ut, block_stage(blocks, w, False), lower=False)
+    assert np.linalg.norm(got - ref) <= 1e-13 * np.linalg.norm(ref)
