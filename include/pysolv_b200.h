@@ -100,6 +100,15 @@ int psb_jacobi_sweep(psb_csr_t A, const double* d_dinv, double omega,
 int psb_dot(int64_t n, const double* d_x, const double* d_y, double* d_out,
             void* stream);
 
+/* ------------------------------------------------ setup helpers (host) -- */
+/* Phase 1 of the reference's smoothed-aggregation coarsening (SmoothedAggregation.py:84-89), a
+ * sequential sweep over the nodes, as host code: a free node whose whole strong neighbourhood
+ * (CSR lists h_s_ptr / h_s_cols, int64) is still free founds the next aggregate.  h_agg_of (int64,
+ * -1 = free) comes in with the isolated nodes assigned and *n_agg with their count; new roots are
+ * appended to h_roots (capacity n).  No device work. */
+int psb_sa_phase1(int64_t n, const int64_t* h_s_ptr, const int64_t* h_s_cols, int64_t* h_agg_of,
+                  int64_t* h_roots, int64_t* n_agg);
+
 /* --------------------------------------------- input generators (device) -- */
 /* The finite-difference Laplacians of the benchmark configurations assembled directly in HBM
  * (examples/FDLaplacian2D.py:5-23 and its 7-point 3-D extension): CSR rows [row_lo, row_hi) of the

@@ -71,31 +71,18 @@ def build_aggregates(A, lvl=1, tol=None):
     size = np.diff(s_ptr) + (~has_diag)
 
     # isolated nodes first (SmoothedAggregation.py:72-76), then phase 1 (:84-89): a node whose
-    # whole strong neighbourhood is still free founds an aggregate.  Sequential by nature;
-    # plain Python containers keep the O(nnz) sweep at ~1 us per node.
-    agg_list = [-1] * n
-    roots = []
-    for i in np.flatnonzero(size == 1).tolist():
-        agg_list[i] = len(roots)
-        roots.append(i)
-    ptr_l = s_ptr.tolist()
-    col_l = s_cols.tolist()
-    for i in range(n):
-        if agg_list[i] >= 0:
-            continue
-        a, b = ptr_l[i], ptr_l[i + 1]
-        ok = True
-        for k in range(a, b):
-            if agg_list[col_l[k]] >= 0:
-                ok = False
-                break
-        if ok:
-            j = len(roots)
-            for k in range(a, b):
-                agg_list[col_l[k]] = j
-            agg_list[i] = j
-            roots.append(i)
-    agg_of = np.asarray(agg_list, dtype=np.int64)
+    # whole strong neighbourhood is still free founds an aggregate.  Sequential by nature: the sweep
+    # runs in the library's host helper psb_sa_phase1 (a Python loop costs ~1 us per node, seconds
+    # at 4 M nodes); the pure-Python version below is kept as its restatement and fallback.
+    iso = np.flatnonzero(size == 1)
+    agg_of = np.full(n, -1, dtype=np.int64)
+    agg_of[iso] = np.arange(iso.size, dtype=np.int64)
+    roots_arr = np.empty(n, dtype=np.int64)
+    roots_arr[:iso.size] = iso
+    n_roots = _phase1_native(n, s_ptr, s_cols, agg_of, roots_arr, iso.size)
+    if n_roots is None:
+        n_roots = _phase1_python(n, s_ptr, s_cols, agg_of, roots_arr, iso.size)
+    roots = roots_arr[:n_roots]
     snapshot = agg_of.copy()
     n_agg = len(roots)
     # phase 2 (:104-127), all remaining nodes at once against the snapshot
@@ -132,6 +119,48 @@ def build_aggregates(A, lvl=1, tol=None):
         choice[node_o[good]] = agg_o[good]
         agg_of[rem] = choice[rem]
     return agg_of, n_agg, np.asarray(roots, dtype=np.int64), (strong, rows, cols, snapshot)
+
+
+def _phase1_python(n, s_ptr, s_cols, agg_of, roots, n_roots):
+    """The phase-1 sweep in plain Python containers (restatement of psb_sa_phase1)."""
+    agg_list = agg_of.tolist()
+    ptr_l = s_ptr.tolist()
+    col_l = s_cols.tolist()
+    for i in range(n):
+        if agg_list[i] >= 0:
+            continue
+        a, b = ptr_l[i], ptr_l[i + 1]
+        ok = True
+        for k in range(a, b):
+            if agg_list[col_l[k]] >= 0:
+                ok = False
+                break
+        if ok:
+            for k in range(a, b):
+                agg_list[col_l[k]] = n_roots
+            agg_list[i] = n_roots
+            roots[n_roots] = i
+            n_roots += 1
+    agg_of[:] = np.asarray(agg_list, dtype=np.int64)
+    return n_roots
+
+
+def _phase1_native(n, s_ptr, s_cols, agg_of, roots, n_roots):
+    """The same sweep in libpysolv_b200 (host code, no device needed); None if the library is
+    not available."""
+    import ctypes as C
+    try:
+        from .. import _native as nat
+        lib = nat.lib()
+    except Exception:
+        return None
+    s_ptr = np.ascontiguousarray(s_ptr, dtype=np.int64)
+    s_cols = np.ascontiguousarray(s_cols, dtype=np.int64)
+    cnt = C.c_int64(int(n_roots))
+    nat.check(lib.psb_sa_phase1(n, s_ptr.ctypes.data_as(C.c_void_p), s_cols.ctypes.data_as(C.c_void_p),
+                                agg_of.ctypes.data_as(C.c_void_p), roots.ctypes.data_as(C.c_void_p),
+                                C.byref(cnt)), 'psb_sa_phase1')
+    return int(cnt.value)
 
 
 def filtered_matrix(A, agg_of, roots, aux):

@@ -50,6 +50,7 @@ SIGNATURES = {
     'psb_spmv_add': (C.c_int, [_vp, _vp, _vp, _vp]),
     'psb_jacobi_sweep': (C.c_int, [_vp, _vp, _dbl, _vp, _vp, _vp, _vp]),
     'psb_dot': (C.c_int, [_i64, _vp, _vp, _vp, _vp]),
+    'psb_sa_phase1': (C.c_int, [_i64, _vp, _vp, _vp, _vp, C.POINTER(_i64)]),
     'psb_stencil_nnz': (_i64, [C.c_int, _i64, _i64, _i64]),
     'psb_stencil_fill': (C.c_int, [C.c_int, _i64, _i64, _i64, _dbl, _dbl, _vp, _vp, _vp, _vp]),
     'psb_trsv_create': (C.c_int, [_i64, _vp, _vp, _vp, C.c_int, C.c_int, _vp, C.POINTER(_vp)]),

@@ -119,3 +119,30 @@ def test_supernodal_collapse_is_the_same_solve(s_min):
     ref = spla.spsolve_triangular(U, w, lower=False)
     got = spla.spsolve_triangular(Ut, block_stage(blocks, w, False), lower=False)
     assert np.linalg.norm(got - ref) <= 1e-13 * np.linalg.norm(ref)
+
+
+def test_phase1_native_equals_python_sweep():
+    """psb_sa_phase1 (host code in the library) and its pure-Python restatement give the same
+    aggregates and roots."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(12)
+    n = 3000
+    G = sp.random(n, n, density=3.0 / n, random_state=rng, format='csr')
+    G = ((G + G.T) > 0).astype(np.float64).tocsr()
+    G.setdiag(0)
+    G.eliminate_zeros()
+    s_ptr = G.indptr.astype(np.int64)
+    s_cols = G.indices.astype(np.int64)
+    size = np.diff(s_ptr) + 1
+    iso = np.flatnonzero(size == 1)
+    outs = []
+    for fn in (amg_setup._phase1_native, amg_setup._phase1_python):
+        agg = np.full(n, -1, dtype=np.int64)
+        agg[iso] = np.arange(iso.size)
+        roots = np.empty(n, dtype=np.int64)
+        roots[:iso.size] = iso
+        k = fn(n, s_ptr, s_cols, agg, roots, iso.size)
+        assert k is not None
+        outs.append((k, agg.copy(), roots[:k].copy()))
+    assert outs[0][0] == outs[1][0] and outs[0][0] > iso.size
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
