@@ -201,6 +201,9 @@ int psb_splitlu_set_blockdiag(psb_prec_t P, int upper, int64_t n_rows, const int
  * level of the rows row i depends on, 0 if none. */
 int psb_tri_levels(int64_t n, const int32_t* h_rowptr, const int32_t* h_colind, int lower,
                    int32_t* h_level);
+/* Heights of the rows of an UPPER triangular CSR matrix (HOST) in its elimination tree = the levels
+ * of U^T, computed without transposing: h(i) = 1 + max h(k) over rows k < i with U[k, i] != 0. */
+int psb_tri_heights_upper(int64_t n, const int32_t* h_rowptr, const int32_t* h_colind, int32_t* h_height);
 /* z = M^-1 r (z must not alias r).  Preconditioner.applyRight / applyLeft. */
 int psb_prec_apply(psb_prec_t P, const double* d_r, double* d_z, void* stream);
 int psb_prec_destroy(psb_prec_t P);

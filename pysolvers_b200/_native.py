@@ -67,6 +67,7 @@ SIGNATURES = {
     'psb_splitlu_create': (C.c_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     'psb_splitlu2_create': (C.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     'psb_splitlu_set_blockdiag': (C.c_int, [_vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    'psb_tri_heights_upper': (C.c_int, [_i64, _vp, _vp, _vp]),
     'psb_tri_levels': (C.c_int, [_i64, _vp, _vp, C.c_int, _vp]),
     'psb_prec_apply': (C.c_int, [_vp, _vp, _vp, _vp]),
     'psb_prec_destroy': (C.c_int, [_vp]),

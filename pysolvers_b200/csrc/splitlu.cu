@@ -342,3 +342,19 @@ extern "C" int psb_tri_levels(int64_t n, const int32_t* h_rowptr, const int32_t*
   else       for (int64_t i = n - 1; i >= 0; --i) visit(i);
   return PSB_OK;
 }
+
+// Heights of the rows of an UPPER triangular CSR matrix in its elimination tree: h(i) = 1 + max h(k)
+// over the rows k < i that need row i (U[k, i] != 0), i.e. the dependency level of row i in U^T --
+// computed by pushing along the rows, without transposing (host code).
+extern "C" int psb_tri_heights_upper(int64_t n, const int32_t* h_rowptr, const int32_t* h_colind, int32_t* h_height) {
+  PSB_REQUIRE(n >= 0 && h_rowptr && h_height && (n == 0 || h_colind), PSB_ERR_ARG, "psb_tri_heights_upper: NULL argument");
+  for (int64_t i = 0; i < n; ++i) h_height[i] = 0;
+  for (int64_t k = 0; k < n; ++k) {
+    const int32_t hk = h_height[k] + 1;
+    for (int32_t p = h_rowptr[k]; p < h_rowptr[k + 1]; ++p) {
+      const int32_t i = h_colind[p];
+      if (i > k && h_height[i] < hk) h_height[i] = hk;
+    }
+  }
+  return PSB_OK;
+}

@@ -284,6 +284,19 @@ def tri_levels(T, lower):
     return lev
 
 
+def tri_heights_upper(U):
+    """h(i) = dependency level of row i in U^T for an upper triangular scipy CSR matrix, without
+    forming the transpose (host arithmetic in the library)."""
+    U = sp.csr_matrix(U)
+    n = U.shape[0]
+    ip = np.ascontiguousarray(U.indptr, dtype=np.int32)
+    ix = np.ascontiguousarray(U.indices, dtype=np.int32)
+    h = np.zeros(n, dtype=np.int32)
+    nat.check(nat.lib().psb_tri_heights_upper(n, ip.ctypes.data_as(C.c_void_p), ix.ctypes.data_as(C.c_void_p),
+                                              h.ctypes.data_as(C.c_void_p)), 'psb_tri_heights_upper')
+    return h
+
+
 def _dense_block_by_level(T, lower, tail):
     """Symmetric permutation q (new position -> old row) that moves the dense block of a
     triangular factor to the end, and the number n1 of rows left in front.  The block holds the
@@ -296,7 +309,7 @@ def _dense_block_by_level(T, lower, tail):
     sparse triangular solve on the rest has h* levels -- not the levels of an arbitrary trailing
     index range (Bratu 1024^2 coarse L, 8 192 dense rows: 218 instead of 1 079)."""
     n = T.shape[0]
-    h = tri_levels(T, True) if lower else tri_levels(sp.csr_matrix(T.T), True)
+    h = tri_levels(T, True) if lower else tri_heights_upper(T)
     counts = np.bincount(h)
     above = np.cumsum(counts[::-1])[::-1]                     # rows with h >= level
     ok = np.flatnonzero(above <= tail)

@@ -181,7 +181,7 @@ def test_dense_block_by_height_keeps_factors_triangular():
     import scipy.sparse as sp
     import scipy.sparse.linalg as spla
     from oracle import precond
-    from pysolvers_b200.device import _dense_block_by_level, tri_levels
+    from pysolvers_b200.device import _dense_block_by_level, tri_heights_upper, tri_levels
     from pysolvers_b200.problems import fd_laplacian_2d
     rng = np.random.default_rng(8)
     n = 30 * 30
@@ -190,6 +190,7 @@ def test_dense_block_by_height_keeps_factors_triangular():
     L, U = lu.L.tocsr(), lu.U.tocsr()
     assert np.array_equal(tri_levels(L, True), precond.level_sets(L, lower=True)[0])
     assert np.array_equal(tri_levels(U, False), precond.level_sets(U, lower=False)[0])
+    assert np.array_equal(tri_heights_upper(U), precond.level_sets(sp.csr_matrix(U.T), lower=True)[0])
     ipr = np.empty(n, dtype=np.int64)
     ipr[lu.perm_r] = np.arange(n)
     ipc = np.empty(n, dtype=np.int64)
