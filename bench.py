@@ -11,9 +11,13 @@ the un-preconditioned system -FDLaplacian2D(0,1,4096) x = 1.
 * ``e2e``      iterations/s through the public API ``PCGSolver.solve(A, b)`` with
                HOST operands (scipy CSR + numpy vector in pinned memory): every
                step uploads A and b and downloads x and the residual history
-* ``roofline`` dominant kernel (SpMV fused with p.Ap): algorithmic bytes
+* ``roofline`` dominant kernel = the persistent PCG kernel (one launch per step):
+               algorithmic bytes 32 n + 200 (12 nnz + 4 (n+1) + 88 n) / CUDA-event time
+               of the step; ``spmv_roofline``: the stand-alone SpMV fused with p.Ap,
                12 nnz + 4 (n+1) + 16 n per launch / mean launch time (events)
 * ``iter_roofline``  the whole iteration: 12 nnz + 4 (n+1) + 88 n bytes / time
+* ``ic_pcg``   configs[2] as named (PCG + incomplete Cholesky) at m = 1024, the largest
+               size whose SuperLU setup fits a bench run
 * ``cpu_baseline``   the oracle port (same numpy/scipy calls as the reference)
                      timed on this host on a bounded sample of the workload
 

@@ -215,3 +215,29 @@ def test_dense_block_by_height_keeps_factors_triangular():
         out[ipc[qU]] = x
         ref = lu.solve(v)
         assert np.linalg.norm(out - ref) <= 1e-12 * np.linalg.norm(ref)
+
+
+def test_bench_reference_arm_contract():
+    """``bench.py --impl reference`` (the reference's CPU path, oracle port) prints one JSON line with
+    the contract's keys; run here on a small grid so that it takes seconds."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PSB_BENCH_M='192', PSB_REF_ITERS_PER_STEP='3')
+    p = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '2',
+                        '--warmup', '1'], capture_output=True, text=True, env=env, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['metric'] == 'pcg_iterations_per_second'
+    assert line['unit'] == 'iter/s' and line['higher_is_better'] is True and line['value'] > 0
+    assert line['steps'] == 2 and line['warmup'] == 1 and line['n_gpus'] == 1
+    assert line['e2e']['value'] == line['value'] and line['e2e']['h2d_bytes_per_step'] == 0
+    cb = line['cpu_baseline']
+    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == line['value'] and 'sample' in cb
+    assert 'workload' in line['config']
+    # ranks other than 0 of a torchrun launch exit 0 without output
+    p2 = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference'], capture_output=True,
+                        text=True, env=dict(env, RANK='1', WORLD_SIZE='2'), timeout=120)
+    assert p2.returncode == 0 and p2.stdout.strip() == ''

@@ -74,3 +74,33 @@ def test_stencil_prefix_matches_host_generators():
             assert lib.psb_stencil_nnz(dim, m, 0, k) == A.indptr[k]
         assert lib.psb_stencil_nnz(dim, m, n // 3, n) == A.indptr[n] - A.indptr[n // 3]
     assert lib.psb_stencil_nnz(4, 3, 0, 1) == -1 and lib.psb_stencil_nnz(2, 3, 5, 2) == -1
+
+
+def test_argument_validation_without_a_device():
+    """Entry points reject bad arguments with an error code and a message BEFORE any device work."""
+    import ctypes as C
+    from pysolvers_b200 import _native as nat
+    lib = nat.lib()
+    out = C.c_void_p()
+    z32 = (C.c_int32 * 4)(0, 1, 2, 3)
+    one = (C.c_double * 1)(1.0)
+    # split LU: n1 must be < n, NULL maps, out-of-range map entries
+    assert lib.psb_splitlu2_create(4, 4, 0, None, None, None, None, one, one, z32, None, z32, None, C.byref(out)) < 0
+    assert b'n1' in lib.psb_last_error()
+    assert lib.psb_splitlu2_create(4, 0, 0, None, None, None, None, one, one, None, None, z32, None, C.byref(out)) < 0
+    bad = (C.c_int32 * 4)(0, 1, 2, 9)
+    assert lib.psb_splitlu2_create(4, 0, 0, None, None, None, None, one, one, bad, None, z32, None, C.byref(out)) < 0
+    assert b'map entry' in lib.psb_last_error()
+    # generators
+    assert lib.psb_stencil_fill(5, 3, 0, 1, 1.0, 1.0, None, None, None, None) < 0
+    assert lib.psb_stencil_fill(2, 3, 0, 10, 1.0, 1.0, z32, z32, one, None) < 0        # row_hi > n
+    # levels / heights helpers: NULL pointers
+    assert lib.psb_tri_levels(3, None, None, 1, None) < 0
+    assert lib.psb_tri_heights_upper(3, None, None, None) < 0
+    # kernel selection on a NULL factor
+    assert lib.psb_trsv_set_kernel(None, 1) < 0
+    assert lib.psb_trsv_info2(None, None) < 0
+    # aggregation sweep: count larger than n
+    cnt = C.c_int64(7)
+    i64 = (C.c_int64 * 4)(0, 0, 0, 0)
+    assert lib.psb_sa_phase1(3, i64, i64, i64, i64, C.byref(cnt)) < 0
