@@ -230,3 +230,30 @@ def test_prec_frozen_reuse(cuda):
     s.unfreezePrec()
     _run(s, A, np.ones(A.shape[0]))
     assert s.precond is not first
+
+
+def test_rows_longer_than_the_staging_buffer(cuda):
+    """Wide levels AND long rows: the upper triangle of a 4 x 6-point stencil on a 200 x 200 grid
+    (23 dependencies per row, ~100 rows per level, 40 000 rows).  The analysis picks the cluster
+    configuration (16 384-slot window, 15 staged entries per lane), so every chunk needs two staging
+    rounds -- in all three kernels the same bits, and the same as the row-wise restatement."""
+    from oracle import precond
+    from pysolvers_b200.device import DeviceTrsv
+    m = 200
+    rng = np.random.default_rng(31)
+    B1 = sp.diags([np.full(m - a, 1.0) for a in range(4)], list(range(4)), shape=(m, m))
+    B2 = sp.diags([np.full(m - b, 1.0) for b in range(6)], list(range(6)), shape=(m, m))
+    U = sp.kron(B2, B1).tocsr()
+    U.data = -0.04 * rng.random(U.nnz) - 0.001
+    U.setdiag(1.0 + rng.random(m * m))
+    U = U.tocsr()
+    assert sp.tril(U, -1).nnz == 0 and np.diff(U.indptr).max() == 24
+    v = rng.standard_normal(m * m)
+    dT, x = _both_kernels(U, False, False, v)
+    i2 = dT.info2()
+    assert i2['cluster_ok'] and i2['wslots'] == 16384 and i2['stage_len'] < 23
+    assert dT.info()['levels'] == 2 * m - 1
+    assert np.array_equal(x, precond.trsv_rowwise(U, v, lower=False))
+    L = sp.csr_matrix(U.T)
+    dT2, x2 = _both_kernels(L, True, False, v)
+    assert np.array_equal(x2, precond.trsv_rowwise(L, v, lower=True))
