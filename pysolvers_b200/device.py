@@ -339,45 +339,35 @@ class DeviceSplitLU(DevicePrec):
         if tail is None:
             tail = DENSE_TAIL_LARGE if n >= DENSE_TAIL_LARGE_N else DENSE_TAIL
         tail = max(1, min(n, int(tail)))
-        L = lu.L.tocsr()
-        U = lu.U.tocsr()
-        if by_level and tail < n:
-            qL, n1L = _dense_block_by_level(L, True, tail)
-            qU, n1U = _dense_block_by_level(U, False, tail)
-        else:
-            qL = qU = np.arange(n)
-            n1L = n1U = n - tail
-        ident_L = bool(np.array_equal(qL, np.arange(n)))
-        ident_U = bool(np.array_equal(qU, np.arange(n)))
-        if not ident_L:
-            L = L[qL][:, qL].tocsr()
-        if not ident_U:
-            U = U[qU][:, qU].tocsr()
+        # Host preparation of the two factors (format conversion, heights, permutation, blocks,
+        # supernodal collapse: scipy / numpy code that releases the GIL) runs for L and U side by
+        # side; everything that touches the device happens afterwards on this thread.
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=2) as pool:
+            fut_U = pool.submit(self._prepare_side, lu.U, False, n, tail, by_level, collapse)
+            pL = self._prepare_side(lu.L, True, n, tail, by_level, collapse)
+            pU = fut_U.result()
+        qL, n1L, ident_L = pL['q'], pL['n1'], pL['ident']
+        qU, n1U, ident_U = pU['q'], pU['n1'], pU['ident']
         dev = torch.device('cuda', torch.cuda.current_device())
 
-        def inverse(block, upper, unit):
-            k = block.shape[0]
+        def inverse(dense, upper, unit):
+            k = dense.shape[0]
             eye = torch.eye(k, dtype=torch.float64, device=dev)
-            d = torch.from_numpy(block.toarray()).to(dev)
+            d = torch.from_numpy(dense).to(dev)
             return torch.linalg.solve_triangular(d, eye, upper=upper, unitriangular=unit).contiguous()
-        self.invL22 = inverse(L[n1L:, n1L:], False, True)
-        self.invU22 = inverse(U[n1U:, n1U:], True, False)
+        self.invL22 = inverse(pL['T22'], False, True)
+        self.invU22 = inverse(pU['T22'], True, False)
         self.L11 = self.U11 = self.L21 = self.U12 = None
-        bd_L = bd_U = None
-        self.collapsed = (0, 0)
+        bd_L, bd_U = pL['bd'], pU['bd']
         if n1L > 0:
-            L11 = L[:n1L, :n1L].tocsr()
-            if collapse is not False:
-                L11, bd_L = self._collapse(L11, True, collapse)
-            self.L11 = DeviceTrsv(L11, lower=True, unit_diag=True)
-            self.L21 = DeviceCSR(L[n1L:, :n1L].tocsr())
+            self.L11 = DeviceTrsv(pL['T11'], lower=True, unit_diag=True)
+            self.L21 = DeviceCSR(pL['Toff'])
         if n1U > 0:
-            U11 = U[:n1U, :n1U].tocsr()
-            if collapse is not False:
-                U11, bd_U = self._collapse(U11, False, collapse)
-            self.U11 = DeviceTrsv(U11, lower=False)
-            self.U12 = DeviceCSR(U[:n1U, n1U:].tocsr())
+            self.U11 = DeviceTrsv(pU['T11'], lower=False)
+            self.U12 = DeviceCSR(pU['Toff'])
         self.collapsed = (0 if bd_L is None else bd_L[5], 0 if bd_U is None else bd_U[5])
+        del pL, pU
         # (Pr v)[perm_r[i]] = v[i]  ->  L position p (row qL[p]) takes v[iperm_r[qL[p]]]
         # (Pc z)[i] = z[perm_c[i]]  ->  U position p (row qU[p]) goes to result[iperm_c[qU[p]]]
         ipr = np.empty(n, dtype=np.int64)
@@ -409,6 +399,27 @@ class DeviceSplitLU(DevicePrec):
                     c_hi.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
                     vals.ctypes.data_as(C.c_void_p), vals.shape[0], current_stream_ptr()),
                     'psb_splitlu_set_blockdiag')
+
+    @staticmethod
+    def _prepare_side(T, lower, n, tail, by_level, collapse):
+        """Host-only preparation of one factor: CSR, dense block chosen (by height or trailing),
+        symmetric permutation, the four blocks, supernodal collapse of the sparse leading block."""
+        T = T.tocsr()
+        if by_level and tail < n:
+            q, n1 = _dense_block_by_level(T, lower, tail)
+        else:
+            q, n1 = np.arange(n), n - tail
+        ident = bool(np.array_equal(q, np.arange(n)))
+        if not ident:
+            T = T[q][:, q].tocsr()
+        out = dict(q=q, n1=n1, ident=ident, T22=T[n1:, n1:].toarray(), T11=None, Toff=None, bd=None)
+        if n1 > 0:
+            T11 = T[:n1, :n1].tocsr()
+            if collapse is not False:
+                T11, out['bd'] = DeviceSplitLU._collapse(T11, lower, collapse)
+            out['T11'] = T11
+            out['Toff'] = (T[n1:, :n1] if lower else T[:n1, n1:]).tocsr()
+        return out
 
     @staticmethod
     def _collapse(T11, lower, collapse):
