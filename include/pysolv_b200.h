@@ -241,6 +241,12 @@ int psb_pcg_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, double* d_x,
                   int32_t fail_on_maxiter, double* d_hist,
                   psb_solve_result* result, void* stream);
 
+/* Profiling hook of the persistent PCG kernel (csrc/pcg_mega.cu; no reference counterpart):
+ * solves launched afterwards record %globaltimer stamps of iterations [first_iter,
+ * first_iter + n_iters) into d_buf, laid out [iteration][CTA][6] uint64: 0 phase A starts,
+ * 1 phase A done, 2 p.Ap reduced, 3 phase B done, 4 r.r reduced.  d_buf == NULL disables. */
+int psb_debug_mega_timeline(void* d_buf, int32_t first_iter, int32_t n_iters);
+
 /* ---------------------------------------------------------------- GMRES -- */
 #define PSB_ORTH_CGS2  1  /* classical Gram-Schmidt twice, batched dots (default)   */
 #define PSB_ORTH_MGS   2  /* modified Gram-Schmidt in the reference's order

@@ -77,6 +77,7 @@ SIGNATURES = {
     'psb_pcg_workspace_bytes': (_i64, [_i64, C.c_int]),
     'psb_pcg_solve': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _dbl, _i32, _vp,
                                 C.POINTER(SolveResult), _vp]),
+    'psb_debug_mega_timeline': (C.c_int, [_vp, _i32, _i32]),
     'psb_gmres_workspace_bytes': (_i64, [_i64, _i32]),
     'psb_gmres_solve': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _dbl, _i32, _i32, _vp,
                                   C.POINTER(SolveResult), _vp]),

@@ -24,15 +24,6 @@
 
 namespace psb {
 
-struct AmgState {
-  double norm_b, norm_r, tau;
-  double bb, rr;
-  int skip;        // != 0: every kernel of the remaining cycles is a no-op
-  int cycles;      // cycles completed
-  int status;
-  int maxiter;
-};
-
 __global__ void __launch_bounds__(kBlock)
 amg_copy_kernel(double* __restrict__ dst, const double* __restrict__ src, int64_t n, const int* d_skip) {
   if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
@@ -79,30 +70,6 @@ amg_begin_kernel(AmgState* st, const int* outer_skip, int64_t n, const double* _
       st->status = PSB_MAXITER;
       st->skip = outer;
       if (!outer && bb == 0.0) { st->skip = 1; st->status = PSB_TRIVIAL; }   // x = b = 0
-    }
-  }
-}
-
-// end of a cycle: ||r||, history, strict '<' convergence test (VCycleSolver.py:87-91)
-__global__ void __launch_bounds__(kBlock)
-amg_cycle_end_kernel(AmgState* st, int64_t n, const double* __restrict__ r, double* hist, ReduceBuf rb) {
-  __shared__ double scratch[kWarps];
-  if (ld_cg(&st->skip) != 0) return;
-  double acc = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
-    acc += r[i] * r[i];
-  double t = block_sum(acc, scratch);
-  if (threadIdx.x == 0) rb.partials[blockIdx.x] = t;
-  if (last_block(rb.ticket)) {
-    double rr = sum_partials(rb.partials, gridDim.x, scratch);
-    if (threadIdx.x == 0) {
-      const double nr = sqrt(rr);
-      const int k = st->cycles;
-      st->norm_r = nr;
-      if (hist != nullptr) hist[k] = nr;
-      st->cycles = k + 1;
-      if (nr < st->tau * st->norm_b) { st->status = PSB_CONVERGED; st->skip = 1; }
-      else if (k + 1 >= st->maxiter) { st->skip = 1; }
     }
   }
 }
@@ -195,9 +162,11 @@ struct AmgPrec : psb_prec {
     return smooth(l, f, x, spare, nu_post, s);                                // :60
   }
 
-  // maxiter V-cycles on (b -> x_out); hist nullable
+  // maxiter V-cycles on (b -> x_out); hist nullable.  `final_residual`: also evaluate ||b - A x||
+  // after the LAST cycle (the solver reports it; as a preconditioner nothing depends on it --
+  // AMGPreconditioner.py:46-51 returns x whether or not the last test passes, failOnMaxiter=False).
   int solve(const double* b, double* x_out, int maxiter, double tol, double* hist,
-            const int* outer_skip, cudaStream_t s) {
+            const int* outer_skip, bool final_residual, cudaStream_t s) {
     const int top = (int)lev.size() - 1;
     AmgLevel& F = lev[top];
     const int grid = stream_grid(F.n, rb.max_grid);
@@ -221,17 +190,18 @@ struct AmgPrec : psb_prec {
         amg_copy_kernel<<<grid, kBlock, 0, s>>>(x_out, x, F.n, skip);
         PSB_LAUNCH_CHECK();
       }
-      EpiArgs ea; ea.f = b;
-      rc = spmv_launch(F.A, EPI_RESID, x_out, F.r, ea, skip, s);             // VCycleSolver.py:84
+      if (k + 1 == maxiter && !final_residual) break;
+      // r = b - A x with ||r||, the history entry and the strict '<' test done by the kernel's
+      // last CTA (VCycleSolver.py:84-91): no separate pass over r
+      EpiArgs ea; ea.f = b; ea.amg_state = st; ea.amg_hist = hist;
+      rc = spmv_launch(F.A, EPI_RESID_NORM, x_out, F.r, ea, skip, s);
       if (rc != PSB_OK) return rc;
-      amg_cycle_end_kernel<<<grid, kBlock, 0, s>>>(st, F.n, F.r, hist, rb);
-      PSB_LAUNCH_CHECK();
     }
     return PSB_OK;
   }
 
   int apply(const double* r, double* z, const int* d_skip, cudaStream_t s) override {
-    return solve(r, z, n_iters, tau, nullptr, d_skip, s);
+    return solve(r, z, n_iters, tau, nullptr, d_skip, false, s);
   }
 };
 
@@ -305,7 +275,7 @@ extern "C" int psb_amg_solve(psb_prec_t amg, const double* d_b, double* d_x, int
   PSB_REQUIRE(d_b != d_x, PSB_ERR_ARG, "psb_amg_solve: x must not alias b");
   AmgPrec* M = static_cast<AmgPrec*>(amg);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = M->solve(d_b, d_x, maxiter, tau, d_hist, nullptr, st);
+  int rc = M->solve(d_b, d_x, maxiter, tau, d_hist, nullptr, true, st);
   if (rc != PSB_OK) return rc;
   PSB_CUDA(cudaStreamSynchronize(st));
   AmgState hs;

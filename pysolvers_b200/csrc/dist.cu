@@ -817,13 +817,12 @@ static int dist_pcg_p2p(psb_dist_t D, const double* d_b, double* d_x, void* d_wo
   const int grid = stream_grid(std::max<int64_t>(n, 1), rb.max_grid);
   {
     const char* env = getenv("PSB_DIST_MEGA");
-    const bool mega_ok = D->A->kind == PSB_SPMV_STREAM && D->A->rpt == 1 && (D->r0 % 256) == 0 &&
-                         ((D->r1 % 256) == 0 || D->r1 == n) && n > 0 && !(env && env[0] == '0');
+    const bool mega_ok = D->A->kind == PSB_SPMV_STREAM && D->A->rpt == 1 && n > 0 && !(env && env[0] == '0');
     if (mega_ok) {
       // the whole solve as ONE persistent kernel per GPU; halo + all-reduces over NVLink peer memory
       MegaParams P;
       memset(&P, 0, sizeof(P));
-      P.A = *D->A; P.n = n; P.n_halo = D->n_halo;
+      P.n = n; P.n_halo = D->n_halo;
       P.b = d_b; P.x = d_x; P.Ap = Ap;
       P.r = (double*)(D->shm + D->rbuf_off);
       P.pbuf[0] = pbuf[0]; P.pbuf[1] = pbuf[1];
@@ -841,12 +840,10 @@ static int dist_pcg_p2p(psb_dist_t D, const double* d_b, double* d_x, void* d_wo
         P.push_flag[k] = D->pushes[k].remote_flag;
       }
       P.n_wait = n_wait; P.my_flags = my_flags; P.halo_epoch0 = h0e;
-      P.rot_t0 = D->r0 / 256; P.rot_t1 = (D->r1 + 255) / 256;
+      P.int_r0 = D->r0; P.int_r1 = D->r1;
       P.maxiter = maxiter; P.tau = tau; P.fail_on_maxiter = fail_on_maxiter;
-      size_t smem;
-      pcg_mega_caps(D->A, &P.cap_v, &P.cap_c, &smem);
       P.error = D->d_error;
-      rc = pcg_mega_launch(P, st);
+      rc = pcg_mega_launch(P, D->A, st);
       if (rc != PSB_OK) return rc;
       PSB_CUDA(cudaStreamSynchronize(st));
       MegaState ms;

@@ -353,7 +353,7 @@ extern "C" int psb_pcg_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, do
       char* base = (char*)d_work;
       MegaParams P;
       memset(&P, 0, sizeof(P));
-      P.A = *A; P.n = n; P.n_halo = 0;
+      P.n = n; P.n_halo = 0;
       P.b = d_b; P.x = d_x; P.r = w.r; P.Ap = w.Ap; P.pbuf[0] = w.p; P.pbuf[1] = w.p2;
       P.hist = d_hist;
       P.st = (MegaState*)base;
@@ -367,12 +367,10 @@ extern "C" int psb_pcg_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, do
       PSB_CUDA(cudaStreamSynchronize(st));                  // h_ptrs is on the stack
       P.my_slots = slots; P.slot_ptrs = d_ptrs; P.nranks = 1; P.epoch0 = 1;
       P.n_push = 0; P.n_wait = 0; P.halo_epoch0 = 1;
-      P.rot_t0 = P.rot_t1 = 0;
+      P.int_r0 = P.int_r1 = 0;
       P.maxiter = maxiter; P.tau = tau; P.fail_on_maxiter = fail_on_maxiter;
-      size_t smem;
-      pcg_mega_caps(A, &P.cap_v, &P.cap_c, &smem);
       P.error = (int*)(base + 1024 + 128);
-      rc = pcg_mega_launch(P, st);
+      rc = pcg_mega_launch(P, A, st);
       if (rc == PSB_OK) {
       PSB_CUDA(cudaStreamSynchronize(st));
       MegaState ms;

@@ -6,14 +6,27 @@
 // and the all-reduce itself is the barrier:
 //
 //   phase A   p = r + beta p_old formed on the fly (gathers + own rows), Ap = A p, CTA partial of
-//             p.Ap  (bulk-async staged STREAM SpMV, spmv_bulk.cuh); new boundary rows of p are
-//             also stored into the neighbours' halo (NVLink peer stores)
+//             p.Ap  (bulk-async staged STREAM SpMV, spmv_bulk.cuh); on its own rows the CTA also
+//             applies the PREVIOUS iteration's solution update x += alpha_{k-1} p_{k-1} (p_{k-1}
+//             is in a register there anyway); new boundary rows of p are also stored into the
+//             neighbours' halo (NVLink peer stores)
 //   reduce    CTA partials -> last CTA (ticket) -> fixed-order sum -> epoch-tagged store of the
 //             rank's value into its slot in EVERY rank's memory; all CTAs of all ranks poll their
 //             LOCAL slots and add them in rank order (same bits everywhere)
-//   phase B   x += alpha p ; r -= alpha Ap ; CTA partial of r.r ; boundary entries of r are
-//             stored into the neighbours' halo, then their halo flag is raised
+//   phase B   r -= alpha Ap ; CTA partial of r.r, on the SAME rows the CTA owned in phase A (its
+//             Ap values were written by the very same threads); boundary entries of r are stored
+//             into the neighbours' halo, then their halo flag is raised
 //   reduce    as above; convergence test (PCGSolver.py:125-131) taken identically by every CTA
+//
+// Vector traffic per iteration: r, p_old, x read + p, Ap, x written (A) and r, Ap read + r written
+// (B) = 72 n bytes (SURVEY.md section 8d counts 88 n for the three-kernel form).  The last
+// x += alpha p is applied when the loop ends.
+//
+// Latency of the two barriers is what limits strong scaling (profiles/round2_mega_timeline.md), so
+// everything that does not depend on the reduced scalar is put in flight BEFORE the CTA polls: the
+// bulk copies of its first SpMV tile (the matrix never changes) and the loads of its first
+// phase-B rows.  Rows per tile are chosen per launch so that every CTA gets the same number of
+// tiles (no tail round).
 //
 // alpha, beta, r.r live in registers (every CTA derives the same values from the same slots);
 // kernel-launch boundaries, their drain/fill bubbles and the NCCL launches are gone.  The
@@ -28,215 +41,338 @@
 
 namespace psb {
 
+__device__ __forceinline__ unsigned long long mega_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 // Grid-wide (and rank-wide) sum of `v`.  Every thread of every CTA calls it; all return the same
-// bits.  `raise`: the calling phase stored halo data into the neighbours' memory -- publish it
-// (system fence by every thread, flags by the last CTA).
+// bits.  `pushed`: this thread stored halo data into a neighbour's memory since the last raise
+// (it orders those stores system-wide before its CTA takes the ticket).  `raise`: the last CTA
+// publishes the halo by raising the neighbours' flags to `halo_epoch`.  `push_base` (lanes
+// 0..nranks-1 of warp 0): this rank's ring-0 slot in rank <lane>'s memory.  Returns false in
+// *ok when a peer never answered.
 __device__ __forceinline__ double mega_allreduce(const MegaParams& P, double v, unsigned int epoch,
-                                                 double* scratch, bool raise,
-                                                 unsigned long long halo_epoch) {
+                                                 double* scratch, bool pushed, bool raise,
+                                                 unsigned long long halo_epoch,
+                                                 unsigned long long* push_base, bool* ok) {
   __shared__ double s_sum;
+  __shared__ int s_ok;
   const double t = block_sum(v, scratch);
   if (threadIdx.x == 0) P.partials[blockIdx.x] = t;
-  if (raise && P.n_push > 0) __threadfence_system();
+  if (pushed) __threadfence_system();
+  const size_t ring = (size_t)(epoch % kRing) * kMaxRanks * 2;
   if (last_block(P.ticket)) {
     const double s = sum_partials(P.partials, gridDim.x, scratch);
-    if (threadIdx.x == 0)
-      for (int q = 0; q < P.nranks; ++q)
-        peer_push(P.slot_ptrs[(size_t)(epoch % kRing) * P.nranks + q], s, epoch);
-    if (raise && threadIdx.x < P.n_push) {
+    if ((int)threadIdx.x < P.nranks) peer_push(push_base + ring, s, epoch);
+    if (raise && (int)threadIdx.x < P.n_push) {
       __threadfence_system();
       asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(P.push_flag[threadIdx.x]), "l"(halo_epoch) : "memory");
     }
   }
   if (threadIdx.x < 32) {                       // one lane per rank polls, then a fixed-order sum
     double mine = 0.0;
-    if ((int)threadIdx.x < P.nranks) {
-      if (!peer_wait(P.my_slots + ((size_t)(epoch % kRing) * kMaxRanks + threadIdx.x) * 2, epoch, &mine))
-        *P.error = 1;
-    }
+    bool good = true;
+    if ((int)threadIdx.x < P.nranks) good = peer_wait(P.my_slots + ring + threadIdx.x * 2, epoch, &mine);
     double s = 0.0;
     for (int q = 0; q < P.nranks; ++q) s += __shfl_sync(0xffffffffu, mine, q);
-    if (threadIdx.x == 0) s_sum = s;
+    const bool all_good = __all_sync(0xffffffffu, good);
+    if (threadIdx.x == 0) { s_sum = s; s_ok = all_good ? 1 : 0; if (!all_good) *P.error = 1; }
   }
   __syncthreads();
   __threadfence();                              // acquire; invalidates L1 (weak loads below see fresh data)
+  *ok = s_ok != 0;
   return s_sum;
 }
 
-__device__ __forceinline__ double2 mega_ld2(const double* p) {     // coherent, no L1 allocation
-  double2 v;
-  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+__device__ __forceinline__ double mega_ld(const double* p) {       // coherent, no L1 allocation
+  double v;
+  asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
-
-__device__ __forceinline__ void mega_push_r(const MegaParams& P, long long i, double v) {
-#pragma unroll
-  for (int k = 0; k < kMaxPush; ++k)
-    if (k < P.n_push && i >= P.push_off[k] && i < P.push_off[k] + P.push_cnt[k])
-      P.push_r[k][i - P.push_off[k]] = v;
+__device__ __forceinline__ void mega_st(double* p, double v) {
+  asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
 }
 
-template <int MINB, bool C16>
+__device__ __forceinline__ bool mega_push_r(const MegaParams& P, int i, double v) {
+  bool did = false;
+#pragma unroll
+  for (int k = 0; k < kMaxPush; ++k)
+    if (k < P.n_push && i >= P.push_off[k] && i < P.push_off[k] + P.push_cnt[k]) {
+      P.push_r[k][i - P.push_off[k]] = v;
+      did = true;
+    }
+  return did;
+}
+
+template <int MINB, bool C16, int G>
 __global__ void __launch_bounds__(kBlock, MINB)
 pcg_mega_kernel(const MegaParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double scratch[kWarps];
-  __shared__ __align__(8) uint64_t full[2];
+  __shared__ __align__(8) BulkShared bsh;
+  constexpr int kMegaUnroll = MINB <= 4 ? 4 : 2;   // phase-B tiles whose loads are in flight together
   BulkPipe pipe;
-  bulk_pipe_init(pipe, smem_raw, full, P.cap_v, P.cap_c);
+  bulk_pipe_init(pipe, smem_raw, &bsh, P.cap_v, P.cap_c);
+  pipe.tile_rows = P.tile_rows;
 
-  const long long n = P.n;
-  const long long gtid = blockIdx.x * (long long)kBlock + threadIdx.x;
-  const long long gstride = (long long)gridDim.x * kBlock;
-  const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
+  const int n = (int)P.n;                                // rows fit 31 bits (psb_csr_create)
+  const int tid = threadIdx.x;
+  const int R = P.tile_rows;
+  const int n_tiles = (n + R - 1) / R;
+  const int rot_t0 = (int)P.rot_t0, rot_t1 = (int)P.rot_t1;
+  const int n_int = rot_t1 - rot_t0;
+  const int gstep = gridDim.x;
+  // my tiles: logical lt = blockIdx.x + j * gridDim.x, interior tiles first (as in bulk_pass)
+  auto tile_row = [&](int lt) -> int {
+    const int t = lt < n_int ? rot_t0 + lt : (lt < rot_t1 ? lt - n_int : lt);
+    return t * R + tid;                              // this thread's row of the tile
+  };
+  auto row_ok = [&](int lt, int row) -> bool { return lt < n_tiles && tid < R && row < n; };
+  const bool leader = blockIdx.x == 0 && tid == 0;
   unsigned int e = P.epoch0;
   const unsigned long long h0 = P.halo_epoch0;
+  unsigned long long* push_base = nullptr;
+  if (tid < P.nranks) push_base = P.slot_ptrs[tid];          // ring 0; ring k is kMaxRanks * 2 words further
+
+  // constant part of the SpMV arguments; the bounds of the first two tiles are cached
+  EpiArgs ea;
+  ea.rot_t0 = P.rot_t0; ea.rot_t1 = P.rot_t1;
+  ea.error_flag = P.error;
+  ea.pp_n = P.n_push;
+#pragma unroll
+  for (int k = 0; k < kMaxPush; ++k) { ea.pp_off[k] = P.push_off[k]; ea.pp_cnt[k] = P.push_cnt[k]; }
+  ea.xsol = P.x;
+  bulk_cache_bounds<1, C16>(P.A, ea, pipe);
+
+  unsigned long long* tl = nullptr;                          // profiling: 6 stamps per CTA per iteration
+  auto stamp = [&](int it, int slot) {
+    if (tl != nullptr && tid == 0 && it >= P.tl_first && it < P.tl_first + P.tl_count)
+      tl[((size_t)(it - P.tl_first) * gridDim.x + blockIdx.x) * 6 + slot] = mega_now();
+  };
+  tl = P.timeline;
 
   // ---- init: r = b, x = 0, p_{-1} = 0 (so that p_0 = r + 0 * p_{-1}), b.b  (PCGSolver.py:97-102)
   double acc = 0.0;
-  for (long long i = gtid; i < n; i += gstride) {
-    const double v = P.b[i];
-    P.r[i] = v; P.x[i] = 0.0; P.pbuf[1][i] = 0.0;
-    mega_push_r(P, i, v);
-    acc += v * v;
+  bool pushed = false, ok = true;
+  for (int lt = blockIdx.x; lt < n_tiles; lt += gstep) {
+    const int row = tile_row(lt);
+    if (row_ok(lt, row)) {
+      const double v = P.b[row];
+      P.r[row] = v; P.x[row] = 0.0; P.pbuf[1][row] = 0.0;
+      pushed |= mega_push_r(P, row, v);
+      acc += v * v;
+    }
   }
-  for (long long i = gtid; i < P.n_halo; i += gstride) P.pbuf[1][n + i] = 0.0;
-  const double bb = mega_allreduce(P, acc, e++, scratch, true, h0);
+  for (int i = blockIdx.x * kBlock + tid; i < (int)P.n_halo; i += gstep * kBlock) P.pbuf[1][n + i] = 0.0;
+  bulk_prime<1, C16>(P.A, ea, pipe);
+  const double bb = mega_allreduce(P, acc, e++, scratch, pushed, true, h0, push_base, &ok);
   const double norm_b = sqrt(bb);
   int status = PSB_MAXITER, k_final = 0, n_hist = 0;
   double norm_r = 0.0;
-  if (bb == 0.0) {                                          // :87-88
+  double alpha = 0.0;                                       // alpha of the previous iteration
+  bool flush_x = false;
+  if (!ok) {
+    status = PSB_MAXITER;
+  } else if (bb == 0.0) {                                   // :87-88
     status = PSB_TRIVIAL;
   } else {
     double rr_old = bb;                                     // dot(u, r) with u = r
     double beta = 0.0;
     for (int it = 0;; ++it) {
-      if (*((volatile int*)P.error) != 0) { status = PSB_MAXITER; k_final = it; break; }
-      // ---------------- phase A: p = r + beta p_old ; Ap = A p ; p.Ap -------------------------
-      EpiArgs ea;
+      // ---------------- phase A: p = r + beta p_old ; Ap = A p ; p.Ap ; x += alpha_prev p_old ------
+      stamp(it, 0);
       ea.pold = P.pbuf[(it + 1) & 1];
       ea.pnew = P.pbuf[it & 1];
-      ea.rot_t0 = P.rot_t0; ea.rot_t1 = P.rot_t1;
-      ea.error_flag = P.error;
       if (P.n_wait > 0) { ea.wait_flags = P.my_flags; ea.wait_n = P.n_wait; ea.wait_value = h0 + (unsigned long long)it; }
-      ea.pp_n = P.n_push;
 #pragma unroll
-      for (int k = 0; k < kMaxPush; ++k) {
-        ea.pp_off[k] = P.push_off[k]; ea.pp_cnt[k] = P.push_cnt[k]; ea.pp_remote[k] = P.push_p[it & 1][k];
-      }
+      for (int k = 0; k < kMaxPush; ++k) ea.pp_remote[k] = P.push_p[it & 1][k];
+      ea.alpha_prev = alpha;
       acc = 0.0;
-      bulk_pass<EPI_DOT_PUP, 1, C16>(P.A, P.r, P.Ap, ea, beta, pipe, acc);
-      const double pAp = mega_allreduce(P, acc, e++, scratch, false, 0ull);
+      bulk_pass<EPI_DOT_PUP, 1, C16, G>(P.A, P.r, P.Ap, ea, beta, pipe, acc);
+      stamp(it, 1);
+      // first phase-B rows: r and this thread's own Ap are final -> loads in flight across the barrier
+      double rv[kMegaUnroll], av[kMegaUnroll];
+#pragma unroll
+      for (int u = 0; u < kMegaUnroll; ++u) {
+        const int lt = blockIdx.x + u * gstep;
+        const int row = tile_row(lt);
+        rv[u] = 0.0; av[u] = 0.0;
+        if (row_ok(lt, row)) { rv[u] = mega_ld(P.r + row); av[u] = mega_ld(P.Ap + row); }
+      }
+      const double pAp = mega_allreduce(P, acc, e++, scratch, false, false, 0ull, push_base, &ok);
+      stamp(it, 2);
+      if (!ok) { status = PSB_MAXITER; k_final = it; break; }
       if (pAp == 0.0) { status = PSB_BREAKDOWN_PAP; k_final = it; break; }     // :114-115
-      const double alpha = rr_old / pAp;                                         // :118
-      // ---------------- phase B: x += alpha p ; r -= alpha Ap ; r.r ------------------------------
-      const double* p = P.pbuf[it & 1];
+      alpha = rr_old / pAp;                                                       // :118
+      // ---------------- phase B: r -= alpha Ap ; r.r  (x += alpha p is deferred to the next phase A)
       acc = 0.0;
-      const long long n2 = n >> 1;
-      // two independent 128-bit chunks per thread per trip, streaming (no L1 allocation)
-      long long i = gtid;
-      for (; i + gstride < n2; i += 2 * gstride) {
-        const long long j = i + gstride;
-        double2 x0 = mega_ld2(P.x + 2 * i), p0 = mega_ld2(p + 2 * i), r0 = mega_ld2(P.r + 2 * i), a0 = mega_ld2(P.Ap + 2 * i);
-        double2 x1 = mega_ld2(P.x + 2 * j), p1 = mega_ld2(p + 2 * j), r1 = mega_ld2(P.r + 2 * j), a1 = mega_ld2(P.Ap + 2 * j);
-        x0.x = x0.x + alpha * p0.x; x0.y = x0.y + alpha * p0.y;
-        r0.x = r0.x - alpha * a0.x; r0.y = r0.y - alpha * a0.y;
-        x1.x = x1.x + alpha * p1.x; x1.y = x1.y + alpha * p1.y;
-        r1.x = r1.x - alpha * a1.x; r1.y = r1.y - alpha * a1.y;
-        st_stream2(P.x + 2 * i, x0); st_stream2(P.r + 2 * i, r0);
-        st_stream2(P.x + 2 * j, x1); st_stream2(P.r + 2 * j, r1);
-        if (P.n_push > 0) {
-          mega_push_r(P, 2 * i, r0.x); mega_push_r(P, 2 * i + 1, r0.y);
-          mega_push_r(P, 2 * j, r1.x); mega_push_r(P, 2 * j + 1, r1.y);
+      pushed = false;
+      for (int base = blockIdx.x; base < n_tiles; base += kMegaUnroll * gstep) {
+        if (base != blockIdx.x) {
+#pragma unroll
+          for (int u = 0; u < kMegaUnroll; ++u) {
+            const int lt = base + u * gstep;
+            const int row = tile_row(lt);
+            if (row_ok(lt, row)) { rv[u] = mega_ld(P.r + row); av[u] = mega_ld(P.Ap + row); }
+          }
         }
-        acc += r0.x * r0.x; acc += r0.y * r0.y;
-        acc += r1.x * r1.x; acc += r1.y * r1.y;
+#pragma unroll
+        for (int u = 0; u < kMegaUnroll; ++u) {
+          const int lt = base + u * gstep;
+          const int row = tile_row(lt);
+          if (row_ok(lt, row)) {
+            const double rn = rv[u] - alpha * av[u];                               // :122
+            mega_st(P.r + row, rn);
+            if (P.n_push > 0) pushed |= mega_push_r(P, row, rn);
+            acc += rn * rn;
+          }
+        }
       }
-      for (; i < n2; i += gstride) {
-        double2 x0 = mega_ld2(P.x + 2 * i), p0 = mega_ld2(p + 2 * i), r0 = mega_ld2(P.r + 2 * i), a0 = mega_ld2(P.Ap + 2 * i);
-        x0.x = x0.x + alpha * p0.x; x0.y = x0.y + alpha * p0.y;
-        r0.x = r0.x - alpha * a0.x; r0.y = r0.y - alpha * a0.y;
-        st_stream2(P.x + 2 * i, x0); st_stream2(P.r + 2 * i, r0);
-        if (P.n_push > 0) { mega_push_r(P, 2 * i, r0.x); mega_push_r(P, 2 * i + 1, r0.y); }
-        acc += r0.x * r0.x; acc += r0.y * r0.y;
-      }
-      if ((n & 1) && leader) {
-        const long long i = n - 1;
-        const double xv = P.x[i] + alpha * p[i];
-        const double rv = P.r[i] - alpha * P.Ap[i];
-        P.x[i] = xv; P.r[i] = rv;
-        mega_push_r(P, i, rv);
-        acc += rv * rv;
-      }
-      const double rr = mega_allreduce(P, acc, e++, scratch, true, h0 + (unsigned long long)it + 1ull);
+      stamp(it, 3);
+      bulk_prime<1, C16>(P.A, ea, pipe);              // first tile of the next phase A: copies in flight
+      const double rr = mega_allreduce(P, acc, e++, scratch, pushed, true, h0 + (unsigned long long)it + 1ull,
+                                       push_base, &ok);
+      stamp(it, 4);
+      if (!ok) { status = PSB_MAXITER; k_final = it; break; }
       norm_r = sqrt(rr);                                                         // :125
       if (leader) P.hist[it] = norm_r;                                           // :126
       n_hist = it + 1;
       if ((norm_r <= P.tau * norm_b) || (!P.fail_on_maxiter && it == P.maxiter - 1)) {   // :129-131
-        status = PSB_CONVERGED; k_final = it; break;
+        status = PSB_CONVERGED; k_final = it; flush_x = true; break;
       }
-      if (it + 1 >= P.maxiter) { status = PSB_MAXITER; k_final = it; break; }
+      if (it + 1 >= P.maxiter) { status = PSB_MAXITER; k_final = it; flush_x = true; break; }
       beta = rr / rr_old;                                                        // :135
       rr_old = rr;
     }
   }
+  bulk_drain(pipe);
+  if (flush_x) {                                            // the last x += alpha p  (:121)
+    const double* p = P.pbuf[k_final & 1];
+    for (int lt = blockIdx.x; lt < n_tiles; lt += gstep) {
+      const int row = tile_row(lt);
+      if (row_ok(lt, row)) P.x[row] = P.x[row] + alpha * mega_ld(p + row);
+    }
+  }
   if (leader) {
     P.st->norm_b = norm_b; P.st->norm_r = norm_r;
-    P.st->status = status; P.st->k_final = k_final; P.st->n_hist = n_hist; P.st->done = 1;
+    P.st->status = status; P.st->k_final = k_final; P.st->n_hist = n_hist; P.st->done = ok ? 1 : 0;
     P.st->epochs_used = e - P.epoch0;
     P.st->halo_epochs_used = (unsigned int)n_hist + 1u;
   }
 }
 
-void pcg_mega_caps(const psb_csr* A, int* cap_v, int* cap_c, size_t* smem) {
-  const int mt = A->max_tile_nnz[0];
-  *cap_v = (mt + 2 + 1) & ~1;
-  *cap_c = (mt + 6 + 3) & ~3;
+static void mega_caps(int tile_nnz, int* cap_v, int* cap_c, size_t* smem) {
+  *cap_v = (tile_nnz + 2 + 1) & ~1;
+  *cap_c = (tile_nnz + 6 + 3) & ~3;
   *smem = 2 * ((size_t)*cap_v * 8 + (size_t)*cap_c * 4 + (size_t)(kBlock + 4) * 4);
 }
 
-template <int MINB, bool C16>
-static int mega_launch_t(const MegaParams& P, cudaStream_t stream) {
-  int cv, cc;
-  size_t smem;
-  pcg_mega_caps(&P.A, &cv, &cc, &smem);
+// Rows per tile (multiple of 4, <= 256) such that the CTAs of a `grid_max`-CTA grid get the same
+// number of tiles: minimise rounds * (rows + overhead), the per-tile overhead (pipeline hand-over,
+// barrier) weighed as 24 rows.  8 192 tiles of 256 rows on 740 CTAs are 12 rounds for 11.07 of
+// work (8 % idle); 240-row tiles make it 12 rounds for 11.81.
+static int balanced_tile_rows(long long n, long long grid_max) {
+  int best = kBlock;
+  long long best_cost = -1;
+  for (int r = kBlock; r >= kBlock / 2; r -= 4) {
+    const long long tiles = (n + r - 1) / r;
+    const long long rounds = (tiles + grid_max - 1) / grid_max;
+    const long long cost = rounds * (r + 24);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = r; }
+  }
+  return best;
+}
+
+static unsigned long long* g_timeline = nullptr;
+static int g_tl_first = 0, g_tl_count = 0;
+
+template <int MINB, bool C16, int G>
+static int mega_launch_t(MegaParams& P, psb_csr* A, cudaStream_t stream) {
   static thread_local int per_sm = 0;
   static thread_local size_t cached_smem = 0;
-  if (per_sm == 0 || cached_smem != smem) {
-    if (smem > 48 * 1024)
-      PSB_CUDA(cudaFuncSetAttribute(pcg_mega_kernel<MINB, C16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_mega_kernel<MINB, C16>, kBlock, smem));
+  size_t smem_max;
+  int cv, cc;
+  mega_caps(A->max_tile_nnz[0], &cv, &cc, &smem_max);       // upper bound: full 256-row tiles
+  if (per_sm == 0 || cached_smem != smem_max) {
+    if (smem_max > 48 * 1024)
+      PSB_CUDA(cudaFuncSetAttribute(pcg_mega_kernel<MINB, C16, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_mega_kernel<MINB, C16, G>, kBlock, smem_max));
     if (per_sm < 1) { set_error("pcg_mega_launch: kernel does not fit on an SM"); return PSB_ERR_UNSUPP; }
-    cached_smem = smem;
+    cached_smem = smem_max;
   }
-  const long long tiles = (P.A.n_rows + kBlock - 1) / kBlock;
-  const long long want = std::max<long long>(tiles, (P.n + kBlock * 8 - 1) / (kBlock * 8));
-  long long grid = std::min<long long>((long long)per_sm * sm_count(), std::max<long long>(want, 1));
-  grid = std::min<long long>(grid, (long long)sm_count() * 16);       // partial buffers hold this many
-  MegaParams Q = P;
-  void* args[] = {(void*)&Q};
-  PSB_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_mega_kernel<MINB, C16>, dim3((unsigned)grid), dim3(kBlock),
-                                       args, smem, stream));
+  const long long grid_max = std::min<long long>((long long)per_sm * sm_count(), (long long)sm_count() * 16);
+  // ---- tile plan, cached on the matrix handle ----
+  if (A->mega_grid != (int)grid_max || A->mega_tile_rows <= 0) {
+    const char* env = getenv("PSB_MEGA_TILE_ROWS");
+    // balanced tiles measured no better than full ones (profiles/round2_mega_timeline.md: the SMs,
+    // not the CTAs, have to be balanced, and 5 CTAs per SM even out a missing tile): opt-in only
+    int rows = env ? (atoi(env) == 0 ? balanced_tile_rows(P.n, grid_max) : atoi(env)) : kBlock;
+    if (rows < 4 || rows > kBlock || (rows & 3)) rows = kBlock;
+    int tile_nnz = A->max_tile_nnz[0];
+    if (rows != kBlock) {
+      int rc = csr_max_tile_nnz(A, rows, &tile_nnz, stream);
+      if (rc != PSB_OK) return rc;
+    }
+    A->mega_grid = (int)grid_max; A->mega_tile_rows = rows; A->mega_tile_nnz = tile_nnz;
+  }
+  P.tile_rows = A->mega_tile_rows;
+  size_t smem;
+  mega_caps(A->mega_tile_nnz, &P.cap_v, &P.cap_c, &smem);
+  if (smem > smem_max) { set_error("pcg_mega_launch: tile plan exceeds the shared-memory bound"); return PSB_ERR_UNSUPP; }
+  const long long R = P.tile_rows;
+  const long long tiles = (P.n + R - 1) / R;
+  P.rot_t0 = 0; P.rot_t1 = 0;
+  if (P.int_r1 > P.int_r0) {
+    const long long t0 = (P.int_r0 + R - 1) / R;
+    const long long t1 = P.int_r1 >= P.n ? tiles : P.int_r1 / R;
+    if (t1 > t0) { P.rot_t0 = t0; P.rot_t1 = t1; }
+  }
+  P.timeline = g_timeline; P.tl_first = g_tl_first; P.tl_count = g_tl_count;
+  const long long grid = std::max<long long>(1, std::min<long long>(grid_max, tiles));
+  void* args[] = {(void*)&P};
+  PSB_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_mega_kernel<MINB, C16, G>, dim3((unsigned)grid), dim3(kBlock),
+                                       args, smem_max, stream));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return PSB_OK;
 }
 
-int pcg_mega_launch(const MegaParams& P, cudaStream_t stream) {
-  // resident CTAs per SM the kernel is compiled for: 4 (64 registers), 5 (48) or 6 (40)
-  static int minb = 0;
+int pcg_mega_launch(MegaParams& P, psb_csr* A, cudaStream_t stream) {
+  // Kernel variant = (resident CTAs per SM it is compiled for, gathers per row loaded together).
+  // Measured on B200 (profiles/round2_mega_timeline.md): 4 CTAs per SM with 64 registers and the
+  // loads of a WHOLE stencil row (5 or 7 gathers = 10 / 14 loads) in flight at once beat 5 CTAs
+  // with 48 registers and 4 gathers by 5 % (C3) - 8 % (3-D).  PSB_MEGA_MINB=5 selects the latter.
+  static int minb = 0, g_env = 0;
   if (minb == 0) {
     const char* env = getenv("PSB_MEGA_MINB");
-    minb = env ? atoi(env) : 5;       // measured best on B200: 5 CTAs/SM, 48 registers, no spills
-    if (minb < 4 || minb > 6) minb = 5;
+    minb = env ? atoi(env) : 4;
+    if (minb != 4 && minb != 5) minb = 4;
+    env = getenv("PSB_MEGA_G");
+    g_env = env ? atoi(env) : -1;
   }
-  if (P.A.colind16 != nullptr) {
-    if (minb == 6) return mega_launch_t<6, true>(P, stream);
-    if (minb == 4) return mega_launch_t<4, true>(P, stream);
-    return mega_launch_t<5, true>(P, stream);
-  }
-  if (minb == 6) return mega_launch_t<6, false>(P, stream);
-  if (minb == 4) return mega_launch_t<4, false>(P, stream);
-  return mega_launch_t<5, false>(P, stream);
+  P.A = *A;
+  const bool c16 = P.A.colind16 != nullptr;
+  int g = g_env > 0 ? g_env : std::min(std::max(A->max_row, 4), 8);
+  if (minb == 5) g = 4;
+#define PSB_MEGA_CASE(MB, GG)                                                        \
+  if (minb == MB && g == GG)                                                         \
+    return c16 ? mega_launch_t<MB, true, GG>(P, A, stream) : mega_launch_t<MB, false, GG>(P, A, stream);
+  PSB_MEGA_CASE(5, 4)
+  PSB_MEGA_CASE(4, 4) PSB_MEGA_CASE(4, 5) PSB_MEGA_CASE(4, 6) PSB_MEGA_CASE(4, 7) PSB_MEGA_CASE(4, 8)
+#undef PSB_MEGA_CASE
+  set_error("pcg_mega_launch: no kernel variant for PSB_MEGA_MINB=%d PSB_MEGA_G=%d", minb, g);
+  return PSB_ERR_UNSUPP;
 }
 
 }  // namespace psb
+
+// Profiling hook: the persistent PCG kernels launched afterwards record %globaltimer stamps of
+// iterations [first_iter, first_iter + n_iters) into d_buf, laid out [iteration][CTA][6] u64:
+// 0 phase A starts, 1 phase A done, 2 p.Ap reduced, 3 phase B done, 4 r.r reduced.  NULL disables.
+extern "C" int psb_debug_mega_timeline(void* d_buf, int32_t first_iter, int32_t n_iters) {
+  psb::g_timeline = (unsigned long long*)d_buf;
+  psb::g_tl_first = first_iter;
+  psb::g_tl_count = d_buf ? n_iters : 0;
+  return PSB_OK;
+}

@@ -42,17 +42,24 @@ struct MegaParams {
   int n_wait;
   const unsigned long long* my_flags;
   unsigned long long halo_epoch0;
-  long long rot_t0, rot_t1;                      // interior tiles first
+  long long int_r0, int_r1;                      // rows [int_r0, int_r1) touch no halo column (set by the caller)
   int maxiter;
   double tau;
   int fail_on_maxiter;
-  int cap_v, cap_c;
   int* error;
+  // ---- filled by pcg_mega_launch ----
+  int tile_rows;                                 // rows per SpMV tile, balanced over the grid
+  long long rot_t0, rot_t1;                      // interior tiles [rot_t0, rot_t1) run first
+  int cap_v, cap_c;
+  unsigned long long* timeline;                  // profiling (psb_debug_mega_timeline), nullable
+  int tl_first, tl_count;
 };
 
-// Whole PCG solve (identity preconditioner) in ONE cooperative launch.  Fills *st (device).
-int pcg_mega_launch(const MegaParams& P, cudaStream_t stream);
-// shared-memory bytes / staging capacities of the STREAM pipeline for A (256-row tiles)
-void pcg_mega_caps(const psb_csr* A, int* cap_v, int* cap_c, size_t* smem);
+// Whole PCG solve (identity preconditioner) in ONE cooperative launch.  Fills *P.st (device).
+// `A` is the handle P.A was copied from: the tile plan (rows per tile, fullest tile) is cached on it.
+int pcg_mega_launch(MegaParams& P, psb_csr* A, cudaStream_t stream);
+
+// most nonzeros in any tile of `tile_rows` consecutive rows starting at row 0 (spmv.cu; synchronises)
+int csr_max_tile_nnz(const psb_csr* A, int tile_rows, int* out, cudaStream_t stream);
 
 }  // namespace psb

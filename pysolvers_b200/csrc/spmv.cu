@@ -60,6 +60,19 @@ __global__ void csr_stats_kernel(const int* __restrict__ rowptr, int64_t n_rows,
   atomicMax(&stats[2], m_t512);
 }
 
+// most nonzeros in a tile of `tile_rows` consecutive rows (tiles start at row 0 of the view)
+__global__ void csr_tile_stats_kernel(const int* __restrict__ rowptr, int64_t n_rows, int tile_rows,
+                                      int* __restrict__ out) {
+  int m = 0;
+  const int64_t n_tiles = (n_rows + tile_rows - 1) / tile_rows;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_tiles;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t a = t * tile_rows, e = min(a + tile_rows, n_rows);
+    m = max(m, rowptr[e] - rowptr[a]);
+  }
+  atomicMax(out, m);
+}
+
 static int g_cols16 = -1;     // 16-bit column distances for banded matrices: -1 ask PSB_SPMV_C16, 0 off, 1 on
 
 // colind[k] - row as int16 for every entry; *fail is raised when one does not fit
@@ -81,11 +94,24 @@ __global__ void csr_delta16_kernel(const int* __restrict__ rowptr, const int* __
 template <int EPI>
 __device__ __forceinline__ void finish_dot(double acc, const psb_csr A, const EpiArgs& ea,
                                            double* scratch) {
-  if (EPI != EPI_DOT && EPI != EPI_DOT_PUP) return;
+  if (EPI != EPI_DOT && EPI != EPI_DOT_PUP && EPI != EPI_RESID_NORM) return;
   double t = block_sum(acc, scratch);
   if (threadIdx.x == 0) A.partials[blockIdx.x] = t;
   if (last_block(A.ticket)) {
     double total = sum_partials(A.partials, gridDim.x, scratch);
+    if (EPI == EPI_RESID_NORM) {               // end of a V-cycle (VCycleSolver.py:87-91)
+      if (threadIdx.x == 0 && ea.amg_state != nullptr) {
+        AmgState* st = ea.amg_state;
+        const double nr = sqrt(total);
+        const int k = st->cycles;
+        st->norm_r = nr;
+        if (ea.amg_hist != nullptr) ea.amg_hist[k] = nr;
+        st->cycles = k + 1;
+        if (nr < st->tau * st->norm_b) { st->status = PSB_CONVERGED; st->skip = 1; }
+        else if (k + 1 >= st->maxiter) { st->skip = 1; }
+      }
+      return;
+    }
     if (threadIdx.x == 0) {
       if (ea.dot_accumulate) total = *ea.dot + total;
       *ea.dot = total;
@@ -200,14 +226,16 @@ spmv_bulk_kernel(const psb_csr A, const double* x, double* y, const EpiArgs ea,
                  const int* __restrict__ d_skip, int cap_v, int cap_c) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double scratch[kWarps];
-  __shared__ __align__(8) uint64_t full[2];
+  __shared__ __align__(8) BulkShared bsh;
   if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
   double beta = 0.0;
   if (EPI == EPI_DOT_PUP) beta = ld_cg(ea.beta_num) / ld_cg(ea.beta_den);     // PCGSolver.py:135
   BulkPipe P;
-  bulk_pipe_init(P, smem_raw, full, cap_v, cap_c);
+  bulk_pipe_init(P, smem_raw, &bsh, cap_v, cap_c);
   double acc = 0.0;
-  bulk_pass<EPI, RPT, C16>(A, x, y, ea, beta, P, acc);
+  // all loads of a row of <= 8 entries in flight at once; the fused direction update doubles the
+  // loads per gather, so it stays at 4
+  bulk_pass<EPI, RPT, C16, (EPI == EPI_DOT_PUP ? 4 : 8)>(A, x, y, ea, beta, P, acc);
   finish_dot<EPI>(acc, A, ea, scratch);
 }
 
@@ -362,7 +390,40 @@ psb_csr csr_row_view(const psb_csr* A, int64_t r0, int64_t r1) {
   v.rowptr = A->rowptr + r0;
   v.n_rows = r1 - r0;
   v.row_off = A->row_off + r0;
+  // max_tile_nnz was measured on tiles aligned to 256 / 512 parent rows; the view's tiles start
+  // at r0.  A misaligned tile straddles two aligned ones, so twice the parent's figure (or the
+  // longest row times the tile height, if smaller) bounds it -- the stages are sized from this.
+  for (int i = 0; i < 2; ++i) {
+    const int64_t rows = (int64_t)kBlock * (i + 1);
+    if (r0 % rows != 0) {
+      const int64_t twice = 2 * (int64_t)A->max_tile_nnz[i];
+      const int64_t by_row = rows * (int64_t)A->max_row;
+      v.max_tile_nnz[i] = (int)std::min<int64_t>(twice, by_row);
+    }
+  }
+  v.mega_grid = 0; v.mega_tile_rows = 0; v.mega_tile_nnz = 0;
   return v;
+}
+
+int csr_max_tile_nnz(const psb_csr* A, int tile_rows, int* out, cudaStream_t st) {
+  if (tile_rows < 1) { set_error("csr_max_tile_nnz: bad tile size"); return PSB_ERR_ARG; }
+  *out = 0;
+  if (A->n_rows == 0) return PSB_OK;
+  int* d = nullptr;
+  PSB_CUDA(cudaMalloc(&d, sizeof(int)));
+  cudaError_t e = cudaMemsetAsync(d, 0, sizeof(int), st);
+  if (e == cudaSuccess) {
+    const int64_t tiles = (A->n_rows + tile_rows - 1) / tile_rows;
+    const int grid = (int)std::min<int64_t>((tiles + kBlock - 1) / kBlock, (int64_t)sm_count() * 8);
+    csr_tile_stats_kernel<<<std::max(grid, 1), kBlock, 0, st>>>(A->rowptr, A->n_rows, tile_rows, d);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaPeekAtLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) { set_error("csr_max_tile_nnz: %s", cudaGetErrorString(e)); return PSB_ERR_CUDA; }
+  return PSB_OK;
 }
 
 int spmv_launch(const psb_csr* A, Epi epi, const double* x, double* y, const EpiArgs& ea,
@@ -379,6 +440,7 @@ int spmv_launch(const psb_csr* A, Epi epi, const double* x, double* y, const Epi
     case EPI_RESID:  return launch_epi<EPI_RESID>(A, x, y, ea, d_skip, st);
     case EPI_ADD:    return launch_epi<EPI_ADD>(A, x, y, ea, d_skip, st);
     case EPI_JACOBI: return launch_epi<EPI_JACOBI>(A, x, y, ea, d_skip, st);
+    case EPI_RESID_NORM: return launch_epi<EPI_RESID_NORM>(A, x, y, ea, d_skip, st);
     default: break;
   }
   set_error("spmv_launch: unknown epilogue %d", (int)epi);
@@ -428,9 +490,10 @@ extern "C" int psb_csr_create(int64_t n_rows, int64_t n_cols, int64_t nnz,
   PSB_REQUIRE(A != nullptr, PSB_ERR_ARG, "psb_csr_create: out of host memory");
   A->n_rows = n_rows; A->n_cols = n_cols; A->nnz = nnz; A->row_off = 0;
   A->rowptr = d_rowptr; A->colind = d_colind; A->vals = d_vals;
-  A->vec_loads = aligned16(d_colind) && aligned16(d_vals);
+  A->vec_loads = aligned16(d_colind) && aligned16(d_vals) && aligned16(d_rowptr);   // rowptr is bulk-copied too
   A->max_grid = sm_count() * 16;
   A->partials = nullptr; A->ticket = nullptr; A->colind16 = nullptr;
+  A->mega_grid = 0; A->mega_tile_rows = 0; A->mega_tile_nnz = 0;
   int h_stats[4] = {0, 0, 0, 0};        // longest row, fullest 256- / 512-row tile, "a column delta does not fit 16 bits"
   int* d_stats = nullptr;
   cudaError_t e = cudaMalloc(&A->partials, sizeof(double) * A->max_grid);

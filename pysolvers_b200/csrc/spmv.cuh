@@ -19,6 +19,8 @@ struct psb_csr {
   double*       partials;   // per-CTA partial sums of the fused dot
   unsigned int* ticket;     // last-CTA ticket
   int  max_grid;        // CTAs the partial buffer can hold
+  // persistent PCG kernel: tile plan cached per (grid) -- rows per tile and the fullest such tile
+  int  mega_grid, mega_tile_rows, mega_tile_nnz;
 };
 
 namespace psb {
@@ -31,7 +33,19 @@ enum Epi : int {
   EPI_JACOBI = 4,  // y = x + omega * dinv .* (f - A x)
   EPI_DOT_PUP = 5, // PCG: p = x + beta*pold formed on the fly (gathers and own row), pnew = p,
                    // y = A p, dot = p . y   (STREAM kernel only)
+  EPI_RESID_NORM = 6,  // y = f - A x ; sum of y^2 handed to the finish hook below (AMG cycle end)
   EPI_COUNT
+};
+
+// State of a V-cycle solve (amg.cu); lives here because the residual SpMV that ends a cycle
+// finishes it in its own last CTA (EPI_RESID_NORM) instead of a separate pass over r.
+struct AmgState {
+  double norm_b, norm_r, tau;
+  double bb, rr;
+  int skip;        // != 0: every kernel of the remaining cycles is a no-op
+  int cycles;      // cycles completed
+  int status;
+  int maxiter;
 };
 
 struct EpiArgs {
@@ -45,6 +59,12 @@ struct EpiArgs {
   double*       pnew = nullptr;
   const double* beta_num = nullptr;
   const double* beta_den = nullptr;
+  // RESID_NORM: the last CTA ends the V-cycle -- ||r||, history, strict '<' test (VCycleSolver.py:87-91)
+  AmgState*     amg_state = nullptr;
+  double*       amg_hist = nullptr;
+  // DOT_PUP, persistent PCG: deferred solution update xsol += alpha_prev * pold on the tile's own rows
+  double*       xsol = nullptr;
+  double        alpha_prev = 0.0;
   // DOT_PUP, multi-GPU: rows in [pp_off, pp_off+pp_cnt) of the new p are also stored into the
   // neighbour's halo at pp_remote
   int pp_n = 0;

@@ -3,10 +3,6 @@
 #pragma once
 #include "spmv.cuh"
 
-#ifndef PSB_PUP_WINDOW
-#define PSB_PUP_WINDOW 0
-#endif
-
 namespace psb {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -42,26 +38,57 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 
 // ---------------------------------------------------------------------------
-// epilogue shared by both kernels
+// epilogue shared by all SpMV kernels.  The operands that belong to the ROW itself (f, dinv,
+// x[row], y[row]) are loaded by epi_preload BEFORE the row's gathers are consumed, so that they
+// travel together with them instead of costing a second memory round trip per tile.
 // ---------------------------------------------------------------------------
+struct EpiRow { double a, b, c; };
+
 template <int EPI>
-__device__ __forceinline__ void epilogue(int64_t row, double sum, const double* x, double* y,
-                                         const EpiArgs& ea, double& acc) {
+__device__ __forceinline__ EpiRow epi_preload(int64_t row, const double* x, const double* y, const EpiArgs& ea) {
+  EpiRow o;
+  o.a = 0.0; o.b = 0.0; o.c = 0.0;
+  if (EPI == EPI_DOT) {
+    o.a = __ldg(x + row);
+  } else if (EPI == EPI_RESID || EPI == EPI_RESID_NORM) {
+    o.a = ea.f[row];
+  } else if (EPI == EPI_ADD) {
+    o.a = y[row];
+  } else if (EPI == EPI_JACOBI) {
+    o.a = ea.f[row]; o.b = ea.dinv[row]; o.c = __ldg(x + row);
+  }
+  return o;
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_finish(int64_t row, double sum, const EpiRow& o, double* y,
+                                           const EpiArgs& ea, double& acc) {
   if (EPI == EPI_STORE) {
     y[row] = sum;
   } else if (EPI == EPI_DOT) {
     y[row] = sum;
-    acc += __ldg(x + row) * sum;
+    acc += o.a * sum;
   } else if (EPI == EPI_RESID) {
-    y[row] = ea.f[row] - sum;
+    y[row] = o.a - sum;
+  } else if (EPI == EPI_RESID_NORM) {
+    const double r = o.a - sum;
+    y[row] = r;
+    acc += r * r;
   } else if (EPI == EPI_ADD) {
-    y[row] = y[row] + sum;
+    y[row] = o.a + sum;
   } else if (EPI == EPI_JACOBI) {
-    double r = ea.f[row] - sum;
-    double d = ea.dinv[row] * r;
+    double r = o.a - sum;
+    double d = o.b * r;
     if (ea.omega != 1.0) d = ea.omega * d;
-    y[row] = __ldg(x + row) + d;
+    y[row] = o.c + d;
   }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue(int64_t row, double sum, const double* x, double* y,
+                                         const EpiArgs& ea, double& acc) {
+  const EpiRow o = epi_preload<EPI>(row, x, y, ea);
+  epi_finish<EPI>(row, sum, o, y, ea, acc);
 }
 
 
@@ -82,116 +109,204 @@ __device__ __forceinline__ void wait_for_halo(const EpiArgs& ea) {
 
 // Double-buffered staging area of one CTA: two stages of
 //   vals[cap_v] doubles | cols[cap_c] ints | rp[R + 4] ints     (all 16-byte aligned)
+// the part of the pipeline state only the producer (thread 0) touches lives in shared memory:
+// persistent kernels are short of registers
+struct BulkShared {
+  uint64_t full[2];         // two mbarriers
+  uint64_t pol;             // L2 evict-first policy
+  int s_first, e_first, s_second, e_second;   // nonzero bounds of this CTA's first two tiles
+  int s_next, e_next;       // bounds of the tile to be staged next, between prime and pass
+};
 struct BulkPipe {
   unsigned char* smem;      // dynamic shared memory
-  uint64_t* full;           // two mbarriers
+  BulkShared* sh;
+  uint64_t* full;           // = sh->full
   int cap_v, cap_c;
   uint32_t phase_bits;      // parity of each stage's barrier; carried across passes
-  uint64_t pol;             // L2 evict-first policy (thread 0)
+  int tile_rows;            // rows per tile at run time (multiple of 4, <= kBlock * RPT); 0 = kBlock * RPT
+  // bulk_prime() already staged the first tile of the coming pass (thread 0 keeps the bounds
+  // of the second one): lets a persistent kernel put the first copies in flight BEFORE it
+  // waits at a grid barrier
+  bool primed;
+  bool issued;              // ... and a copy is really in flight (the CTA owns at least one tile)
+  // the bounds of the first two tiles are iteration-invariant: cached (in sh) by a persistent
+  // kernel so that priming costs no global load
+  bool bounds_cached;
 };
 
-__device__ __forceinline__ void bulk_pipe_init(BulkPipe& P, unsigned char* smem, uint64_t* full,
+__device__ __forceinline__ void bulk_pipe_init(BulkPipe& P, unsigned char* smem, BulkShared* sh,
                                                int cap_v, int cap_c) {
-  P.smem = smem; P.full = full; P.cap_v = cap_v; P.cap_c = cap_c; P.phase_bits = 0u; P.pol = 0;
+  P.smem = smem; P.sh = sh; P.full = sh->full; P.cap_v = cap_v; P.cap_c = cap_c; P.phase_bits = 0u;
+  P.tile_rows = 0; P.primed = false; P.issued = false;
+  P.bounds_cached = false;
   if (threadIdx.x == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+    mbar_init(&sh->full[0], 1);
+    mbar_init(&sh->full[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    P.pol = policy_evict_first();
+    sh->pol = policy_evict_first();
+    sh->s_first = sh->e_first = sh->s_second = sh->e_second = sh->s_next = sh->e_next = 0;
   }
   __syncthreads();
 }
 
-// One pass over all tiles of A assigned to this CTA (grid-stride).  `beta` is used by
-// EPI_DOT_PUP only.  x may have been written earlier by this same kernel (persistent PCG):
-// it is read through the coherent path.
-template <int EPI, int RPT, bool C16 = false>
-__device__ __forceinline__ void bulk_pass(const psb_csr& A, const double* x, double* y,
-                                          const EpiArgs& ea, const double beta, BulkPipe& P,
-                                          double& acc) {
-  constexpr int R = kBlock * RPT;
-  const uint64_t pol = P.pol;
-  uint64_t* const full = P.full;
-  unsigned char* const smem_raw = P.smem;
-  const int cap_v = P.cap_v, cap_c = P.cap_c;
-  const int tid = threadIdx.x;
-  const size_t stage_bytes = (size_t)cap_v * 8 + (size_t)cap_c * 4 + (size_t)(R + 4) * 4;
-  const int64_t n_tiles = (A.n_rows + R - 1) / R;
+// Tile bookkeeping shared by bulk_prime and bulk_pass: which rows a logical tile covers and how
+// its three slices are staged.  All members are cheap to rebuild (a few registers).
+template <int RPT, bool C16>
+struct BulkTiler {
+  static constexpr int kCA = C16 ? 7 : 3;                    // column entries per 16 bytes, minus 1
+  const psb_csr& A;
+  const EpiArgs& ea;
+  const BulkPipe& P;
+  int R;                                                     // rows per tile (run time)
+  int64_t n_tiles, n_int;
+  int nnz_v_lim, nnz_c_lim, rp_lim;
+  size_t stage_bytes;
+
+  __device__ __forceinline__ BulkTiler(const psb_csr& A_, const EpiArgs& ea_, const BulkPipe& P_)
+      : A(A_), ea(ea_), P(P_) {
+    R = P.tile_rows > 0 ? P.tile_rows : kBlock * RPT;
+    n_tiles = (A.n_rows + R - 1) / R;
+    n_int = ea.rot_t1 - ea.rot_t0;
+    nnz_v_lim = (int)(A.nnz & ~(int64_t)1);                  // bulk copies stop at the last
+    nnz_c_lim = (int)(A.nnz & ~(int64_t)kCA);                // whole 16-byte chunk of each array
+    rp_lim = (int)((A.n_rows + 1) & ~(int64_t)3);
+    stage_bytes = (size_t)P.cap_v * 8 + (size_t)P.cap_c * 4 + (size_t)(kBlock * RPT + 4) * 4;
+  }
   // logical -> physical tile: interior tiles [rot_t0, rot_t1) first (multi-GPU overlap)
-  const int64_t n_int = ea.rot_t1 - ea.rot_t0;
-  auto phys = [&](int64_t t) -> int64_t {
+  __device__ __forceinline__ int64_t phys(int64_t t) const {
     return t < n_int ? ea.rot_t0 + t : (t < ea.rot_t1 ? t - n_int : t);
-  };
-  bool waited = (ea.wait_n == 0);
-  const int nnz_v_lim = (int)(A.nnz & ~(int64_t)1);          // bulk copies stop at the last
-  constexpr int kCA = C16 ? 7 : 3;                           // column entries per 16 bytes, minus 1
-  const int nnz_c_lim = (int)(A.nnz & ~(int64_t)kCA);        // whole 16-byte chunk of each array
-  const int rp_lim = (int)((A.n_rows + 1) & ~(int64_t)3);
-
-  auto stage_vals = [&](int st) { return reinterpret_cast<double*>(smem_raw + st * stage_bytes); };
-  auto stage_cols = [&](int st) { return reinterpret_cast<int*>(smem_raw + st * stage_bytes + (size_t)cap_v * 8); };
-  auto stage_rp = [&](int st) {
-    return reinterpret_cast<int*>(smem_raw + st * stage_bytes + (size_t)cap_v * 8 + (size_t)cap_c * 4);
-  };
-
-
-  // producer (thread 0): stage tile `t` whose nonzero range is [s, e)
-  auto issue = [&](int64_t lt, int st, int s, int e) {
+  }
+  __device__ __forceinline__ double* stage_vals(int st) const {
+    return reinterpret_cast<double*>(P.smem + st * stage_bytes);
+  }
+  __device__ __forceinline__ int* stage_cols(int st) const {
+    return reinterpret_cast<int*>(P.smem + st * stage_bytes + (size_t)P.cap_v * 8);
+  }
+  __device__ __forceinline__ int* stage_rp(int st) const {
+    return reinterpret_cast<int*>(P.smem + st * stage_bytes + (size_t)P.cap_v * 8 + (size_t)P.cap_c * 4);
+  }
+  __device__ __forceinline__ int cap_c_entries() const { return C16 ? 2 * P.cap_c : P.cap_c; }
+  __device__ __forceinline__ void tile_bounds(int64_t lt, int& s, int& e) const {
+    const int64_t row0 = phys(lt) * R;
+    s = ld_stream_i(A.rowptr + row0);
+    e = ld_stream_i(A.rowptr + min(row0 + R, A.n_rows));
+  }
+  // producer (thread 0): stage tile `lt` whose nonzero range is [s, e).  The byte counts are
+  // clamped to the stage capacity: a tile fuller than the capacity the host sized the stages for
+  // (it never is when the capacity comes from the statistics of THIS tiling) cannot overrun
+  // shared memory -- its surplus entries are fetched by the fix-up loads in bulk_pass.
+  __device__ __forceinline__ void issue(int64_t lt, int st, int s, int e) const {
     const int64_t row0 = phys(lt) * R;
     const int nr = (int)min((int64_t)R, A.n_rows - row0);
     const int v0 = s & ~1, c0 = s & ~kCA;
-    const int v1 = min((e + 1) & ~1, nnz_v_lim);
-    const int c1 = min((e + kCA) & ~kCA, nnz_c_lim);
+    const int v1 = min(min((e + 1) & ~1, nnz_v_lim), v0 + (P.cap_v & ~1));
+    const int c1 = min(min((e + kCA) & ~kCA, nnz_c_lim), c0 + (cap_c_entries() & ~kCA));
     const int r1 = (int)min((int64_t)((nr + 1 + 3) & ~3), (int64_t)rp_lim - row0);
     const uint32_t bv = v1 > v0 ? (uint32_t)(v1 - v0) * 8u : 0u;
     const uint32_t bc = c1 > c0 ? (uint32_t)(c1 - c0) * (C16 ? 2u : 4u) : 0u;
     const uint32_t br = r1 > 0 ? (uint32_t)r1 * 4u : 0u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(&full[st], bv + bc + br);
-    if (bv) bulk_g2s(stage_vals(st), A.vals + v0, bv, &full[st], pol);
+    mbar_expect_tx(&P.full[st], bv + bc + br);
+    const uint64_t pol = P.sh->pol;
+    if (bv) bulk_g2s(stage_vals(st), A.vals + v0, bv, &P.full[st], pol);
     if (bc) {
-      if (C16) bulk_g2s(stage_cols(st), A.colind16 + c0, bc, &full[st], pol);
-      else     bulk_g2s(stage_cols(st), A.colind + c0, bc, &full[st], pol);
+      if (C16) bulk_g2s(stage_cols(st), A.colind16 + c0, bc, &P.full[st], pol);
+      else     bulk_g2s(stage_cols(st), A.colind + c0, bc, &P.full[st], pol);
     }
-    if (br) bulk_g2s(stage_rp(st), A.rowptr + row0, br, &full[st], pol);
-  };
-  auto tile_bounds = [&](int64_t lt, int& s, int& e) {
-    const int64_t row0 = phys(lt) * R;
-    s = ld_stream_i(A.rowptr + row0);
-    e = ld_stream_i(A.rowptr + min(row0 + R, A.n_rows));
-  };
+    if (br) bulk_g2s(stage_rp(st), A.rowptr + row0, br, &P.full[st], pol);
+  }
+};
+
+// Put the copies of this CTA's first tile in flight (stage 0 is free between passes).  The
+// matrix arrays never change, so a persistent kernel calls this BEFORE waiting at the barrier
+// that precedes the pass; bulk_pass then finds the tile staged.
+template <int RPT, bool C16 = false>
+__device__ __forceinline__ void bulk_prime(const psb_csr& A, const EpiArgs& ea, BulkPipe& P) {
+  if (P.primed) return;
+  const BulkTiler<RPT, C16> T(A, ea, P);
+  const int64_t tile = blockIdx.x;
+  if (threadIdx.x == 0 && tile < T.n_tiles) {
+    BulkShared* sh = P.sh;
+    if (!P.bounds_cached) {
+      T.tile_bounds(tile, sh->s_first, sh->e_first);
+      if (tile + gridDim.x < T.n_tiles) T.tile_bounds(tile + gridDim.x, sh->s_second, sh->e_second);
+    }
+    T.issue(tile, 0, sh->s_first, sh->e_first);
+    sh->s_next = sh->s_second; sh->e_next = sh->e_second;
+  }
+  P.primed = true;
+  P.issued = tile < T.n_tiles;
+}
+
+// Persistent kernels: compute the bounds of the first two tiles once (tile order must not change
+// afterwards), so that bulk_prime issues its copies without touching global memory.
+template <int RPT, bool C16 = false>
+__device__ __forceinline__ void bulk_cache_bounds(const psb_csr& A, const EpiArgs& ea, BulkPipe& P) {
+  const BulkTiler<RPT, C16> T(A, ea, P);
+  const int64_t tile = blockIdx.x;
+  if (threadIdx.x == 0 && tile < T.n_tiles) {
+    T.tile_bounds(tile, P.sh->s_first, P.sh->e_first);
+    if (tile + gridDim.x < T.n_tiles) T.tile_bounds(tile + gridDim.x, P.sh->s_second, P.sh->e_second);
+  }
+  P.bounds_cached = true;
+}
+
+// A primed pass that will not run (the solver stopped): wait for the staged tile so that no
+// bulk copy is in flight when the CTA exits.
+__device__ __forceinline__ void bulk_drain(BulkPipe& P) {
+  if (P.primed && P.issued) {
+    while (!mbar_try_wait(&P.full[0], P.phase_bits & 1u)) {}
+    P.phase_bits ^= 1u;
+  }
+  P.primed = false; P.issued = false;
+}
+
+// One pass over all tiles of A assigned to this CTA (grid-stride).  `beta` is used by
+// EPI_DOT_PUP only.  x may have been written earlier by this same kernel (persistent PCG):
+// it is read through the coherent path.
+// G: gathers of a row whose loads are all issued before the first product is formed (rows with
+// more entries continue four at a time).
+template <int EPI, int RPT, bool C16 = false, int G = 4>
+__device__ __forceinline__ void bulk_pass(const psb_csr& A, const double* x, double* y,
+                                          const EpiArgs& ea, const double beta, BulkPipe& P,
+                                          double& acc) {
+  constexpr int kCA = C16 ? 7 : 3;
+  bulk_prime<RPT, C16>(A, ea, P);
+  const BulkTiler<RPT, C16> T(A, ea, P);
+  uint64_t* const full = P.full;
+  const int tid = threadIdx.x;
+  const int R = T.R;
+  const int64_t n_tiles = T.n_tiles;
+  const int64_t n_int = T.n_int;
+  bool waited = (ea.wait_n == 0);
+  const int nnz_v_lim = T.nnz_v_lim, nnz_c_lim = T.nnz_c_lim, rp_lim = T.rp_lim;
 
   int64_t tile = blockIdx.x;
-  int s_next = 0, e_next = 0;       // bounds of the tile to be staged next (thread 0 only)
-  if (tid == 0 && tile < n_tiles) {
-    int s, e;
-    tile_bounds(tile, s, e);
-    issue(tile, 0, s, e);
-    if (tile + gridDim.x < n_tiles) tile_bounds(tile + gridDim.x, s_next, e_next);
-  }
+  int s_next = 0, e_next = 0;                     // bounds of the tile to be staged next (thread 0 only)
+  if (tid == 0) { s_next = P.sh->s_next; e_next = P.sh->e_next; }
 
   uint32_t phase_bits = P.phase_bits;
   int st = 0;
   for (; tile < n_tiles; tile += gridDim.x, st ^= 1) {
     const int64_t nxt = tile + gridDim.x;
     if (tid == 0 && nxt < n_tiles) {
-      issue(nxt, st ^ 1, s_next, e_next);              // stage st^1 was released by the
+      T.issue(nxt, st ^ 1, s_next, e_next);            // stage st^1 was released by the
       if (nxt + gridDim.x < n_tiles)                   // __syncthreads of the previous trip
-        tile_bounds(nxt + gridDim.x, s_next, e_next);
+        T.tile_bounds(nxt + gridDim.x, s_next, e_next);
     }
     while (!mbar_try_wait(&full[st], (phase_bits >> st) & 1u)) {}
     phase_bits ^= (1u << st);
     if (!waited && tile >= n_int) { wait_for_halo(ea); waited = true; }   // uniform per CTA
 
-    const int64_t row0 = phys(tile) * R;
+    const int64_t row0 = T.phys(tile) * R;
     const int nr = (int)min((int64_t)R, A.n_rows - row0);
-    const double* sv = stage_vals(st);
-    const int*    sc = stage_cols(st);
-    int*          rp = stage_rp(st);
+    const double* sv = T.stage_vals(st);
+    const int*    sc = T.stage_cols(st);
+    int*          rp = T.stage_rp(st);
 
-    // Bulk copies stop at the last whole 16-byte chunk of each array; the few elements
-    // past it (they can only matter to the tiles at the very end of the matrix) are
-    // fetched with ordinary loads.  All conditions are uniform across the CTA.
+    // Bulk copies stop at the last whole 16-byte chunk of each array (and at the stage
+    // capacity); the few elements past it (they can only matter to the tiles at the very end
+    // of the matrix) are fetched with ordinary loads.  All conditions are uniform across the CTA.
     if (row0 + nr + 1 > rp_lim) {
       for (int64_t i = max(row0, (int64_t)rp_lim) + tid; i <= row0 + nr; i += kBlock)
         rp[i - row0] = A.rowptr[i];
@@ -200,15 +315,22 @@ __device__ __forceinline__ void bulk_pass(const psb_csr& A, const double* x, dou
     }
     {
       const int s0 = rp[0], e0 = rp[nr];
-      if (e0 > nnz_v_lim || e0 > nnz_c_lim) {
-        double* svw = stage_vals(st);
-        int*    scw = stage_cols(st);
-        for (int i = max(s0, nnz_v_lim) + tid; i < e0; i += kBlock) svw[i - (s0 & ~1)] = A.vals[i];
-        if (C16) {
-          short* scw16 = reinterpret_cast<short*>(scw);
-          for (int i = max(s0, nnz_c_lim) + tid; i < e0; i += kBlock) scw16[i - (s0 & ~kCA)] = A.colind16[i];
+      const int v_end = min(nnz_v_lim, (s0 & ~1) + (P.cap_v & ~1));      // first entry NOT bulk-copied
+      const int c_end = min(nnz_c_lim, (s0 & ~kCA) + (T.cap_c_entries() & ~kCA));
+      if (e0 > v_end || e0 > c_end) {
+        double* svw = T.stage_vals(st);
+        int*    scw = T.stage_cols(st);
+        // entries past the capacity do not fit the stage at all: host-side sizing error
+        if (e0 - (s0 & ~1) > P.cap_v || e0 - (s0 & ~kCA) > T.cap_c_entries()) {
+          if (ea.error_flag) *ea.error_flag = 2;
         } else {
-          for (int i = max(s0, nnz_c_lim) + tid; i < e0; i += kBlock) scw[i - (s0 & ~kCA)] = A.colind[i];
+          for (int i = max(s0, v_end) + tid; i < e0; i += kBlock) svw[i - (s0 & ~1)] = A.vals[i];
+          if (C16) {
+            short* scw16 = reinterpret_cast<short*>(scw);
+            for (int i = max(s0, c_end) + tid; i < e0; i += kBlock) scw16[i - (s0 & ~kCA)] = A.colind16[i];
+          } else {
+            for (int i = max(s0, c_end) + tid; i < e0; i += kBlock) scw[i - (s0 & ~kCA)] = A.colind[i];
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
@@ -218,48 +340,58 @@ __device__ __forceinline__ void bulk_pass(const psb_csr& A, const double* x, dou
     const int s = rp[0];
     const int offv = s & ~1, offc = s & ~kCA;
     const short* sc16 = reinterpret_cast<const short*>(sc);
-    // EPI_DOT_PUP: the tile's own rows of p = x + beta * pold are formed once, kept in shared
-    // memory and stored; gathers that fall inside the tile's row window (the k, k-1, k+1 entries
-    // of a stencil) read them back instead of two global gathers each.
-    __shared__ double ptile[EPI == EPI_DOT_PUP ? R : 1];
-    constexpr bool kWindow = PSB_PUP_WINDOW != 0;       // serve in-tile gathers from ptile
     const long long win0 = A.row_off + row0;
-    if constexpr (EPI == EPI_DOT_PUP) {
-#pragma unroll
-      for (int j = 0; j < RPT; ++j) {
-        const int lr = tid + j * kBlock;
-        if (lr < nr) {
-          const int64_t row = win0 + lr;
-          const double pn = ld_ca(x + row) + beta * ld_ca(ea.pold + row);   // as K3 would store it
-          ptile[lr] = pn;
-          ea.pnew[row] = pn;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)                 // boundary rows also go to the neighbours' halo
-            if (q < ea.pp_n && row >= ea.pp_off[q] && row < ea.pp_off[q] + ea.pp_cnt[q])
-              ea.pp_remote[q][row - ea.pp_off[q]] = pn;
-        }
-      }
-      if (kWindow) __syncthreads();
-    }
-    auto gather = [&](int c) -> double {
-      if constexpr (EPI == EPI_DOT_PUP) {
-        const long long d = (long long)c - win0;
-        if (kWindow && d >= 0 && d < nr) return ptile[d];
-        return ld_ca(x + c) + beta * ld_ca(ea.pold + c);
-      } else {
-        return ld_ca(x + c);
-      }
-    };
+    // One thread per row.  Order of the memory operations: (1) the row's own operands and the
+    // first G gathers are ALL loaded before anything is consumed or stored -- one memory round
+    // trip per tile, not one per dependent step (stores in between would also keep the compiler
+    // from hoisting the later loads: the vectors may alias for all it knows); (2) products added
+    // in stored order from +0 (bit-identical to csr_matvec); (3) stores.
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
       const int lr = tid + j * kBlock;
       if (lr < nr) {
+        const int64_t row = win0 + lr;
         const int a = rp[lr], b = rp[lr + 1];
-        double sum = 0.0;
-        int k = a;
-        const int rabs = (int)(A.row_off + row0 + lr);  // C16: columns are stored relative to the row
+        const int rabs = (int)row;                      // C16: columns are stored relative to the row
         auto col = [&](int kk) -> int { return C16 ? rabs + (int)sc16[kk - offc] : sc[kk - offc]; };
-        for (; k + 4 <= b; k += 4) {                   // 4 independent gathers in flight
+        // (1) own-row operands
+        double po = 0.0, rown = 0.0, xo = 0.0;
+        EpiRow own;
+        if constexpr (EPI == EPI_DOT_PUP) {
+          po = ld_ca(ea.pold + row);
+          rown = ld_ca(x + row);
+          if (ea.xsol != nullptr) xo = ea.xsol[row];
+        } else {
+          own = epi_preload<EPI>(row, x, y, ea);
+        }
+        // first G gathers, predicated on the row length
+        int cg[G];
+        double gx[G], gp[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) cg[g] = (a + g < b) ? col(a + g) : -1;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          gx[g] = 0.0; gp[g] = 0.0;
+          if (cg[g] >= 0) {
+            gx[g] = ld_ca(x + cg[g]);
+            if constexpr (EPI == EPI_DOT_PUP) gp[g] = ld_ca(ea.pold + cg[g]);
+          }
+        }
+        // (2) sum in stored order
+        double sum = 0.0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (a + g < b) {
+            const double xv = (EPI == EPI_DOT_PUP) ? gx[g] + beta * gp[g] : gx[g];   // p as K3 would store it
+            sum += sv[a + g - offv] * xv;
+          }
+        }
+        auto gather = [&](int c) -> double {
+          if constexpr (EPI == EPI_DOT_PUP) return ld_ca(x + c) + beta * ld_ca(ea.pold + c);
+          else return ld_ca(x + c);
+        };
+        int k = a + G;
+        for (; k + 4 <= b; k += 4) {                   // longer rows: 4 independent gathers in flight
           const int c0 = col(k), c1 = col(k + 1), c2 = col(k + 2), c3 = col(k + 3);
           const double x0 = gather(c0), x1 = gather(c1), x2 = gather(c2), x3 = gather(c3);
           sum += sv[k - offv] * x0;
@@ -267,20 +399,30 @@ __device__ __forceinline__ void bulk_pass(const psb_csr& A, const double* x, dou
           sum += sv[k + 2 - offv] * x2;
           sum += sv[k + 3 - offv] * x3;
         }
-        for (; k < b; ++k) {
-          sum += sv[k - offv] * gather(col(k));
-        }
+        for (; k < b; ++k) sum += sv[k - offv] * gather(col(k));
+        // (3) stores
         if constexpr (EPI == EPI_DOT_PUP) {
-          y[win0 + lr] = sum;
-          acc += ptile[lr] * sum;                   // own element: written by this very thread
+          const double pn = rown + beta * po;                                   // as K3 would store it
+          ea.pnew[row] = pn;
+          y[row] = sum;
+          // deferred solution update of the PREVIOUS iteration, x += alpha_{k-1} p_{k-1}
+          // (PCGSolver.py:121): p_{k-1} is in a register here anyway, so the update pass never
+          // has to read p -- same operands, same rounding, 8 bytes per row less traffic
+          if (ea.xsol != nullptr) ea.xsol[row] = xo + ea.alpha_prev * po;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)                 // boundary rows also go to the neighbours' halo
+            if (q < ea.pp_n && row >= ea.pp_off[q] && row < ea.pp_off[q] + ea.pp_cnt[q])
+              ea.pp_remote[q][row - ea.pp_off[q]] = pn;
+          acc += pn * sum;
         } else {
-          epilogue<EPI>(A.row_off + row0 + lr, sum, x, y, ea, acc);
+          epi_finish<EPI>(row, sum, own, y, ea, acc);
         }
       }
     }
     __syncthreads();                                   // stage st may be refilled now
   }
   P.phase_bits = phase_bits;
+  P.primed = false; P.issued = false;
 }
 
 }  // namespace psb

@@ -14,12 +14,8 @@ the halo id lists); the solve itself -- halo send/recv overlapped with the
 interior SpMV, two scalar all-reduces per iteration -- runs inside
 libpysolv_b200 (csrc/dist.cu) on raw NCCL.
 """
-import contextlib
 import ctypes as C
-import io
-import json
 import os
-import time
 
 import numpy as np
 import torch
@@ -107,50 +103,52 @@ class Comm:
         self._h = C.c_void_p()
         nat.check(nat.lib().psb_comm_create(ident, self.rank, self.world, C.byref(self._h)),
                   'psb_comm_create')
+        # partition plans (halo lists, peer-memory mappings, device structure) of the matrices
+        # solved on this communicator, most recently used last; see DistCSR
+        self._plans = []
+        self.max_plans = int(os.environ.get('PSB_DIST_PLAN_CACHE', '4'))
 
     @property
     def handle(self):
         return self._h
 
+    def _evict(self, keep):
+        """Collective (called at the same point on every rank): destroy the oldest idle plans."""
+        idle = [p for p in self._plans if not p.in_use]
+        while len(self._plans) > keep and idle:
+            victim = idle.pop(0)
+            self._plans.remove(victim)
+            victim.destroy()
+
     def close(self):
+        """Collective: releases every cached plan (peer mappings are closed only after all
+        ranks have stopped using them) and the communicator."""
+        for p in list(self._plans):
+            p.destroy()
+        self._plans = []
         if self._h:
             nat.lib().psb_comm_destroy(self._h)
             self._h = C.c_void_p()
 
 
-class DistCSR:
-    """This rank's row block of a row-partitioned matrix plus its halo plan.
+class _DistPlan:
+    """Everything about a row block that depends only on its sparsity STRUCTURE: device copies
+    of indptr / global and local column ids, halo lists, send lists, the psb_dist handle with
+    its NCCL plan and NVLink peer-memory mappings.  Built collectively once per structure and
+    kept on the communicator; a later DistCSR with the same structure only uploads values."""
 
-    ``indptr, indices, data``: the block's CSR arrays with GLOBAL column ids
-    (numpy arrays or torch tensors, host or device); ``lo, hi``: its row range;
-    ``n``: global size.
-    """
-
-    def __init__(self, comm, indptr, indices, data, lo, hi, n):
+    def __init__(self, comm, ip, ix, data, lo, hi, n, mark):
         import torch.distributed as dist
-        import time as _time
-        _timing = os.environ.get('PSB_DIST_TIMING', '0') == '1'
-        _t = [_time.perf_counter()]
-
-        def _mark(what):
-            if _timing:
-                torch.cuda.synchronize()
-                now = _time.perf_counter()
-                if comm.rank == 0:
-                    print('[DistCSR] %-28s %7.2f ms' % (what, 1e3 * (now - _t[0])), flush=True)
-                _t[0] = now
-        self._mark = _mark
         self.comm = comm
+        self.in_use = False
         self.lo, self.hi, self.n = int(lo), int(hi), int(n)
         self.n_loc = self.hi - self.lo
         self.starts = row_starts(n, comm.world)
         assert self.starts[comm.rank] == self.lo and self.starts[comm.rank + 1] == self.hi
-        dev = torch.device('cuda', torch.cuda.current_device())
-        ip = torch.as_tensor(indptr).to(dev)
-        ix = torch.as_tensor(indices).to(dev)
-        _mark('upload indptr, indices')
+        dev = ix.device
+        self.ip_global, self.ix_global = ip, ix
         loc = localize(ip, ix, self.lo, self.hi, self.starts)
-        _mark('localize (halo lists)')
+        mark('localize (halo lists)')
         self.recv = loc['recv'].cpu().numpy()
         self.recv_owner = loc['recv_owner'].cpu().numpy()
         self.n_halo = int(self.recv.size)
@@ -158,12 +156,10 @@ class DistCSR:
         gathered = [None] * comm.world
         dist.all_gather_object(gathered, (self.recv, self.recv_owner))
         self.send = send_lists(comm.rank, self.lo, gathered)
-        _mark('all_gather halo lists')
-        self.A = DeviceCSR(indptr=ip.to(torch.int32), indices=loc['local_indices'],
-                           data=torch.as_tensor(data).to(dev),
+        mark('all_gather halo lists')
+        self.A = DeviceCSR(indptr=ip.to(torch.int32), indices=loc['local_indices'], data=data,
                            shape=(self.n_loc, self.n_loc + self.n_halo))
-        del ix
-        _mark('upload data, csr_create')
+        mark('csr_create')
         # peers: union of the ranks we send to / receive from
         peers = sorted(set(self.send) | set(int(o) for o in np.unique(self.recv_owner)))
         k = len(peers)
@@ -195,12 +191,11 @@ class DistCSR:
             comm.handle, self.A.handle, self.n_loc, self.n_halo, self.r0, self.r1, k,
             peer_rank, send_off, send_cnt, idx_ptrs, recv_off, recv_cnt, C.byref(self._h)),
             'psb_dist_create')
-
-        _mark('psb_dist_create')
+        mark('psb_dist_create')
         self.p2p = False
         if os.environ.get('PSB_DIST_MODE', 'p2p') != 'nccl':
             self._enable_p2p(gathered)
-        _mark('peer-memory mapping')
+        mark('peer-memory mapping')
 
     def _enable_p2p(self, all_recv):
         """Map every rank's exported region (NVLink peer memory) so that the solve
@@ -251,25 +246,114 @@ class DistCSR:
         dist.barrier()
         self.p2p = True
 
+    def destroy(self):
+        """Collective.  A peer's last halo / flag store into this rank's exported region may
+        still be in flight when this rank is done: all ranks meet before anything is unmapped."""
+        import torch.distributed as dist
+        if not self._h:
+            return
+        torch.cuda.synchronize()
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
+        nat.lib().psb_dist_destroy(self._h)
+        self._h = C.c_void_p()
+        self.A = None
+
+
+class DistCSR:
+    """This rank's row block of a row-partitioned matrix plus its halo plan.
+
+    ``indptr, indices, data``: the block's CSR arrays with GLOBAL column ids
+    (numpy arrays or torch tensors, host or device); ``lo, hi``: its row range;
+    ``n``: global size.  Construction is collective.  The structure-dependent part (halo
+    lists, send lists, peer-memory mappings) is looked up on the communicator: when a block
+    with the same indptr / indices was partitioned before, only the arrays are uploaded (and
+    compared with the cached structure on the device) -- a Newton iteration or a sequence of
+    solves does not rebuild its plan.
+    """
+
+    def __init__(self, comm, indptr, indices, data, lo, hi, n):
+        import torch.distributed as dist
+        import time as _time
+        _timing = os.environ.get('PSB_DIST_TIMING', '0') == '1'
+        _t = [_time.perf_counter()]
+
+        def _mark(what):
+            if _timing:
+                torch.cuda.synchronize()
+                now = _time.perf_counter()
+                if comm.rank == 0:
+                    print('[DistCSR] %-28s %7.2f ms' % (what, 1e3 * (now - _t[0])), flush=True)
+                _t[0] = now
+        self.comm = comm
+        dev = torch.device('cuda', torch.cuda.current_device())
+        ip = torch.as_tensor(indptr).to(dev, non_blocking=True)
+        ix = torch.as_tensor(indices).to(dev, non_blocking=True)
+        dt = torch.as_tensor(data).to(dev, non_blocking=True)
+        _mark('upload indptr, indices, data')
+        plan = None
+        for cand in reversed(comm._plans):
+            if (not cand.in_use and cand.lo == int(lo) and cand.hi == int(hi) and cand.n == int(n)
+                    and cand.ix_global.shape == ix.shape and cand.ix_global.dtype == ix.dtype
+                    and cand.ip_global.dtype == ip.dtype):
+                plan = cand
+                break
+        hit = torch.zeros(1, dtype=torch.int32, device=dev)
+        if plan is not None:
+            same = torch.equal(plan.ix_global, ix) and torch.equal(plan.ip_global, ip)
+            hit.fill_(1 if same else 0)
+        if comm.world > 1:
+            dist.all_reduce(hit, op=dist.ReduceOp.MIN)           # every rank must take the same branch
+        if int(hit.item()) == 1:
+            plan.A.data.copy_(dt)                                # values only; structure stays
+            comm._plans.remove(plan)
+            comm._plans.append(plan)
+            _mark('plan cache hit: values copied')
+        else:
+            comm._evict(max(comm.max_plans - 1, 0))
+            plan = _DistPlan(comm, ip, ix, dt, lo, hi, n, _mark)
+            comm._plans.append(plan)
+        plan.in_use = True
+        self._plan = plan
+
+    # the plan's fields, under the names the rest of the package uses
+    lo = property(lambda self: self._plan.lo)
+    hi = property(lambda self: self._plan.hi)
+    n = property(lambda self: self._plan.n)
+    n_loc = property(lambda self: self._plan.n_loc)
+    n_halo = property(lambda self: self._plan.n_halo)
+    starts = property(lambda self: self._plan.starts)
+    recv = property(lambda self: self._plan.recv)
+    recv_owner = property(lambda self: self._plan.recv_owner)
+    send = property(lambda self: self._plan.send)
+    r0 = property(lambda self: self._plan.r0)
+    r1 = property(lambda self: self._plan.r1)
+    A = property(lambda self: self._plan.A)
+    p2p = property(lambda self: self._plan.p2p)
+
     @property
     def handle(self):
-        return self._h
+        return self._plan._h
 
     def matvec(self, x_loc):
         """y_loc = (A x)_loc for the distributed vector whose local slice is x_loc."""
         ext = torch.zeros(self.n_loc + self.n_halo, dtype=torch.float64, device=x_loc.device)
         ext[:self.n_loc] = x_loc
         y = torch.empty(self.n_loc, dtype=torch.float64, device=x_loc.device)
-        nat.check(nat.lib().psb_dist_spmv(self._h, ptr(ext), ptr(y), current_stream_ptr()),
+        nat.check(nat.lib().psb_dist_spmv(self.handle, ptr(ext), ptr(y), current_stream_ptr()),
                   'psb_dist_spmv')
         torch.cuda.synchronize()
         return y
 
+    def close(self):
+        """Hand the plan back to the communicator's cache (not collective)."""
+        if getattr(self, '_plan', None) is not None:
+            self._plan.in_use = False
+            self._plan = None
+
     def __del__(self):
         try:
-            if self._h:
-                nat.lib().psb_dist_destroy(self._h)
-                self._h = C.c_void_p()
+            self.close()
         except Exception:
             pass
 
@@ -347,147 +431,3 @@ def laplacian_block_device(dim, a, b, m, lo, hi, device, negate_2d=True):
     vals_row[0] = diag
     data = vals_row.repeat(k.numel(), 1)[V]
     return indptr.to(torch.int32), Cc, data
-
-
-# ---------------------------------------------------------------------------------
-# bench.py --gpus N (N > 1): strong scaling of the metric workload
-# ---------------------------------------------------------------------------------
-def bench_multi_gpu(args, bench):
-    import torch.distributed as dist
-    from .csrc.build import build_native
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', str(args.gpus)))
-    local_rank = int(os.environ.get('LOCAL_RANK', str(rank)))
-    torch.cuda.set_device(local_rank)
-    build_native()
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    lib = nat.lib()
-    comm = Comm()
-    dev = torch.device('cuda', local_rank)
-
-    which = os.environ.get('PSB_BENCH_WORKLOAD', 'c3')
-    if which == 'c4':
-        dim, m = 3, int(os.environ.get('PSB_BENCH_M3', '512'))
-        n = m ** 3
-        name = ('3-D 7-point Laplacian m=%d (n=%d), un-preconditioned PCG, b=1, %d iterations per step'
-                % (m, n, bench.ITERS_PER_STEP))
-    else:
-        dim, m = 2, bench.M_GRID
-        n = m * m
-        name = bench.workload_name(m)
-    starts = row_starts(n, world)
-    lo, hi = int(starts[rank]), int(starts[rank + 1])
-    indptr, cols, data = laplacian_block_device(dim, 0.0, 1.0, m, lo, hi, dev)
-    nnz_loc = int(data.numel())
-    D = DistCSR(comm, indptr, cols, data, lo, hi, n)
-    del cols
-    torch.cuda.empty_cache()
-    n_loc = hi - lo
-    b_d = torch.ones(n_loc, dtype=torch.float64, device=dev)
-    x_d = torch.empty(n_loc, dtype=torch.float64, device=dev)
-    iters = bench.ITERS_PER_STEP
-    wbytes = int(lib.psb_dist_pcg_workspace_bytes(n_loc, D.n_halo))
-    work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
-    hist_d = torch.empty(iters, dtype=torch.float64, device=dev)
-    res = nat.SolveResult()
-    stream = current_stream_ptr()
-
-    def step():
-        nat.check(lib.psb_dist_pcg_solve(D.handle, ptr(b_d), ptr(x_d), ptr(work), wbytes, iters, 0.0, 0,
-                                         ptr(hist_d), C.byref(res), stream), 'psb_dist_pcg_solve')
-        assert res.n_hist == iters
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    dist.barrier()
-    sampler = bench.ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    l0 = nat.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    launches = nat.launch_count() - l0
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    dev_ms = float(ms.item())
-    clocks = sampler.finish() if sampler else None
-    value = args.steps * iters / (dev_ms * 1e-3)
-
-    # e2e: public API with host operands on every rank (upload block + b, download x)
-    skip_e2e = os.environ.get('PSB_BENCH_SKIP_E2E', '0') == '1'
-    e2e_value, h2d_total, final_resid = None, 0, float(hist_d[-1].item())
-    nnz_t = torch.tensor([nnz_loc], dtype=torch.float64, device=dev)
-    dist.all_reduce(nnz_t)
-    nnz = int(nnz_t.item())
-    mode = 'nvlink-p2p' if D.p2p else 'nccl'
-    if not skip_e2e:
-        # host operands in page-locked memory, as in the single-GPU bench (the e2e leg copies from
-        # pinned memory; pageable arrays cost 2 - 4 x in the upload)
-        pin = lambda t: t.cpu().pin_memory().numpy()
-        ip_h, dt_h = pin(indptr), pin(data)
-        cols_h = pin(laplacian_block_device(dim, 0.0, 1.0, m, lo, hi, dev)[1])
-        b_h = torch.ones(n_loc, dtype=torch.float64).pin_memory().numpy()
-        solver = DistributedPCG(CommonSolverArgs(maxiter=iters, tau=0.0, failOnMaxiter=False,
-                                                 showIters=False, showFinal=False))
-        del D
-        torch.cuda.empty_cache()
-
-        def api_step():
-            Dm = DistCSR(comm, ip_h, cols_h, dt_h, lo, hi, n)
-            with contextlib.redirect_stdout(io.StringIO()):
-                st = solver.solve(Dm, b_h)
-            assert st.success() and st.iters() == iters
-            return st
-        for _ in range(2):                  # as in the single-GPU leg: the first two solves touch
-            api_step()                      # freshly allocated device memory (measured 76 vs 47 ms)
-        torch.cuda.synchronize()
-        dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            st = api_step()
-        torch.cuda.synchronize()
-        dist.barrier()
-        e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-        e2e_value = args.steps * iters / float(e2e_s.item())
-        h2d = torch.tensor([ip_h.nbytes + cols_h.nbytes + dt_h.nbytes + b_h.nbytes], dtype=torch.float64, device=dev)
-        dist.all_reduce(h2d)
-        h2d_total = int(h2d.item())
-        final_resid = float(st.resid())
-
-    if rank == 0:
-        peak, peak_src = bench.peaks()
-        iter_bytes = 12 * nnz + 4 * (n + world) + 88 * n
-        iter_ms = dev_ms / (args.steps * iters)
-        gbs = iter_bytes / (iter_ms * 1e-3) / 1e9
-        line = {
-            'metric': bench.METRIC, 'value': value, 'unit': bench.UNIT, 'n_gpus': world,
-            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': dev_ms / args.steps,
-            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic',
-            'config': {'workload': name, 'n': n, 'nnz': nnz, 'iters_per_step': iters,
-                       'parallelism': 'row partition over %d GPUs, collectives: %s' % (world, mode),
-                       'l2': 'inputs larger than L2: %.2f GB touched per iteration per GPU'
-                             % (iter_bytes / world / 1e9)},
-            'e2e': {'value': e2e_value, 'unit': bench.UNIT, 'h2d_bytes_per_step': h2d_total,
-                    'd2h_bytes_per_step': int(8 * n + 8 * iters * world)},
-            'gpu_launches': int(launches), 'clocks': clocks,
-            'roofline': {'bound': 'hbm', 'kernel': 'whole PCG iteration (aggregate over GPUs)',
-                         'achieved': gbs, 'peak': peak * world, 'unit': 'GB/s',
-                         'frac': gbs / (peak * world), 'traffic': None,
-                         'bytes_per_iteration': iter_bytes, 'ms_per_iteration': iter_ms,
-                         'peak_source': peak_src + ' x %d GPUs' % world},
-            'cpu_baseline': None,
-            'final_residual': final_resid,
-        }
-        print(json.dumps(line))
-    comm.close()
-    dist.destroy_process_group()
-    return 0

@@ -77,11 +77,13 @@ def fd_laplacian_3d(a, b, m, row_lo=0, row_hi=None):
     return _stencil_csr(n, k, cols, vals, valid)
 
 
-def device_fd_laplacian(dim, a, b, m, negate=False, row_lo=0, row_hi=None):
+def device_fd_laplacian(dim, a, b, m, negate=False, row_lo=0, row_hi=None, raw=False):
     """The same matrices as ``fd_laplacian_2d`` (dim = 2; ``negate`` gives the SPD
     ``-FDLaplacian2D`` of examples/FDBratu2D.py:15) and ``fd_laplacian_3d`` (dim = 3),
     bit for bit, assembled directly in HBM (psb_stencil_fill): returns a DeviceCSR that the
-    solvers accept in place of the scipy matrix -- no host assembly, no upload."""
+    solvers accept in place of the scipy matrix -- no host assembly, no upload.  ``raw``: return
+    the three device arrays (indptr, indices with GLOBAL column ids, data) instead, e.g. as the
+    row block handed to ``dist.DistCSR``."""
     import torch
     from . import _native as nat
     from .device import DeviceCSR, current_stream_ptr, ptr, require_cuda
@@ -102,6 +104,8 @@ def device_fd_laplacian(dim, a, b, m, negate=False, row_lo=0, row_hi=None):
     data = torch.empty(nnz, dtype=torch.float64, device='cuda')
     nat.check(nat.lib().psb_stencil_fill(dim, m, row_lo, row_hi, float(diag), float(off), ptr(indptr),
                                          ptr(indices), ptr(data), current_stream_ptr()), 'psb_stencil_fill')
+    if raw:
+        return indptr, indices, data
     return DeviceCSR(indptr=indptr, indices=indices, data=data, shape=(row_hi - row_lo, n))
 
 

@@ -9,6 +9,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden', 'reference_golden.npz')
+GOLDEN_LARGE = os.path.join(ROOT, 'tests', 'golden', 'reference_golden_large.npz')
 
 
 def pytest_configure(config):
@@ -21,6 +22,33 @@ def golden():
     (tests/golden/make_golden.py)."""
     z = np.load(GOLDEN)
     return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope='session')
+def golden_large():
+    """At-size fixtures of the reference (tests/golden/make_golden_large.py): SHA-256 digests of
+    the m = 128 / 256 smoothed-aggregation hierarchies and IC factors, IC-PCG histories."""
+    z = np.load(GOLDEN_LARGE)
+    return {k: z[k] for k in z.files}
+
+
+def csr_digest(M):
+    """(sha indptr, sha indices, sha data) with make_golden_large.py's convention."""
+    import hashlib
+    import scipy.sparse as sp
+    M = sp.csr_matrix(M)
+    h = lambda a, t: hashlib.sha256(np.ascontiguousarray(a, dtype=t).tobytes()).hexdigest()
+    return h(M.indptr, np.int32), h(M.indices, np.int32), h(M.data, np.float64)
+
+
+def assert_csr_digest(M, g, prefix):
+    import scipy.sparse as sp
+    M = sp.csr_matrix(M)
+    assert tuple(int(v) for v in g[prefix + '/shape']) == M.shape, prefix
+    assert int(g[prefix + '/nnz']) == M.nnz, prefix
+    got = csr_digest(M)
+    want = tuple(str(g[prefix + k]) for k in ('/sha_indptr', '/sha_indices', '/sha_data'))
+    assert got == want, prefix
 
 
 @pytest.fixture(scope='session')

@@ -45,6 +45,30 @@ def test_aggregates_match_reference(golden, m, nlev):
         assert np.array_equal(np.sort(np.flatnonzero(agg_of == j)), members), j
 
 
+@pytest.mark.parametrize('m,nlev', [(128, 2), (128, 3), (256, 2)])
+def test_hierarchy_at_size_digests(golden_large, m, nlev):
+    """SURVEY.md section 8f-1 asks for m <= 256: phase-2 tie breaking, ``agg_idx = -1`` and the set
+    aliasing are size-dependent paths.  The reference's hierarchies at these sizes are pinned
+    by SHA-256 digests of every array (tests/golden/make_golden_large.py)."""
+    import hashlib
+    from conftest import assert_csr_digest
+    A = -fd_laplacian_2d(0.0, 1.0, m)
+    ops, ups, downs = amg_setup.build_hierarchy(A, num_levels=nlev)
+    tag = 'amg/m%d_L%d' % (m, nlev)
+    for k in range(nlev):
+        assert_csr_digest(ops[k], golden_large, '%s/A%d' % (tag, k))
+    for k in range(nlev - 1):
+        assert_csr_digest(ups[k], golden_large, '%s/P%d' % (tag, k))
+        assert_csr_digest(downs[k], golden_large, '%s/R%d' % (tag, k))
+    agg_of, n_agg, roots, _ = amg_setup.build_aggregates(A, lvl=nlev - 1)
+    assert n_agg == int(golden_large[tag + '/n_agg'])
+    order = np.argsort(agg_of, kind='stable')                 # members ascending inside each aggregate
+    sizes = np.bincount(agg_of, minlength=n_agg).astype(np.int64)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype=np.int64).tobytes()).hexdigest()
+    assert sha(sizes) == str(golden_large[tag + '/sha_agg_sizes'])
+    assert sha(order) == str(golden_large[tag + '/sha_agg_flat'])
+
+
 @pytest.mark.parametrize('tag,nlev', [('amg/dh7_L2', 2), ('amg/dh9_L3', 3), ('amg/bratuJ_m20_L2', 2),
                                       ('amg/rand300_L2', 2)])
 def test_hierarchy_irregular_matrices(golden, tag, nlev):

@@ -158,6 +158,38 @@ def test_full_size_c3_properties(cuda):
     assert np.array_equal(hist4, 4.0 * hist)
 
 
+def test_full_size_c3_history_vs_oracle(cuda):
+    """The headline system itself (m = 4096, n = 16 777 216) against the oracle: the first 40
+    residual norms to 1e-10 relative (about 11 s of host time for the oracle)."""
+    from oracle import krylov
+    from pysolvers_b200 import CommonSolverArgs
+    from pysolvers_b200.Linear import PCG
+    A = _lap(4096)
+    b = np.ones(A.shape[0])
+    args = dict(maxiter=40, tau=0.0, failOnMaxiter=False)
+    st, hist = _run(PCG(CommonSolverArgs(**args)).makeSolver(), A, b)
+    ref = krylov.pcg(A, b, maxiter=40, tau=0.0, fail_on_maxiter=False)
+    assert st.iters() == ref['iters'] == 40 and len(hist) == 40
+    assert rel_err(hist, ref['hist']) < HIST_RTOL
+    assert np.linalg.norm(st.soln() - ref['soln']) <= 1e-8 * np.linalg.norm(ref['soln'])
+
+
+def test_3d_m128_history_vs_oracle(cuda):
+    """3-D 7-point Laplacian at m = 128 (n = 2 097 152): 40 iterations against the oracle."""
+    from oracle import krylov
+    from pysolvers_b200 import CommonSolverArgs
+    from pysolvers_b200.Linear import PCG
+    from pysolvers_b200.problems import fd_laplacian_3d
+    A = fd_laplacian_3d(0.0, 1.0, 128)
+    b = np.ones(A.shape[0])
+    args = dict(maxiter=40, tau=0.0, failOnMaxiter=False)
+    st, hist = _run(PCG(CommonSolverArgs(**args)).makeSolver(), A, b)
+    ref = krylov.pcg(A, b, maxiter=40, tau=0.0, fail_on_maxiter=False)
+    assert st.iters() == ref['iters'] == 40
+    assert rel_err(hist, ref['hist']) < HIST_RTOL
+    assert np.linalg.norm(st.soln() - ref['soln']) <= 1e-8 * np.linalg.norm(ref['soln'])
+
+
 @pytest.mark.parametrize('mode', ['persistent', 'fused-kernels', 'kernel-per-phase'])
 def test_pcg_driver_variants_agree(cuda, golden, mode, monkeypatch):
     """The three PCG drivers (one persistent cooperative kernel; SpMV with the direction update

@@ -199,6 +199,23 @@ def test_icpcg_history_vs_reference_golden(cuda, golden, m):
     assert np.linalg.norm(st.soln() - gx) <= 1e-8 * np.linalg.norm(gx)
 
 
+@pytest.mark.parametrize('m', [128, 256])
+def test_icpcg_history_at_size_vs_reference(cuda, golden_large, m):
+    """IC-PCG at m = 128 / 256 against histories the reference itself produced
+    (tests/golden/make_golden_large.py): 1e-10 per iteration, iterations +-1, solution 1e-8."""
+    from pysolvers_b200 import CommonSolverArgs
+    from pysolvers_b200.Linear import PCG, RightIC
+    A = _lap(m)
+    st, hist = _run(PCG(CommonSolverArgs(maxiter=500, tau=1e-8), precond=RightIC()).makeSolver(),
+                    A, np.ones(A.shape[0]))
+    key = 'icpcg/lap2d_m%d' % m
+    assert st.success() and abs(st.iters() - int(golden_large[key + '/iters'])) <= 1
+    k = min(len(hist), len(golden_large[key + '/hist']))
+    assert rel_err(hist[:k], golden_large[key + '/hist'][:k]) < 1e-10
+    gx = golden_large[key + '/x']
+    assert np.linalg.norm(st.soln()[::97] - gx) <= 1e-8 * np.linalg.norm(gx)
+
+
 def test_known_answer_dh10(cuda, golden):
     """The assertions of the reference's own (stale) tests on the current API:
     tests/TestPCG.py:28-40 and tests/TestGMRES.py:28-40 -- ||x - x_ex|| <= 1e-8."""
