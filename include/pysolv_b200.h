@@ -137,7 +137,7 @@ int psb_trsv_destroy(psb_trsv_t T);
 int psb_trsv_info(psb_trsv_t T, int64_t info[8]);
 /* Which solve kernel the analysis chose, and the data of the shared-memory window kernels:
  * info[0]=kernel (0 grid-wide, hand-over through L2; 1 one CTA, hand-over through shared
- * memory; 2 a cluster of 8 CTAs, window replicated through distributed shared memory),
+ * memory; 2 a cluster of 4 CTAs, window replicated through distributed shared memory),
  * [1]=window slots, [2]=dependencies older than the window (read from the global
  * vector), [3]=largest distance of a dependency in processing order, [4]=forced kernel or -1,
  * [5]=entries per lane of a staging buffer, [6]=the cluster kernel may be forced. */
@@ -342,6 +342,32 @@ int64_t psb_dist_pcg_workspace_bytes(int64_t n_loc, int64_t n_halo);
 int psb_dist_pcg_solve(psb_dist_t D, const double* d_b_loc, double* d_x_loc, void* d_work,
                        int64_t work_bytes, int32_t maxiter, double tau, int32_t fail_on_maxiter,
                        double* d_hist, psb_solve_result* result, void* stream);
+
+
+/* ---- row-partitioned GMRES and AMG V-cycle (the reference is single-process:
+ * GMRESSolver.py:104-125 and VCycleManager.py:31-62 are the loops being sharded) ------------------
+ * psb_dist_create also accepts RECTANGULAR row blocks (restriction / prolongation): the local
+ * matrix is n_loc x (n_own + n_halo), n_own = owned entries of the operator's INPUT vector.
+ *
+ * psb_dist_amg_create: level l >= 1 (n_levels - 1 = finest): A[l] = this rank's row block of A_l,
+ * d_dinv[l] = reciprocal diagonal of those rows; R[l-1] = its block of the restriction to level l-1;
+ * P[l-1] (l-1 >= 1) = its block of the prolongator from level l-1; P0 = its rows of the prolongator
+ * from the COARSEST level as a plain local CSR with GLOBAL column indices -- the coarsest vector is
+ * replicated: the ranks gather the coarse right-hand side (h_starts0[nranks+1] = its row
+ * partition) and each runs `coarse`, an exact solver of the whole coarsest system.  Damped-Jacobi
+ * smoothing (Gauss-Seidel has a global dependency chain: single GPU only).  The handle works with
+ * psb_prec_apply (slices in, slices out), psb_amg_solve and psb_dist_gmres_solve. */
+int psb_dist_amg_create(psb_comm_t comm, int32_t n_levels, const psb_dist_t* A, const psb_dist_t* P,
+                        const psb_dist_t* R, psb_csr_t P0, const double* const* d_dinv,
+                        psb_prec_t coarse, const int64_t* h_starts0, double omega, int32_t nu_pre,
+                        int32_t nu_post, int32_t n_iters, double tau, psb_prec_t* out);
+int64_t psb_dist_gmres_workspace_bytes(int64_t n_loc, int64_t n_halo, int32_t maxiter);
+/* psb_gmres_solve on this rank's row block D: every reduction (||b||, the batched Gram-Schmidt
+ * dots, ||w||^2, the true residual) is all-reduced, the SpMV exchanges its halo. */
+int psb_dist_gmres_solve(psb_dist_t D, psb_prec_t prec, const double* d_b_loc, double* d_x_loc,
+                         void* d_work, int64_t work_bytes, int32_t maxiter, double tau,
+                         int32_t fail_on_maxiter, int32_t orth, double* d_hist,
+                         psb_solve_result* result, void* stream);
 
 #ifdef __cplusplus
 }

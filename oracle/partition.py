@@ -57,6 +57,38 @@ def partition(A, nranks):
     return out
 
 
+def partition_rect(M, nranks):
+    """The same contract for a RECTANGULAR operator (restriction / prolongation blocks of the
+    row-partitioned V-cycle): rows split like ``row_starts(n_rows)``, the INPUT vector like
+    ``row_starts(n_cols)``; a rank's halo = sorted unique column ids outside its own input
+    range, local numbering = owned input entries first, then halo in sorted-global order."""
+    M = sp.csr_matrix(M)
+    rs, cs = row_starts(M.shape[0], nranks), row_starts(M.shape[1], nranks)
+    out = []
+    for r in range(nranks):
+        lo, hi, clo, chi = int(rs[r]), int(rs[r + 1]), int(cs[r]), int(cs[r + 1])
+        blk = M[lo:hi, :]
+        cols = blk.indices.astype(np.int64)
+        off = (cols < clo) | (cols >= chi)
+        recv = np.unique(cols[off])
+        owner = np.searchsorted(cs, recv, side='right') - 1
+        local_cols = np.empty_like(cols)
+        local_cols[~off] = cols[~off] - clo
+        local_cols[off] = (chi - clo) + np.searchsorted(recv, cols[off])
+        out.append(dict(lo=lo, hi=hi, clo=clo, chi=chi, indptr=blk.indptr.astype(np.int32),
+                        indices=local_cols.astype(np.int32), recv=recv, recv_owner=owner))
+    for r in range(nranks):
+        send = {}
+        for q in range(nranks):
+            if q == r:
+                continue
+            ids = out[q]['recv'][out[q]['recv_owner'] == r]
+            if ids.size:
+                send[q] = (ids - out[r]['clo']).astype(np.int32)
+        out[r]['send'] = send
+    return out
+
+
 def interior_boundary_rows(indptr, indices, nloc):
     """Rows with no halo column (interior) / at least one (boundary)."""
     has_halo = np.zeros(len(indptr) - 1, dtype=bool)

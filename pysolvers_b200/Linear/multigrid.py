@@ -145,10 +145,12 @@ class SmoothedAggregationMLHierarchy(MLHierarchy):
 
     def __init__(self, A_fine, numLevels=2, tol=None, normalize=True):
         super().__init__(numLevels=numLevels, normalize=normalize)
+        # ``tol`` is accepted and stored exactly like the reference does -- and, exactly like
+        # there, it changes nothing: SA_coarsen calls BuildAggregates WITHOUT it
+        # (SmoothedAggregation.py:218, so the strength test always uses 0.08 * 0.5^(lvl-1)) and
+        # BuildFilteredMatrix takes it as an argument it never reads (:156-183).
         self.tol = tol
         self.normalize = normalize
-        if tol is not None:
-            raise NotImplementedError('only the default (Vanek) tolerance is supported')
         tab = Tab()
         for lev in reversed(range(numLevels - 1)):
             print('{}making prolongator from level {} to {}'.format(tab, lev, lev + 1))
@@ -161,8 +163,7 @@ class SmoothedAggregationMLHierarchy(MLHierarchy):
 def SA_coarsen(A, tol=None, lvl=1):
     """(P, aggregates) of one coarsening step (SmoothedAggregation.py:208-229);
     aggregates as a list of sets."""
-    if tol is not None:
-        raise NotImplementedError('only the default (Vanek) tolerance is supported')
+    # tol: accepted, without effect -- as in the reference (see SmoothedAggregationMLHierarchy)
     P, agg_of = amg_setup.sa_coarsen(A, lvl=lvl)
     n_agg = P.shape[1]
     order = np.argsort(agg_of, kind='stable')
@@ -218,7 +219,7 @@ class DeviceAMG:
     def handle(self):
         return self.prec.handle
 
-    def solve(self, b, maxiter, tau):
+    def solve(self, b, maxiter, tau, keep_on_device=False):
         """(x, result, hist) of up to maxiter V-cycles from x0 = b."""
         b_d = to_device(b)
         x_d = torch.empty_like(b_d)
@@ -226,7 +227,7 @@ class DeviceAMG:
         res = nat.SolveResult()
         nat.check(nat.lib().psb_amg_solve(self.handle, ptr(b_d), ptr(x_d), int(maxiter), float(tau),
                                           ptr(hist), C.byref(res), current_stream_ptr()), 'psb_amg_solve')
-        return to_host(x_d), res, hist[:res.n_hist].cpu().numpy()
+        return (x_d if keep_on_device else to_host(x_d)), res, hist[:res.n_hist].cpu().numpy()
 
 
 class VCycleManager:
@@ -279,16 +280,20 @@ class AMGVCycleSolver(IterativeLinearSolver):
     def solve(self, A, b):
         n = self._check_system(A, b)
         self._require_euclidean_norm()
-        b = np.asarray(b)
-        if n == 0 or not np.any(b):
-            return self.handleConvergence(0, np.zeros_like(b), 0, 0)
+        # device right-hand sides stay on the device, like PCG / GMRES (DeviceFDBratu2D hands them in)
+        on_device = isinstance(b, torch.Tensor)
+        if not on_device:
+            b = np.asarray(b)
+        zeros = (lambda: torch.zeros_like(b)) if on_device else (lambda: np.zeros_like(b))
+        if n == 0 or not bool((b != 0).any()):
+            return self.handleConvergence(0, zeros(), 0, 0)
         dev = self.device_amg(A)
-        x, res, hist = dev.solve(b, int(self.maxiter()), float(self.tau()))
+        x, res, hist = dev.solve(b, int(self.maxiter()), float(self.tau()), keep_on_device=on_device)
         self.last_history = hist
         for k in range(res.n_hist):
             self.reportIter(k, hist[k], res.norm_b)
         if res.status == nat.TRIVIAL:
-            return self.handleConvergence(0, np.zeros_like(b), 0, 0)
+            return self.handleConvergence(0, zeros(), 0, 0)
         if res.status == nat.CONVERGED:
             return self.handleConvergence(res.k, x, res.norm_r, res.norm_b)
         return self.handleMaxiter(res.k, x, res.norm_r, res.norm_b)

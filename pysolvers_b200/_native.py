@@ -96,6 +96,11 @@ SIGNATURES = {
     'psb_dist_pcg_workspace_bytes': (_i64, [_i64, _i64]),
     'psb_dist_pcg_solve': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _dbl, _i32, _vp,
                                      C.POINTER(SolveResult), _vp]),
+    'psb_dist_amg_create': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i32, _i32, _i32, _dbl,
+                                      C.POINTER(_vp)]),
+    'psb_dist_gmres_workspace_bytes': (_i64, [_i64, _i64, _i32]),
+    'psb_dist_gmres_solve': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _dbl, _i32, _i32, _vp,
+                                       C.POINTER(SolveResult), _vp]),
 }
 
 _lib = None

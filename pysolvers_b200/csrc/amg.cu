@@ -74,10 +74,66 @@ amg_begin_kernel(AmgState* st, const int* outer_skip, int64_t n, const double* _
   }
 }
 
+// row-partitioned solve: the same two steps with the all-reduce of the local sums in between
+__global__ void __launch_bounds__(kBlock)
+amg_begin_local_kernel(AmgState* st, const int* outer_skip, int64_t n, const double* __restrict__ b,
+                       double* __restrict__ x, ReduceBuf rb) {
+  __shared__ double scratch[kWarps];
+  const int outer = outer_skip ? ld_cg(outer_skip) : 0;
+  double acc = 0.0;
+  if (!outer) {
+    for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+      const double v = b[i];
+      x[i] = v;                                             // x0 = b   (VCycleSolver.py:69)
+      acc += v * v;
+    }
+  }
+  double t = block_sum(acc, scratch);
+  if (threadIdx.x == 0) rb.partials[blockIdx.x] = t;
+  if (last_block(rb.ticket)) {
+    double bb = sum_partials(rb.partials, gridDim.x, scratch);
+    if (threadIdx.x == 0) { st->bb = bb; st->skip = outer; }
+  }
+}
+
+__global__ void amg_begin_finish_kernel(AmgState* st, double tau, int maxiter) {
+  if (threadIdx.x != 0) return;
+  const double bb = st->bb;                                 // summed over the ranks
+  st->tau = tau; st->maxiter = maxiter; st->cycles = 0; st->norm_r = 0.0;
+  st->norm_b = sqrt(bb);
+  st->status = PSB_MAXITER;
+  if (!st->skip && bb == 0.0) { st->skip = 1; st->status = PSB_TRIVIAL; }
+}
+
+__global__ void amg_cycle_finish_kernel(AmgState* st, double* hist) {   // VCycleSolver.py:87-91
+  if (threadIdx.x != 0 || st->skip != 0) return;
+  const double nr = sqrt(st->rr);
+  const int k = st->cycles;
+  st->norm_r = nr;
+  if (hist != nullptr) hist[k] = nr;
+  st->cycles = k + 1;
+  if (nr < st->tau * st->norm_b) { st->status = PSB_CONVERGED; st->skip = 1; }
+  else if (k + 1 >= st->maxiter) { st->skip = 1; }
+}
+
+// An operator of the hierarchy: the whole matrix (one GPU) or this rank's row block with its halo
+// plan (row-partitioned: the input vector must then be an EXTENDED buffer, owned entries
+// followed by room for the halo, which the exchange fills in place).
+struct AmgOp {
+  psb_csr* local = nullptr;
+  psb_dist* dist = nullptr;
+  bool present() const { return local != nullptr || dist != nullptr; }
+  int launch(Epi epi, double* x, double* y, const EpiArgs& ea, const int* skip, cudaStream_t s) const {
+    return dist ? dist_spmv_epi(dist, epi, x, y, ea, skip, s) : spmv_launch(local, epi, x, y, ea, skip, s);
+  }
+  int64_t rows() const { return dist ? dist_n_loc(dist) : local->n_rows; }
+  int64_t x_len() const { return dist ? dist_n_own(dist) + dist_n_halo(dist) : local->n_cols; }
+};
+
 struct AmgLevel {
-  psb_csr* A = nullptr;
-  psb_csr* P = nullptr;        // this level -> next finer level
-  psb_csr* R = nullptr;        // next finer level -> this level
+  AmgOp A;
+  AmgOp P;                     // this level -> next finer level
+  AmgOp R;                     // next finer level -> this level
   const double* dinv = nullptr;
   psb_trsv* gsU = nullptr;
   int64_t n = 0;
@@ -94,6 +150,11 @@ struct AmgPrec : psb_prec {
   AmgState* st = nullptr;              // owned
   ReduceBuf rb;                        // owned
   double* hist_scratch = nullptr;      // owned
+  // row-partitioned (psb_dist_amg_create): the coarsest system is solved REPLICATED -- its
+  // right-hand side is gathered from the ranks, every rank solves, and the prolongator block
+  // reads the full coarse vector through global column numbers (no exchange)
+  psb_comm* comm = nullptr;
+  std::vector<int64_t> starts0;        // coarsest-level row partition [nranks + 1]
 
   ~AmgPrec() override {
     for (auto& l : lev) { cudaFree(l.x); cudaFree(l.x2); cudaFree(l.f); cudaFree(l.r); }
@@ -104,9 +165,7 @@ struct AmgPrec : psb_prec {
     int bad = coarse ? coarse->check_error() : 0;
     for (auto& l : lev) {
       if (l.gsU) {
-        int f = 0;
-        cudaMemcpy(&f, l.gsU->d_error, sizeof(int), cudaMemcpyDeviceToHost);
-        bad |= f;
+        bad |= trsv_take_error(l.gsU);
       }
     }
     return bad;
@@ -119,12 +178,12 @@ struct AmgPrec : psb_prec {
     for (int i = 0; i < nu; ++i) {
       if (smoother == PSB_SMOOTH_JACOBI) {
         EpiArgs ea; ea.f = f; ea.dinv = L.dinv; ea.omega = omega;
-        int rc = spmv_launch(L.A, EPI_JACOBI, x, spare, ea, skip, s);
+        int rc = L.A.launch(EPI_JACOBI, x, spare, ea, skip, s);
         if (rc != PSB_OK) return rc;
         std::swap(x, spare);
       } else {
         EpiArgs ea; ea.f = f;
-        int rc = spmv_launch(L.A, EPI_RESID, x, L.r, ea, skip, s);          // r = f - A x
+        int rc = L.A.launch(EPI_RESID, x, L.r, ea, skip, s);                // r = f - A x
         if (rc != PSB_OK) return rc;
         rc = trsv_solve(L.gsU, L.r, spare, nullptr, nullptr, nullptr, skip, s);   // dx = U^-1 r
         if (rc != PSB_OK) return rc;
@@ -140,14 +199,22 @@ struct AmgPrec : psb_prec {
   int run_level(int l, const double* f, double*& x, double*& spare, cudaStream_t s) {
     const int* skip = &st->skip;
     AmgLevel& L = lev[l];
-    if (l == 0) return coarse->apply(f, x, skip, s);                          // VCycleManager.py:34-37
+    if (l == 0) {                                                             // VCycleManager.py:34-37
+      if (comm != nullptr) {          // f, x are the FULL coarse vectors: gather the slices, solve everywhere
+        int rc = dist_allgather_slices(comm, const_cast<double*>(f), starts0.data(), s);
+        if (rc != PSB_OK) return rc;
+      }
+      return coarse->apply(f, x, skip, s);
+    }
     int rc = smooth(l, f, x, spare, nu_pre, s);                               // :42
     if (rc != PSB_OK) return rc;
     EpiArgs ea; ea.f = f;
-    rc = spmv_launch(L.A, EPI_RESID, x, L.r, ea, skip, s);                    // :45
+    rc = L.A.launch(EPI_RESID, x, L.r, ea, skip, s);                          // :45
     if (rc != PSB_OK) return rc;
     AmgLevel& C = lev[l - 1];
-    rc = spmv_launch(C.R, EPI_STORE, L.r, C.f, EpiArgs(), skip, s);           // :48
+    // row-partitioned, coarsest level: C.f is the full vector, this rank's rows start at starts0[rank]
+    double* cf_rows = (comm != nullptr && l - 1 == 0) ? C.f + starts0[dist_rank(comm)] : C.f;
+    rc = C.R.launch(EPI_STORE, L.r, cf_rows, EpiArgs(), skip, s);             // :48
     if (rc != PSB_OK) return rc;
     double* cx = C.x;
     double* cs = C.x2;
@@ -157,7 +224,7 @@ struct AmgPrec : psb_prec {
     }
     rc = run_level(l - 1, C.f, cx, cs, s);                                    // :52
     if (rc != PSB_OK) return rc;
-    rc = spmv_launch(C.P, EPI_ADD, cx, x, EpiArgs(), skip, s);                // :55
+    rc = C.P.launch(EPI_ADD, cx, x, EpiArgs(), skip, s);                      // :55
     if (rc != PSB_OK) return rc;
     return smooth(l, f, x, spare, nu_post, s);                                // :60
   }
@@ -165,37 +232,65 @@ struct AmgPrec : psb_prec {
   // maxiter V-cycles on (b -> x_out); hist nullable.  `final_residual`: also evaluate ||b - A x||
   // after the LAST cycle (the solver reports it; as a preconditioner nothing depends on it --
   // AMGPreconditioner.py:46-51 returns x whether or not the last test passes, failOnMaxiter=False).
+  // Row-partitioned (comm != nullptr): b, x_out are this rank's slices; the iterate lives in the
+  // level's own EXTENDED buffers (room for the halo) and is copied to x_out at the end.
   int solve(const double* b, double* x_out, int maxiter, double tol, double* hist,
             const int* outer_skip, bool final_residual, cudaStream_t s) {
     const int top = (int)lev.size() - 1;
     AmgLevel& F = lev[top];
+    const bool dist = comm != nullptr;
     const int grid = stream_grid(F.n, rb.max_grid);
-    amg_begin_kernel<<<grid, kBlock, 0, s>>>(st, outer_skip, F.n, b, x_out, tol, maxiter, rb);
-    PSB_LAUNCH_CHECK();
+    double* home = dist ? F.x : x_out;          // where the iterate lives between cycles
+    if (dist) {
+      amg_begin_local_kernel<<<grid, kBlock, 0, s>>>(st, outer_skip, F.n, b, home, rb);
+      PSB_LAUNCH_CHECK();
+      int rc = dist_allreduce(comm, &st->bb, 1, s);
+      if (rc != PSB_OK) return rc;
+      amg_begin_finish_kernel<<<1, 32, 0, s>>>(st, tol, maxiter);
+      PSB_LAUNCH_CHECK();
+    } else {
+      amg_begin_kernel<<<grid, kBlock, 0, s>>>(st, outer_skip, F.n, b, home, tol, maxiter, rb);
+      PSB_LAUNCH_CHECK();
+    }
     const int* skip = &st->skip;
     for (int k = 0; k < maxiter; ++k) {
-      double* x = x_out;
+      double* x = home;
       double* spare = F.x2;
       int rc;
       if (top == 0) {
         // single level: the "cycle" is the direct solve
         rc = coarse->apply(b, F.x2, skip, s);
         if (rc != PSB_OK) return rc;
-        x = F.x2; spare = x_out;
+        x = F.x2; spare = home;
       } else {
         rc = run_level(top, b, x, spare, s);
         if (rc != PSB_OK) return rc;
       }
-      if (x != x_out) {                       // odd number of ping-pong sweeps: bring x home
-        amg_copy_kernel<<<grid, kBlock, 0, s>>>(x_out, x, F.n, skip);
+      if (x != home) {                        // odd number of ping-pong sweeps: bring x home
+        amg_copy_kernel<<<grid, kBlock, 0, s>>>(home, x, F.n, skip);
         PSB_LAUNCH_CHECK();
       }
       if (k + 1 == maxiter && !final_residual) break;
       // r = b - A x with ||r||, the history entry and the strict '<' test done by the kernel's
       // last CTA (VCycleSolver.py:84-91): no separate pass over r
-      EpiArgs ea; ea.f = b; ea.amg_state = st; ea.amg_hist = hist;
-      rc = spmv_launch(F.A, EPI_RESID_NORM, x_out, F.r, ea, skip, s);
-      if (rc != PSB_OK) return rc;
+      EpiArgs ea; ea.f = b;
+      if (dist) {
+        ea.dot = &st->rr;                     // this rank's part; finished after the all-reduce
+        rc = F.A.launch(EPI_RESID_NORM, home, F.r, ea, skip, s);
+        if (rc != PSB_OK) return rc;
+        rc = dist_allreduce(comm, &st->rr, 1, s);
+        if (rc != PSB_OK) return rc;
+        amg_cycle_finish_kernel<<<1, 32, 0, s>>>(st, hist);
+        PSB_LAUNCH_CHECK();
+      } else {
+        ea.amg_state = st; ea.amg_hist = hist;
+        rc = F.A.launch(EPI_RESID_NORM, home, F.r, ea, skip, s);
+        if (rc != PSB_OK) return rc;
+      }
+    }
+    if (dist) {                               // the result, whether or not the cycles were skipped
+      amg_copy_kernel<<<grid, kBlock, 0, s>>>(x_out, home, F.n, outer_skip);
+      PSB_LAUNCH_CHECK();
     }
     return PSB_OK;
   }
@@ -208,6 +303,44 @@ struct AmgPrec : psb_prec {
 }  // namespace psb
 
 using namespace psb;
+
+static int amg_finish_create(AmgPrec* M, psb_prec_t* out) {
+  cudaError_t e = cudaSuccess;
+  const int n_levels = (int)M->lev.size();
+  const bool dist = M->comm != nullptr;
+  for (int l = 0; l < n_levels && e == cudaSuccess; ++l) {
+    AmgLevel& L = M->lev[l];
+    // buffer lengths: x / x2 are read by A_l and by P_l (towards level l+1), r by R_{l-1};
+    // row-partitioned these are extended buffers, and the coarsest x / f hold the FULL vectors
+    int64_t len_x = L.n, len_r = L.n, len_f = L.n;
+    if (dist) {
+      if (l == 0) { len_x = len_f = M->starts0.back(); }
+      else {
+        len_x = std::max(len_x, L.A.x_len());
+        if (L.P.present()) len_x = std::max(len_x, L.P.x_len());
+        len_r = std::max(len_r, M->lev[l - 1].R.x_len());
+      }
+    }
+    auto bytes = [](int64_t n) { return (size_t)std::max<int64_t>(n, 1) * sizeof(double); };
+    e = cudaMalloc((void**)&L.x, bytes(len_x));
+    if (e == cudaSuccess) e = cudaMemset(L.x, 0, bytes(len_x));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&L.x2, bytes(len_x));
+    if (e == cudaSuccess) e = cudaMemset(L.x2, 0, bytes(len_x));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&L.f, bytes(len_f));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&L.r, bytes(len_r));
+    if (e == cudaSuccess) e = cudaMemset(L.r, 0, bytes(len_r));
+  }
+  M->n = M->lev[n_levels - 1].n;
+  M->rb.max_grid = sm_count() * 16;
+  if (e == cudaSuccess) e = cudaMalloc((void**)&M->st, sizeof(AmgState));
+  if (e == cudaSuccess) e = cudaMemset(M->st, 0, sizeof(AmgState));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&M->rb.partials, sizeof(double) * M->rb.max_grid);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&M->rb.ticket, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(M->rb.ticket, 0, sizeof(unsigned int));
+  if (e != cudaSuccess) { delete M; set_error("psb_amg_create: %s", cudaGetErrorString(e)); return PSB_ERR_CUDA; }
+  *out = M;
+  return PSB_OK;
+}
 
 extern "C" int psb_amg_create(int32_t n_levels, const psb_csr_t* A, const psb_csr_t* P, const psb_csr_t* R,
                               const double* const* d_dinv, const psb_trsv_t* gsU, psb_prec_t coarse,
@@ -223,16 +356,15 @@ extern "C" int psb_amg_create(int32_t n_levels, const psb_csr_t* A, const psb_cs
   M->smoother = smoother; M->omega = omega; M->nu_pre = nu_pre; M->nu_post = nu_post;
   M->n_iters = n_iters; M->tau = tau; M->coarse = coarse;
   M->lev.resize(n_levels);
-  cudaError_t e = cudaSuccess;
-  for (int l = 0; l < n_levels && e == cudaSuccess; ++l) {
+  for (int l = 0; l < n_levels; ++l) {
     AmgLevel& L = M->lev[l];
-    L.A = A[l];
-    if (!L.A || L.A->n_rows != L.A->n_cols) { delete M; set_error("psb_amg_create: level matrix %d invalid", l); return PSB_ERR_ARG; }
-    L.n = L.A->n_rows;
+    L.A.local = A[l];
+    if (!A[l] || A[l]->n_rows != A[l]->n_cols) { delete M; set_error("psb_amg_create: level matrix %d invalid", l); return PSB_ERR_ARG; }
+    L.n = A[l]->n_rows;
     if (l < n_levels - 1) {
-      L.P = P[l]; L.R = R[l];
-      if (!L.P || !L.R || L.P->n_cols != L.n || L.R->n_rows != L.n || L.P->n_rows != A[l + 1]->n_rows ||
-          L.R->n_cols != A[l + 1]->n_rows) {
+      L.P.local = P[l]; L.R.local = R[l];
+      if (!P[l] || !R[l] || P[l]->n_cols != L.n || R[l]->n_rows != L.n || P[l]->n_rows != A[l + 1]->n_rows ||
+          R[l]->n_cols != A[l + 1]->n_rows) {
         delete M; set_error("psb_amg_create: transfer operator shapes do not match at level %d", l); return PSB_ERR_ARG;
       }
     }
@@ -247,23 +379,53 @@ extern "C" int psb_amg_create(int32_t n_levels, const psb_csr_t* A, const psb_cs
         L.gsU = gsU[l];
       }
     }
-    const size_t bytes = (size_t)std::max<int64_t>(L.n, 1) * sizeof(double);
-    e = cudaMalloc((void**)&L.x, bytes);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&L.x2, bytes);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&L.f, bytes);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&L.r, bytes);
   }
-  M->n = M->lev[n_levels - 1].n;
   if (coarse->n != M->lev[0].n) { delete M; set_error("psb_amg_create: coarse solver size mismatch"); return PSB_ERR_ARG; }
-  M->rb.max_grid = sm_count() * 16;
-  if (e == cudaSuccess) e = cudaMalloc((void**)&M->st, sizeof(AmgState));
-  if (e == cudaSuccess) e = cudaMemset(M->st, 0, sizeof(AmgState));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&M->rb.partials, sizeof(double) * M->rb.max_grid);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&M->rb.ticket, sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMemset(M->rb.ticket, 0, sizeof(unsigned int));
-  if (e != cudaSuccess) { delete M; set_error("psb_amg_create: %s", cudaGetErrorString(e)); return PSB_ERR_CUDA; }
-  *out = M;
-  return PSB_OK;
+  return amg_finish_create(M, out);
+}
+
+// Row-partitioned V-cycle ("AMG with Jacobi smoothing shards like SpMV, coarse
+// solve replicated").  Level l >= 1: A[l] is this rank's row block of A_l; R[l-1] its block of the
+// restriction (rows: level l-1, input: level-l vector); P[l-1] its block of the prolongator (rows:
+// level l, input: level l-1 vector) -- for l-1 == 0 that is a plain local CSR P0 whose columns
+// are GLOBAL coarse indices, because the coarsest vector is replicated: every rank gathers the
+// coarse right-hand side (h_starts0 = its row partition) and runs the same exact solve `coarse`
+// (whole coarsest system).  Jacobi smoothing only: Gauss-Seidel has a global dependency chain.
+extern "C" int psb_dist_amg_create(psb_comm_t comm, int32_t n_levels, const psb_dist_t* A, const psb_dist_t* P,
+                                   const psb_dist_t* R, psb_csr_t P0, const double* const* d_dinv,
+                                   psb_prec_t coarse, const int64_t* h_starts0, double omega, int32_t nu_pre,
+                                   int32_t nu_post, int32_t n_iters, double tau, psb_prec_t* out) {
+  PSB_REQUIRE(comm && n_levels >= 2 && A && R && P0 && d_dinv && coarse && h_starts0 && out, PSB_ERR_ARG,
+              "psb_dist_amg_create: bad argument (needs at least two levels)");
+  PSB_REQUIRE(n_levels == 2 || P, PSB_ERR_ARG, "psb_dist_amg_create: prolongator blocks missing");
+  PSB_REQUIRE(nu_pre >= 0 && nu_post >= 0 && n_iters >= 1, PSB_ERR_ARG, "psb_dist_amg_create: bad sweep counts");
+  AmgPrec* M = new (std::nothrow) AmgPrec();
+  PSB_REQUIRE(M != nullptr, PSB_ERR_ARG, "psb_dist_amg_create: out of host memory");
+  M->smoother = PSB_SMOOTH_JACOBI; M->omega = omega; M->nu_pre = nu_pre; M->nu_post = nu_post;
+  M->n_iters = n_iters; M->tau = tau; M->coarse = coarse; M->comm = comm;
+  const int nr = dist_nranks(comm), me = dist_rank(comm);
+  M->starts0.assign(h_starts0, h_starts0 + nr + 1);
+  M->lev.resize(n_levels);
+  M->lev[0].n = M->starts0[me + 1] - M->starts0[me];
+  for (int l = 1; l < n_levels; ++l) {
+    AmgLevel& L = M->lev[l];
+    if (!A[l] || !R[l - 1] || !d_dinv[l] || dist_n_own(A[l]) != dist_n_loc(A[l])) {
+      delete M; set_error("psb_dist_amg_create: operator missing or not square at level %d", l); return PSB_ERR_ARG;
+    }
+    L.A.dist = A[l];
+    L.n = dist_n_loc(A[l]);
+    L.dinv = d_dinv[l];
+    AmgLevel& C = M->lev[l - 1];
+    C.R.dist = R[l - 1];
+    if (l - 1 == 0) C.P.local = P0; else C.P.dist = P[l - 1];
+    const int64_t c_rows = dist_n_loc(R[l - 1]);
+    const bool ok = c_rows == C.n && dist_n_own(R[l - 1]) == L.n &&
+                    (l - 1 == 0 ? (P0->n_rows == L.n && P0->n_cols == M->starts0[nr])
+                                : (P[l - 1] && dist_n_loc(P[l - 1]) == L.n && dist_n_own(P[l - 1]) == C.n));
+    if (!ok) { delete M; set_error("psb_dist_amg_create: transfer operator shapes do not match at level %d", l - 1); return PSB_ERR_ARG; }
+  }
+  if (coarse->n != M->starts0[nr]) { delete M; set_error("psb_dist_amg_create: the coarse solver must cover the whole coarsest system"); return PSB_ERR_ARG; }
+  return amg_finish_create(M, out);
 }
 
 // AMGVCycleSolver.solve: up to maxiter V-cycles from x0 = b; d_hist (maxiter doubles) receives

@@ -91,8 +91,10 @@ struct psb_comm {
 
 struct psb_dist {
   psb_comm* comm = nullptr;
-  psb_csr* A = nullptr;           // local block: n_loc rows, n_loc + n_halo columns
+  psb_csr* A = nullptr;           // local block: n_loc rows, n_own + n_halo columns
   int64_t n_loc = 0, n_halo = 0;
+  int64_t n_own = 0;              // owned entries of the INPUT vector (= n_loc for a square operator;
+                                  // restriction / prolongation blocks are rectangular)
   int64_t r0 = 0, r1 = 0;         // rows [r0, r1) touch no halo column
   struct Peer { int rank; int64_t send_off, send_cnt, recv_off, recv_cnt; int32_t* d_send_idx; double* d_send_buf; };
   std::vector<Peer> peers;
@@ -445,7 +447,7 @@ static int halo_exchange(psb_dist* D, double* v, const int* d_skip) {
       PSB_NCCL(g_nccl.Send(src, (size_t)pr.send_cnt, ncclDouble, pr.rank, c->comm, c->comm_stream));
     }
     if (pr.recv_cnt > 0)
-      PSB_NCCL(g_nccl.Recv(v + D->n_loc + pr.recv_off, (size_t)pr.recv_cnt, ncclDouble, pr.rank, c->comm,
+      PSB_NCCL(g_nccl.Recv(v + D->n_own + pr.recv_off, (size_t)pr.recv_cnt, ncclDouble, pr.rank, c->comm,
                            c->comm_stream));
   }
   PSB_NCCL(g_nccl.GroupEnd());
@@ -514,13 +516,14 @@ extern "C" int psb_dist_create(psb_comm_t comm, psb_csr_t A_local, int64_t n_loc
                                const int64_t* h_recv_cnt, psb_dist_t* out) {
   PSB_REQUIRE(comm && A_local && out && n_loc >= 0 && n_halo >= 0 && n_peers >= 0, PSB_ERR_ARG,
               "psb_dist_create: bad argument");
-  PSB_REQUIRE(A_local->n_rows == n_loc && A_local->n_cols == n_loc + n_halo, PSB_ERR_ARG,
-              "psb_dist_create: local matrix must be n_loc x (n_loc + n_halo)");
+  PSB_REQUIRE(A_local->n_rows == n_loc && A_local->n_cols >= n_halo, PSB_ERR_ARG,
+              "psb_dist_create: local matrix must be n_loc x (n_own + n_halo)");
   PSB_REQUIRE(0 <= r0 && r0 <= r1 && r1 <= n_loc && (r0 % 4) == 0 && (r1 % 4 == 0 || r1 == n_loc),
               PSB_ERR_ARG, "psb_dist_create: interior range must be 4-aligned and inside [0, n_loc]");
   psb_dist* D = new (std::nothrow) psb_dist();
   PSB_REQUIRE(D != nullptr, PSB_ERR_ARG, "psb_dist_create: out of host memory");
   D->comm = comm; D->A = A_local; D->n_loc = n_loc; D->n_halo = n_halo; D->r0 = r0; D->r1 = r1;
+  D->n_own = A_local->n_cols - n_halo;
   for (int i = 0; i < n_peers; ++i) {
     psb_dist::Peer p;
     p.rank = h_peer_rank[i];
@@ -554,6 +557,7 @@ extern "C" int psb_dist_destroy(psb_dist_t D) {
 extern "C" int psb_dist_p2p_alloc(psb_dist_t D, void* h_handle64, int64_t layout[6]) {
   PSB_REQUIRE(D && h_handle64 && layout, PSB_ERR_ARG, "psb_dist_p2p_alloc: NULL argument");
   PSB_REQUIRE(D->comm->nranks <= kMaxRanks, PSB_ERR_UNSUPP, "psb_dist_p2p_alloc: too many ranks");
+  PSB_REQUIRE(D->n_own == D->n_loc, PSB_ERR_UNSUPP, "psb_dist_p2p_alloc: the peer-memory PCG path needs a square operator");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
   const int64_t vec = align_up((D->n_loc + D->n_halo) * 8, 256);
   D->pbuf_off[0] = kSlotsBytes + kFlagsBytes;
@@ -614,10 +618,14 @@ extern "C" int psb_dist_p2p_open(psb_dist_t D, const void* h_handles, int32_t n_
   return PSB_OK;
 }
 
-// y_loc = A_loc [x_loc | halo(x)]: exchanges the halo of d_x_ext (length n_loc + n_halo) and
-// multiplies; interior rows overlap the exchange.  d_dot3 (nullable): three partial x.y sums.
-static int dist_spmv(psb_dist* D, double* d_x_ext, double* d_y, double* d_dot3, const int* d_skip,
-                     cudaStream_t st) {
+namespace psb {
+
+// y_loc = A_loc [x_own | halo(x)] with any SpMV epilogue: exchanges the halo of d_x_ext (length
+// n_own + n_halo) and multiplies; interior rows overlap the exchange.  Reductions: EPI_DOT writes
+// three partial sums to ea.dot[0..2] (boundary-low, interior, boundary-high; absent parts stay
+// untouched: zero them first); EPI_RESID_NORM accumulates ONE local sum in *ea.dot.
+int dist_spmv_epi(psb_dist* D, Epi epi, double* d_x_ext, double* d_y, const EpiArgs& ea0, const int* d_skip,
+                  cudaStream_t st) {
   psb_comm* c = D->comm;
   const bool comm_needed = !D->peers.empty();
   if (comm_needed) {
@@ -627,30 +635,71 @@ static int dist_spmv(psb_dist* D, double* d_x_ext, double* d_y, double* d_dot3, 
     if (rc != PSB_OK) return rc;
     PSB_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
   }
-  const Epi epi = d_dot3 ? EPI_DOT : EPI_STORE;
-  EpiArgs ea;
+  EpiArgs ea = ea0;
+  double* const dot = ea0.dot;
+  int launched = 0;
   int rc;
+  auto part = [&](int64_t a, int64_t b, int which) -> int {
+    psb_csr v = csr_row_view(D->A, a, b);
+    if (epi == EPI_DOT && dot) ea.dot = dot + which;
+    if (epi == EPI_RESID_NORM) ea.dot_accumulate = launched > 0 ? 1 : 0;
+    ++launched;
+    return spmv_launch(&v, epi, d_x_ext, d_y, ea, d_skip, st);
+  };
   if (D->r1 > D->r0) {                                   // interior rows: no halo column
-    psb_csr v = csr_row_view(D->A, D->r0, D->r1);
-    if (d_dot3) ea.dot = d_dot3 + 1;
-    rc = spmv_launch(&v, epi, d_x_ext, d_y, ea, d_skip, st);
+    rc = part(D->r0, D->r1, 1);
     if (rc != PSB_OK) return rc;
   }
   if (comm_needed) PSB_CUDA(cudaStreamWaitEvent(st, c->ev_halo, 0));
   if (D->r0 > 0) {
-    psb_csr v = csr_row_view(D->A, 0, D->r0);
-    if (d_dot3) ea.dot = d_dot3 + 0;
-    rc = spmv_launch(&v, epi, d_x_ext, d_y, ea, d_skip, st);
+    rc = part(0, D->r0, 0);
     if (rc != PSB_OK) return rc;
   }
   if (D->r1 < D->n_loc) {
-    psb_csr v = csr_row_view(D->A, D->r1, D->n_loc);
-    if (d_dot3) ea.dot = d_dot3 + 2;
-    rc = spmv_launch(&v, epi, d_x_ext, d_y, ea, d_skip, st);
+    rc = part(D->r1, D->n_loc, 2);
     if (rc != PSB_OK) return rc;
   }
   return PSB_OK;
 }
+
+static int dist_spmv(psb_dist* D, double* d_x_ext, double* d_y, double* d_dot3, const int* d_skip,
+                     cudaStream_t st) {
+  EpiArgs ea;
+  ea.dot = d_dot3;
+  return dist_spmv_epi(D, d_dot3 ? EPI_DOT : EPI_STORE, d_x_ext, d_y, ea, d_skip, st);
+}
+
+// Sum `count` doubles in place over the ranks of D's communicator (stream-ordered).
+int dist_allreduce(psb_comm* c, double* d_buf, int count, cudaStream_t st) {
+  PSB_NCCL(g_nccl.AllReduce(d_buf, d_buf, (size_t)count, ncclDouble, ncclSum, c->comm, st));
+  return PSB_OK;
+}
+
+// Every rank contributes d_full[starts[rank] .. starts[rank+1]) and receives the other slices
+// (grouped send / recv: the slices need not have equal lengths).  Stream-ordered on st.
+int dist_allgather_slices(psb_comm* c, double* d_full, const int64_t* starts, cudaStream_t st) {
+  const int me = c->rank;
+  PSB_NCCL(g_nccl.GroupStart());
+  for (int q = 0; q < c->nranks; ++q) {
+    if (q == me) continue;
+    const int64_t mine = starts[me + 1] - starts[me], theirs = starts[q + 1] - starts[q];
+    if (mine > 0) PSB_NCCL(g_nccl.Send(d_full + starts[me], (size_t)mine, ncclDouble, q, c->comm, st));
+    if (theirs > 0) PSB_NCCL(g_nccl.Recv(d_full + starts[q], (size_t)theirs, ncclDouble, q, c->comm, st));
+  }
+  PSB_NCCL(g_nccl.GroupEnd());
+  return PSB_OK;
+}
+
+int dist_rank(const psb_comm* c) { return c->rank; }
+int dist_nranks(const psb_comm* c) { return c->nranks; }
+int64_t dist_n_loc(const psb_dist* D) { return D->n_loc; }
+int64_t dist_n_own(const psb_dist* D) { return D->n_own; }
+int64_t dist_n_halo(const psb_dist* D) { return D->n_halo; }
+psb_comm* dist_comm(const psb_dist* D) { return D->comm; }
+
+}  // namespace psb
+
+using namespace psb;
 
 extern "C" int psb_dist_spmv(psb_dist_t D, double* d_x_ext, double* d_y, void* stream) {
   PSB_REQUIRE(D && d_x_ext && d_y, PSB_ERR_ARG, "psb_dist_spmv: NULL argument");

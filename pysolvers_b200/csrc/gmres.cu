@@ -86,13 +86,29 @@ gmres_init_kernel(GmresState* st, GmresSmall sm, int64_t n, const double* __rest
   if (threadIdx.x == 0) rb.partials[blockIdx.x] = t;
   if (last_block(rb.ticket)) {
     double bb = sum_partials(rb.partials, gridDim.x, scratch);
-    if (threadIdx.x == 0) {
-      const double nb = sqrt(bb);
-      st->norm_b = nb; st->beta = nb;
-      sm.g[0] = nb;                                   // g = beta * e1   (GMRESSolver.py:95-97)
-      if (nb == 0.0) { st->done = 1; st->status = PSB_TRIVIAL; st->k_final = 0; }
-    }
+    if (threadIdx.x == 0) st->tmp_dot = bb;           // this rank's part when row-partitioned
   }
+}
+
+// after b.b is complete (all-reduced when row-partitioned)
+__global__ void gmres_init_finish_kernel(GmresState* st, GmresSmall sm) {
+  if (threadIdx.x != 0) return;
+  const double nb = sqrt(st->tmp_dot);
+  st->norm_b = nb; st->beta = nb;
+  sm.g[0] = nb;                                       // g = beta * e1   (GMRESSolver.py:95-97)
+  if (nb == 0.0) { st->done = 1; st->status = PSB_TRIVIAL; st->k_final = 0; }
+}
+
+__global__ void gmres_norm_finish_kernel(GmresState* st) {
+  if (threadIdx.x == 0) st->norm_true = sqrt(st->tmp_dot);
+}
+
+__global__ void __launch_bounds__(kBlock)
+gmres_copy_kernel(const GmresState* st, int64_t n, const double* __restrict__ src, double* __restrict__ dst,
+                  int check_done) {
+  if (check_done && ld_cg(&st->done) != 0) return;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+    dst[i] = src[i];
 }
 
 // MGS step j of iteration k (reference order, GMRESSolver.py:110-115):
@@ -294,7 +310,7 @@ gmres_norm_kernel(GmresState* st, int64_t n, const double* __restrict__ r, Reduc
   if (threadIdx.x == 0) rb.partials[blockIdx.x] = t;
   if (last_block(rb.ticket)) {
     double s = sum_partials(rb.partials, gridDim.x, scratch);
-    if (threadIdx.x == 0) st->norm_true = sqrt(s);
+    if (threadIdx.x == 0) st->tmp_dot = s;
   }
 }
 
@@ -371,26 +387,24 @@ extern "C" int64_t psb_gmres_workspace_bytes(int64_t n, int32_t maxiter) {
   return 4096 + reduce_bytes() + small_bytes(m) + (m + 4) * basis_ld(n) * (int64_t)sizeof(double);
 }
 
-extern "C" int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, double* d_x,
-                               void* d_work, int64_t work_bytes, int32_t maxiter, double tau,
-                               int32_t fail_on_maxiter, int32_t orth, double* d_hist,
-                               psb_solve_result* result, void* stream) {
-  (void)fail_on_maxiter;
-  PSB_REQUIRE(A && d_b && d_x && d_work && d_hist && result, PSB_ERR_ARG, "psb_gmres_solve: NULL argument");
-  PSB_REQUIRE(A->n_rows == A->n_cols, PSB_ERR_ARG, "psb_gmres_solve: matrix must be square");
-  PSB_REQUIRE(maxiter >= 1, PSB_ERR_ARG, "psb_gmres_solve: maxiter must be >= 1");
-  PSB_REQUIRE(orth == PSB_ORTH_CGS2 || orth == PSB_ORTH_MGS, PSB_ERR_ARG, "psb_gmres_solve: unknown orth mode");
-  const int64_t n = A->n_rows, m = maxiter;
+// One GMRES solve; A whole on this GPU (D == nullptr) or this rank's row block D of a
+// row-partitioned system: then every vector is the rank's slice, the SpMV exchanges its halo
+// (the input is staged in an extended buffer `xe`), and every reduction -- ||b||, the batched
+// Gram-Schmidt dots, ||w||^2, the true residual -- is all-reduced between the kernel that forms the
+// local sums and the one that consumes them.  All ranks take identical decisions.
+static int gmres_solve_impl(psb_csr* A, psb_dist* D, psb_prec_t prec, const double* d_b, double* d_x,
+                            void* d_work, int64_t work_bytes, int32_t maxiter, double tau, int32_t orth,
+                            double* d_hist, psb_solve_result* result, cudaStream_t st) {
+  const int64_t n = D ? dist_n_loc(D) : A->n_rows, m = maxiter;
   const bool has_prec = prec != nullptr;
-  PSB_REQUIRE(!has_prec || prec->n == n, PSB_ERR_ARG, "psb_gmres_solve: preconditioner size mismatch");
-  PSB_REQUIRE(work_bytes >= psb_gmres_workspace_bytes(n, maxiter), PSB_ERR_ARG, "psb_gmres_solve: workspace too small");
-  PSB_REQUIRE(aligned16(d_b) && aligned16(d_x) && ((uintptr_t)d_work & 255u) == 0, PSB_ERR_ARG,
-              "psb_gmres_solve: b, x must be 16-byte and work 256-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
+  psb_comm* comm = D ? dist_comm(D) : nullptr;
   int rc = t_gpoll.init();
   if (rc != PSB_OK) return rc;
 
   GmresWork w = carve(d_work, n, m);
+  double* xe = nullptr;                           // extended SpMV input (row-partitioned only)
+  if (D) xe = (double*)((char*)d_work + psb_gmres_workspace_bytes(n, maxiter));
+  (void)work_bytes;
   const int64_t small_total = 4096 + reduce_bytes() + small_bytes(m);
   PSB_CUDA(cudaMemsetAsync(d_work, 0, small_total, st));
   GmresState h0;
@@ -399,7 +413,17 @@ extern "C" int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, 
   PSB_CUDA(cudaMemcpyAsync(w.st, &h0, sizeof(h0), cudaMemcpyHostToDevice, st));
   PSB_CUDA(cudaStreamSynchronize(st));
 
+  auto allreduce = [&](double* buf, int count) -> int { return comm ? dist_allreduce(comm, buf, count, st) : PSB_OK; };
   const int grid = stream_grid(n, w.rb.max_grid);
+  // y = A x (x: n owned entries, not extended) with an SpMV epilogue
+  auto matvec = [&](Epi epi, const double* x, double* y, const EpiArgs& ea, const int* skip) -> int {
+    if (!D) return spmv_launch(A, epi, x, y, ea, skip, st);
+    if (x != xe) {
+      gmres_copy_kernel<<<grid, kBlock, 0, st>>>(w.st, n, x, xe, skip != nullptr ? 1 : 0);
+      PSB_LAUNCH_CHECK();
+    }
+    return dist_spmv_epi(D, epi, xe, y, ea, skip, st);
+  };
   // The basis kernels run as exactly ONE wave of resident CTAs (grid-stride inside): with the
   // generic 8 CTAs per SM and 3 - 5 resident ones the second wave left 40 % of the slots empty
   // (ncu: 53 % of the DRAM peak, profiles/round1h_gmres.md).
@@ -418,6 +442,10 @@ extern "C" int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, 
   const int grid_mgs = one_wave((const void*)gmres_mgs_kernel, &wave_mgs);
   gmres_init_kernel<<<grid, kBlock, 0, st>>>(w.st, w.sm, n, d_b, w.rb);
   PSB_LAUNCH_CHECK();
+  rc = allreduce(&w.st->tmp_dot, 1);
+  if (rc != PSB_OK) return rc;
+  gmres_init_finish_kernel<<<1, 32, 0, st>>>(w.st, w.sm);
+  PSB_LAUNCH_CHECK();
   // q_0 = b / beta   (GMRESSolver.py:90-91); harmless when b == 0 (result unused)
   gmres_scale_kernel<<<grid, kBlock, 0, st>>>(w.st, n, d_b, &w.st->beta, w.Q, 1);
   PSB_LAUNCH_CHECK();
@@ -429,16 +457,19 @@ extern "C" int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, 
     const double* qk = w.Q + (int64_t)k * w.ldq;
     const double* zin = qk;
     if (has_prec) {                                              // z = M^-1 q_k   (:107)
-      rc = prec->apply(qk, w.z, &w.st->done, st);
+      double* zout = D ? xe : w.z;                               // straight into the extended buffer
+      rc = prec->apply(qk, zout, &w.st->done, st);
       if (rc != PSB_OK) return rc;
-      zin = w.z;
+      zin = zout;
     }
-    rc = spmv_launch(A, EPI_STORE, zin, w.w, EpiArgs(), &w.st->done, st);   // w = A z
+    rc = matvec(EPI_STORE, zin, w.w, EpiArgs(), &w.st->done);    // w = A z
     if (rc != PSB_OK) return rc;
     if (orth == PSB_ORTH_MGS) {
       for (int j = 0; j <= k + 1; ++j) {
         gmres_mgs_kernel<<<grid_mgs, kBlock, 0, st>>>(w.st, w.sm, n, w.Q, w.ldq, w.w, j, k, w.rb);
         PSB_LAUNCH_CHECK();
+        rc = allreduce(j == k + 1 ? &w.st->ww : w.sm.hcol + j, 1);
+        if (rc != PSB_OK) return rc;
       }
     } else {
       for (int round = 0; round < 2; ++round) {
@@ -448,6 +479,8 @@ extern "C" int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, 
           gmres_multidot_kernel<<<grid_dot, kBlock, 0, st>>>(w.st, n, w.Q, w.ldq, w.w, j0, cnt, hout, w.rb);
           PSB_LAUNCH_CHECK();
         }
+        rc = allreduce(hout, k + 1);
+        if (rc != PSB_OK) return rc;
         for (int j0 = 0; j0 <= k; j0 += kCh) {
           const int cnt = std::min(kCh, k + 1 - j0);
           const int want_norm = (round == 1 && j0 + kCh > k) ? 1 : 0;
@@ -456,6 +489,8 @@ extern "C" int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, 
           PSB_LAUNCH_CHECK();
         }
       }
+      rc = allreduce(&w.st->ww, 1);
+      if (rc != PSB_OK) return rc;
     }
     gmres_givens_kernel<<<1, 32, 0, st>>>(w.st, w.sm, d_hist, orth == PSB_ORTH_CGS2 ? 1 : 0);
     PSB_LAUNCH_CHECK();
@@ -467,7 +502,7 @@ extern "C" int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, 
     PSB_CUDA(cudaEventRecord(t_gpoll.ev[slot], st));
     pending[slot] = true;
     const int prev = slot ^ 1;
-    if (pending[prev]) {
+    if (pending[prev]) {            // the same logical point on every rank -> the same decision
       PSB_CUDA(cudaEventSynchronize(t_gpoll.ev[prev]));
       pending[prev] = false;
       if (t_gpoll.pinned[prev].done) finished = true;
@@ -502,9 +537,13 @@ extern "C" int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, 
     if (rc != PSB_OK) return rc;
   }
   EpiArgs ea; ea.f = d_b;
-  rc = spmv_launch(A, EPI_RESID, d_x, w.w, ea, nullptr, st);               // r = b - A x
+  rc = matvec(EPI_RESID, d_x, w.w, ea, nullptr);                          // r = b - A x
   if (rc != PSB_OK) return rc;
   gmres_norm_kernel<<<grid, kBlock, 0, st>>>(w.st, n, w.w, w.rb);
+  PSB_LAUNCH_CHECK();
+  rc = allreduce(&w.st->tmp_dot, 1);
+  if (rc != PSB_OK) return rc;
+  gmres_norm_finish_kernel<<<1, 32, 0, st>>>(w.st);
   PSB_LAUNCH_CHECK();
   PSB_CUDA(cudaStreamSynchronize(st));
   PSB_CUDA(cudaMemcpy(&hs, w.st, sizeof(hs), cudaMemcpyDeviceToHost));
@@ -516,4 +555,46 @@ extern "C" int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, 
     return PSB_ERR_CUDA;
   }
   return PSB_OK;
+}
+
+extern "C" int psb_gmres_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, double* d_x,
+                               void* d_work, int64_t work_bytes, int32_t maxiter, double tau,
+                               int32_t fail_on_maxiter, int32_t orth, double* d_hist,
+                               psb_solve_result* result, void* stream) {
+  (void)fail_on_maxiter;
+  PSB_REQUIRE(A && d_b && d_x && d_work && d_hist && result, PSB_ERR_ARG, "psb_gmres_solve: NULL argument");
+  PSB_REQUIRE(A->n_rows == A->n_cols, PSB_ERR_ARG, "psb_gmres_solve: matrix must be square");
+  PSB_REQUIRE(maxiter >= 1, PSB_ERR_ARG, "psb_gmres_solve: maxiter must be >= 1");
+  PSB_REQUIRE(orth == PSB_ORTH_CGS2 || orth == PSB_ORTH_MGS, PSB_ERR_ARG, "psb_gmres_solve: unknown orth mode");
+  PSB_REQUIRE(!prec || prec->n == A->n_rows, PSB_ERR_ARG, "psb_gmres_solve: preconditioner size mismatch");
+  PSB_REQUIRE(work_bytes >= psb_gmres_workspace_bytes(A->n_rows, maxiter), PSB_ERR_ARG, "psb_gmres_solve: workspace too small");
+  PSB_REQUIRE(aligned16(d_b) && aligned16(d_x) && ((uintptr_t)d_work & 255u) == 0, PSB_ERR_ARG,
+              "psb_gmres_solve: b, x must be 16-byte and work 256-byte aligned");
+  return gmres_solve_impl(A, nullptr, prec, d_b, d_x, d_work, work_bytes, maxiter, tau, orth, d_hist, result,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int64_t psb_dist_gmres_workspace_bytes(int64_t n_loc, int64_t n_halo, int32_t maxiter) {
+  if (n_loc < 0 || n_halo < 0 || maxiter < 1) return PSB_ERR_ARG;
+  return psb_gmres_workspace_bytes(n_loc, maxiter) + align_up((n_loc + n_halo + 32) * (int64_t)sizeof(double), 256);
+}
+
+// GMRES on a row-partitioned system: same loop, result codes and history as
+// psb_gmres_solve; `prec` (nullable) must act on this rank's slices (e.g. psb_dist_amg_create).
+extern "C" int psb_dist_gmres_solve(psb_dist_t D, psb_prec_t prec, const double* d_b_loc, double* d_x_loc,
+                                    void* d_work, int64_t work_bytes, int32_t maxiter, double tau,
+                                    int32_t fail_on_maxiter, int32_t orth, double* d_hist,
+                                    psb_solve_result* result, void* stream) {
+  (void)fail_on_maxiter;
+  PSB_REQUIRE(D && d_b_loc && d_x_loc && d_work && d_hist && result, PSB_ERR_ARG, "psb_dist_gmres_solve: NULL argument");
+  PSB_REQUIRE(dist_n_own(D) == dist_n_loc(D), PSB_ERR_ARG, "psb_dist_gmres_solve: operator must be square");
+  PSB_REQUIRE(maxiter >= 1, PSB_ERR_ARG, "psb_dist_gmres_solve: maxiter must be >= 1");
+  PSB_REQUIRE(orth == PSB_ORTH_CGS2 || orth == PSB_ORTH_MGS, PSB_ERR_ARG, "psb_dist_gmres_solve: unknown orth mode");
+  PSB_REQUIRE(!prec || prec->n == dist_n_loc(D), PSB_ERR_ARG, "psb_dist_gmres_solve: preconditioner size mismatch");
+  PSB_REQUIRE(work_bytes >= psb_dist_gmres_workspace_bytes(dist_n_loc(D), dist_n_halo(D), maxiter), PSB_ERR_ARG,
+              "psb_dist_gmres_solve: workspace too small");
+  PSB_REQUIRE(aligned16(d_b_loc) && aligned16(d_x_loc) && ((uintptr_t)d_work & 255u) == 0, PSB_ERR_ARG,
+              "psb_dist_gmres_solve: b, x must be 16-byte and work 256-byte aligned");
+  return gmres_solve_impl(nullptr, D, prec, d_b_loc, d_x_loc, d_work, work_bytes, maxiter, tau, orth, d_hist,
+                          result, (cudaStream_t)stream);
 }

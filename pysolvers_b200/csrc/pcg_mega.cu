@@ -47,6 +47,8 @@ __device__ __forceinline__ unsigned long long mega_now() {
   return t;
 }
 
+__device__ __forceinline__ double mega_sum_partials(const double* partials, int count, double* scratch);
+
 // Grid-wide (and rank-wide) sum of `v`.  Every thread of every CTA calls it; all return the same
 // bits.  `pushed`: this thread stored halo data into a neighbour's memory since the last raise
 // (it orders those stores system-wide before its CTA takes the ticket).  `raise`: the last CTA
@@ -63,13 +65,10 @@ __device__ __forceinline__ double mega_allreduce(const MegaParams& P, double v, 
   if (threadIdx.x == 0) P.partials[blockIdx.x] = t;
   if (pushed) __threadfence_system();
   const size_t ring = (size_t)(epoch % kRing) * kMaxRanks * 2;
-  if (last_block(P.ticket)) {
-    const double s = sum_partials(P.partials, gridDim.x, scratch);
+  const bool last = last_block(P.ticket);
+  if (last) {
+    const double s = mega_sum_partials(P.partials, gridDim.x, scratch);
     if ((int)threadIdx.x < P.nranks) peer_push(push_base + ring, s, epoch);
-    if (raise && (int)threadIdx.x < P.n_push) {
-      __threadfence_system();
-      asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(P.push_flag[threadIdx.x]), "l"(halo_epoch) : "memory");
-    }
   }
   if (threadIdx.x < 32) {                       // one lane per rank polls, then a fixed-order sum
     double mine = 0.0;
@@ -80,10 +79,32 @@ __device__ __forceinline__ double mega_allreduce(const MegaParams& P, double v, 
     const bool all_good = __all_sync(0xffffffffu, good);
     if (threadIdx.x == 0) { s_sum = s; s_ok = all_good ? 1 : 0; if (!all_good) *P.error = 1; }
   }
+  // The halo flags are raised AFTER the poll: the neighbour needs them only when it reaches its
+  // first boundary tile (its last tiles), and by now this thread's scalar push has landed, so the
+  // system fence has nothing remote left to wait for (before the poll it cost 3 - 4 us of the last
+  // CTA's -- i.e. the critical -- path, profiles/round2_mega_timeline.md).
+  if (last && raise && (int)threadIdx.x < P.n_push) {
+    __threadfence_system();
+    asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(P.push_flag[threadIdx.x]), "l"(halo_epoch) : "memory");
+  }
   __syncthreads();
   __threadfence();                              // acquire; invalidates L1 (weak loads below see fresh data)
   *ok = s_ok != 0;
   return s_sum;
+}
+
+// Per-CTA partials summed in a fixed order by the last CTA: up to 4 per thread, all four loads in
+// flight at once (the generic sum_partials loop issues them one dependent trip at a time).
+__device__ __forceinline__ double mega_sum_partials(const double* partials, int count, double* scratch) {
+  double v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = threadIdx.x + j * kBlock;
+    v[j] = i < count ? ld_cg(partials + i) : 0.0;
+  }
+  double a = ((v[0] + v[1]) + v[2]) + v[3];
+  for (int i = threadIdx.x + 4 * kBlock; i < count; i += kBlock) a += ld_cg(partials + i);
+  return block_sum(a, scratch);
 }
 
 __device__ __forceinline__ double mega_ld(const double* p) {       // coherent, no L1 allocation
@@ -129,7 +150,9 @@ pcg_mega_kernel(const MegaParams P) {
     const int t = lt < n_int ? rot_t0 + lt : (lt < rot_t1 ? lt - n_int : lt);
     return t * R + tid;                              // this thread's row of the tile
   };
-  auto row_ok = [&](int lt, int row) -> bool { return lt < n_tiles && tid < R && row < n; };
+  auto row_ok = [&](int lt, int row) -> bool { return lt >= 0 && lt < n_tiles && tid < R && row < n; };
+  // this CTA's last logical tile (-1: none)
+  const int lt_last = (int)blockIdx.x < n_tiles ? (int)blockIdx.x + ((n_tiles - 1 - (int)blockIdx.x) / gstep) * gstep : -1;
   const bool leader = blockIdx.x == 0 && tid == 0;
   unsigned int e = P.epoch0;
   const unsigned long long h0 = P.halo_epoch0;
@@ -166,7 +189,7 @@ pcg_mega_kernel(const MegaParams P) {
     }
   }
   for (int i = blockIdx.x * kBlock + tid; i < (int)P.n_halo; i += gstep * kBlock) P.pbuf[1][n + i] = 0.0;
-  bulk_prime<1, C16>(P.A, ea, pipe);
+  if (!(P.dbg_flags & 1)) bulk_prime<1, C16>(P.A, ea, pipe);
   const double bb = mega_allreduce(P, acc, e++, scratch, pushed, true, h0, push_base, &ok);
   const double norm_b = sqrt(bb);
   int status = PSB_MAXITER, k_final = 0, n_hist = 0;
@@ -192,14 +215,16 @@ pcg_mega_kernel(const MegaParams P) {
       acc = 0.0;
       bulk_pass<EPI_DOT_PUP, 1, C16, G>(P.A, P.r, P.Ap, ea, beta, pipe, acc);
       stamp(it, 1);
-      // first phase-B rows: r and this thread's own Ap are final -> loads in flight across the barrier
+      // first phase-B rows: r and this thread's own Ap are final -> loads in flight across the barrier.
+      // Phase B walks the CTA's tiles LAST to first: the boundary tiles (the last logical ones) come
+      // first, so their peer stores of r have long landed when the CTA fences before the ticket.
       double rv[kMegaUnroll], av[kMegaUnroll];
 #pragma unroll
       for (int u = 0; u < kMegaUnroll; ++u) {
-        const int lt = blockIdx.x + u * gstep;
+        const int lt = lt_last - u * gstep;
         const int row = tile_row(lt);
         rv[u] = 0.0; av[u] = 0.0;
-        if (row_ok(lt, row)) { rv[u] = mega_ld(P.r + row); av[u] = mega_ld(P.Ap + row); }
+        if (!(P.dbg_flags & 2) && row_ok(lt, row)) { rv[u] = mega_ld(P.r + row); av[u] = mega_ld(P.Ap + row); }
       }
       const double pAp = mega_allreduce(P, acc, e++, scratch, false, false, 0ull, push_base, &ok);
       stamp(it, 2);
@@ -209,18 +234,18 @@ pcg_mega_kernel(const MegaParams P) {
       // ---------------- phase B: r -= alpha Ap ; r.r  (x += alpha p is deferred to the next phase A)
       acc = 0.0;
       pushed = false;
-      for (int base = blockIdx.x; base < n_tiles; base += kMegaUnroll * gstep) {
-        if (base != blockIdx.x) {
+      for (int base = lt_last; base >= 0; base -= kMegaUnroll * gstep) {
+        if (base != lt_last || (P.dbg_flags & 2)) {
 #pragma unroll
           for (int u = 0; u < kMegaUnroll; ++u) {
-            const int lt = base + u * gstep;
+            const int lt = base - u * gstep;
             const int row = tile_row(lt);
             if (row_ok(lt, row)) { rv[u] = mega_ld(P.r + row); av[u] = mega_ld(P.Ap + row); }
           }
         }
 #pragma unroll
         for (int u = 0; u < kMegaUnroll; ++u) {
-          const int lt = base + u * gstep;
+          const int lt = base - u * gstep;
           const int row = tile_row(lt);
           if (row_ok(lt, row)) {
             const double rn = rv[u] - alpha * av[u];                               // :122
@@ -231,7 +256,7 @@ pcg_mega_kernel(const MegaParams P) {
         }
       }
       stamp(it, 3);
-      bulk_prime<1, C16>(P.A, ea, pipe);              // first tile of the next phase A: copies in flight
+      if (!(P.dbg_flags & 1)) bulk_prime<1, C16>(P.A, ea, pipe);   // first tile of the next phase A: copies in flight
       const double rr = mega_allreduce(P, acc, e++, scratch, pushed, true, h0 + (unsigned long long)it + 1ull,
                                        push_base, &ok);
       stamp(it, 4);
@@ -330,6 +355,7 @@ static int mega_launch_t(MegaParams& P, psb_csr* A, cudaStream_t stream) {
     if (t1 > t0) { P.rot_t0 = t0; P.rot_t1 = t1; }
   }
   P.timeline = g_timeline; P.tl_first = g_tl_first; P.tl_count = g_tl_count;
+  { static int flags = -1; if (flags < 0) { const char* e = getenv("PSB_MEGA_FLAGS"); flags = e ? atoi(e) : 0; } P.dbg_flags = flags; }
   const long long grid = std::max<long long>(1, std::min<long long>(grid_max, tiles));
   void* args[] = {(void*)&P};
   PSB_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_mega_kernel<MINB, C16, G>, dim3((unsigned)grid), dim3(kBlock),

@@ -144,8 +144,8 @@ struct SplitLuPrec : psb_prec {
   const char* kind() const override { return "splitlu"; }
   int check_error() override {
     int a = 0, b = 0;
-    if (L11) cudaMemcpy(&a, L11->d_error, sizeof(int), cudaMemcpyDeviceToHost);
-    if (U11) cudaMemcpy(&b, U11->d_error, sizeof(int), cudaMemcpyDeviceToHost);
+    a = trsv_take_error(L11);
+    b = trsv_take_error(U11);
     return a | b;
   }
   int apply(const double* r, double* z, const int* d_skip, cudaStream_t st) override {

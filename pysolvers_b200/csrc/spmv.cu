@@ -100,6 +100,10 @@ __device__ __forceinline__ void finish_dot(double acc, const psb_csr A, const Ep
   if (last_block(A.ticket)) {
     double total = sum_partials(A.partials, gridDim.x, scratch);
     if (EPI == EPI_RESID_NORM) {               // end of a V-cycle (VCycleSolver.py:87-91)
+      if (threadIdx.x == 0 && ea.amg_state == nullptr && ea.dot != nullptr) {
+        // row-partitioned: only this rank's part of ||r||^2; the cycle is finished after the all-reduce
+        *ea.dot = ea.dot_accumulate ? *ea.dot + total : total;
+      }
       if (threadIdx.x == 0 && ea.amg_state != nullptr) {
         AmgState* st = ea.amg_state;
         const double nr = sqrt(total);

@@ -91,6 +91,23 @@ struct EpiArgs {
 int spmv_launch(const psb_csr* A, Epi epi, const double* x, double* y,
                 const EpiArgs& ea, const int* d_skip, cudaStream_t stream);
 
+}  // namespace psb
+
+// ---- row-partitioned operators (dist.cu); opaque here -----------------------------------------
+struct psb_dist;
+struct psb_comm;
+namespace psb {
+int dist_spmv_epi(psb_dist* D, Epi epi, double* d_x_ext, double* d_y, const EpiArgs& ea, const int* d_skip,
+                  cudaStream_t st);
+int dist_allreduce(psb_comm* c, double* d_buf, int count, cudaStream_t st);
+int dist_allgather_slices(psb_comm* c, double* d_full, const int64_t* starts, cudaStream_t st);
+int dist_rank(const psb_comm* c);
+int dist_nranks(const psb_comm* c);
+int64_t dist_n_loc(const psb_dist* D);
+int64_t dist_n_own(const psb_dist* D);
+int64_t dist_n_halo(const psb_dist* D);
+psb_comm* dist_comm(const psb_dist* D);
+
 // View of rows [r0, r1) of A (r0 a multiple of 4 keeps the bulk copies aligned).  Shares
 // the parent's arrays and reduction scratch; y, f, dinv and x[row] stay indexed by the
 // parent's row numbers.

@@ -167,7 +167,11 @@ trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
           }
           if (c0 < 0) fed = true;
         } else if (++spins > kSpinLimit) {
+          // a dependency never became ready: raise the flag AND poison the row with an ordinary
+          // quiet NaN (not the sentinel, so consumers do not wait for it in turn) -- the
+          // failure is then visible in the result itself
           *T.error = 1; fed = true;
+          acc = __longlong_as_double(0x7ff8000000000000ll);
         }
       }
       // warps whose dependencies are still levels away back off instead of hammering L2
@@ -273,9 +277,7 @@ struct IcPrec : psb_prec {
   ~IcPrec() override { cudaFree(tmp); }
   const char* kind() const override { return "ic"; }
   int check_error() override {
-    int a = 0, b = 0;
-    cudaMemcpy(&a, L->d_error, sizeof(int), cudaMemcpyDeviceToHost);
-    cudaMemcpy(&b, Lt->d_error, sizeof(int), cudaMemcpyDeviceToHost);
+    const int a = trsv_take_error(L), b = trsv_take_error(Lt);
     return a | b;
   }
   int apply(const double* r, double* z, const int* d_skip, cudaStream_t st) override {
@@ -297,9 +299,7 @@ struct IluPrec : psb_prec {
   ~IluPrec() override { cudaFree(iperm_r); cudaFree(iperm_c); cudaFree(tmp1); cudaFree(tmp2); }
   const char* kind() const override { return "ilu"; }
   int check_error() override {
-    int a = 0, b = 0;
-    cudaMemcpy(&a, L->d_error, sizeof(int), cudaMemcpyDeviceToHost);
-    cudaMemcpy(&b, U->d_error, sizeof(int), cudaMemcpyDeviceToHost);
+    const int a = trsv_take_error(L), b = trsv_take_error(U);
     return a | b;
   }
   int apply(const double* r, double* z, const int* d_skip, cudaStream_t st) override {
@@ -575,9 +575,7 @@ extern "C" int psb_trsv_solve(psb_trsv_t T, const double* d_b, double* d_x, void
 
 extern "C" int psb_trsv_error(psb_trsv_t T, int32_t* h_flag) {
   PSB_REQUIRE(T && h_flag, PSB_ERR_ARG, "psb_trsv_error: NULL argument");
-  int v = 0;
-  PSB_CUDA(cudaMemcpy(&v, T->d_error, sizeof(int), cudaMemcpyDeviceToHost));
-  *h_flag = v;
+  *h_flag = trsv_take_error(T);            // reported once, then cleared
   return PSB_OK;
 }
 

@@ -62,4 +62,14 @@ int trsv_solve(const psb_trsv* T, const double* rhs, double* x, const int32_t* r
 int trsv_solve_cta(const psb_trsv* T, int cluster, const double* rhs, double* x, const int32_t* rhs_map,
                    double* out2, const int32_t* out_map, const int* d_skip, cudaStream_t st);
 
+// Reads a factor's device error flag (synchronising) and clears it once it has been reported,
+// so that one timed-out solve does not condemn every later use of the same factor.
+inline int trsv_take_error(const psb_trsv* T) {
+  int v = 0;
+  if (T == nullptr || T->d_error == nullptr) return 0;
+  if (cudaMemcpy(&v, T->d_error, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+  if (v != 0) cudaMemset(T->d_error, 0, sizeof(int));
+  return v;
+}
+
 }  // namespace psb

@@ -188,7 +188,7 @@ class DeviceTrsv:
                     max_dist=int(buf[3]), forced=int(buf[4]), stage_len=int(buf[5]), cluster_ok=bool(buf[6]))
 
     def set_kernel(self, kernel):
-        """'grid' (hand-over through L2), 'cta' (one CTA, shared-memory window), 'cluster' (8 CTAs,
+        """'grid' (hand-over through L2), 'cta' (one CTA, shared-memory window), 'cluster' (4 CTAs,
         window replicated through distributed shared memory) or None (analysis)."""
         k = {'grid': 0, 'cta': 1, 'cluster': 2, None: -1}[kernel]
         nat.check(nat.lib().psb_trsv_set_kernel(self._h, k), 'psb_trsv_set_kernel')

@@ -37,15 +37,19 @@ def row_starts(n, nranks):
 
 
 def localize(indptr, indices, lo, hi, starts):
-    """Renumber the columns of the row block [lo, hi) and list its halo.
+    """Renumber the columns of a row block and list its halo.
 
     ``indptr`` / ``indices`` are torch tensors (CPU or CUDA) of the block with
-    GLOBAL column ids.  Returns dict(local_indices int32, recv int64 (sorted
+    GLOBAL column ids; ``[lo, hi)`` is the range of column ids (entries of the
+    operator's INPUT vector) this rank owns and ``starts`` the partition of that
+    vector -- for a square operator the block's own row range and the row
+    partition.  Returns dict(local_indices int32, recv int64 (sorted
     global ids), recv_owner int64, r0, r1) with [r0, r1) the largest
     TILE-aligned row range around the middle whose rows touch no halo column.
     """
     dev = indices.device
     n_loc = int(hi - lo)
+    n_rows = int(indptr.numel()) - 1
     cols = indices.to(torch.int64)
     off = (cols < lo) | (cols >= hi)
     recv = torch.unique(cols[off])                      # sorted ascending
@@ -59,13 +63,13 @@ def localize(indptr, indices, lo, hi, starts):
     ip = indptr.to(torch.int64)
     per_row = csum[ip[1:]] - csum[ip[:-1]]
     touched = torch.nonzero(per_row > 0).flatten()
-    mid = n_loc // 2
+    mid = n_rows // 2
     low = touched[touched < mid]
     high = touched[touched >= mid]
     r0 = int(low.max().item()) + 1 if low.numel() else 0
-    r1 = int(high.min().item()) if high.numel() else n_loc
+    r1 = int(high.min().item()) if high.numel() else n_rows
     r0 = -(-r0 // TILE) * TILE
-    if r1 != n_loc:
+    if r1 != n_rows:
         r1 = (r1 // TILE) * TILE
     if r0 >= r1:
         r0 = r1 = 0                                       # no overlap window: all rows wait
@@ -137,7 +141,7 @@ class _DistPlan:
     its NCCL plan and NVLink peer-memory mappings.  Built collectively once per structure and
     kept on the communicator; a later DistCSR with the same structure only uploads values."""
 
-    def __init__(self, comm, ip, ix, data, lo, hi, n, mark):
+    def __init__(self, comm, ip, ix, data, lo, hi, n, mark, n_cols=None, p2p=True):
         import torch.distributed as dist
         self.comm = comm
         self.in_use = False
@@ -145,9 +149,15 @@ class _DistPlan:
         self.n_loc = self.hi - self.lo
         self.starts = row_starts(n, comm.world)
         assert self.starts[comm.rank] == self.lo and self.starts[comm.rank + 1] == self.hi
+        # partition of the INPUT vector: the row partition for a square operator
+        self.n_cols = int(n if n_cols is None else n_cols)
+        self.col_starts = self.starts if self.n_cols == self.n else row_starts(self.n_cols, comm.world)
+        self.clo, self.chi = int(self.col_starts[comm.rank]), int(self.col_starts[comm.rank + 1])
+        self.n_own = self.chi - self.clo
+        self.want_p2p = bool(p2p) and self.n_cols == self.n
         dev = ix.device
         self.ip_global, self.ix_global = ip, ix
-        loc = localize(ip, ix, self.lo, self.hi, self.starts)
+        loc = localize(ip, ix, self.clo, self.chi, self.col_starts)
         mark('localize (halo lists)')
         self.recv = loc['recv'].cpu().numpy()
         self.recv_owner = loc['recv_owner'].cpu().numpy()
@@ -155,10 +165,10 @@ class _DistPlan:
         self.r0, self.r1 = loc['r0'], loc['r1']
         gathered = [None] * comm.world
         dist.all_gather_object(gathered, (self.recv, self.recv_owner))
-        self.send = send_lists(comm.rank, self.lo, gathered)
+        self.send = send_lists(comm.rank, self.clo, gathered)
         mark('all_gather halo lists')
         self.A = DeviceCSR(indptr=ip.to(torch.int32), indices=loc['local_indices'], data=data,
-                           shape=(self.n_loc, self.n_loc + self.n_halo))
+                           shape=(self.n_loc, self.n_own + self.n_halo))
         mark('csr_create')
         # peers: union of the ranks we send to / receive from
         peers = sorted(set(self.send) | set(int(o) for o in np.unique(self.recv_owner)))
@@ -193,7 +203,7 @@ class _DistPlan:
             'psb_dist_create')
         mark('psb_dist_create')
         self.p2p = False
-        if os.environ.get('PSB_DIST_MODE', 'p2p') != 'nccl':
+        if self.want_p2p and os.environ.get('PSB_DIST_MODE', 'p2p') != 'nccl':
             self._enable_p2p(gathered)
         mark('peer-memory mapping')
 
@@ -272,7 +282,7 @@ class DistCSR:
     solves does not rebuild its plan.
     """
 
-    def __init__(self, comm, indptr, indices, data, lo, hi, n):
+    def __init__(self, comm, indptr, indices, data, lo, hi, n, n_cols=None, p2p=True):
         import torch.distributed as dist
         import time as _time
         _timing = os.environ.get('PSB_DIST_TIMING', '0') == '1'
@@ -294,6 +304,8 @@ class DistCSR:
         plan = None
         for cand in reversed(comm._plans):
             if (not cand.in_use and cand.lo == int(lo) and cand.hi == int(hi) and cand.n == int(n)
+                    and cand.n_cols == int(n if n_cols is None else n_cols)
+                    and cand.want_p2p == (bool(p2p) and cand.n_cols == cand.n)
                     and cand.ix_global.shape == ix.shape and cand.ix_global.dtype == ix.dtype
                     and cand.ip_global.dtype == ip.dtype):
                 plan = cand
@@ -311,7 +323,7 @@ class DistCSR:
             _mark('plan cache hit: values copied')
         else:
             comm._evict(max(comm.max_plans - 1, 0))
-            plan = _DistPlan(comm, ip, ix, dt, lo, hi, n, _mark)
+            plan = _DistPlan(comm, ip, ix, dt, lo, hi, n, _mark, n_cols=n_cols, p2p=p2p)
             comm._plans.append(plan)
         plan.in_use = True
         self._plan = plan
@@ -322,6 +334,8 @@ class DistCSR:
     n = property(lambda self: self._plan.n)
     n_loc = property(lambda self: self._plan.n_loc)
     n_halo = property(lambda self: self._plan.n_halo)
+    n_own = property(lambda self: self._plan.n_own)
+    n_cols = property(lambda self: self._plan.n_cols)
     starts = property(lambda self: self._plan.starts)
     recv = property(lambda self: self._plan.recv)
     recv_owner = property(lambda self: self._plan.recv_owner)
@@ -337,8 +351,8 @@ class DistCSR:
 
     def matvec(self, x_loc):
         """y_loc = (A x)_loc for the distributed vector whose local slice is x_loc."""
-        ext = torch.zeros(self.n_loc + self.n_halo, dtype=torch.float64, device=x_loc.device)
-        ext[:self.n_loc] = x_loc
+        ext = torch.zeros(self.n_own + self.n_halo, dtype=torch.float64, device=x_loc.device)
+        ext[:self.n_own] = x_loc
         y = torch.empty(self.n_loc, dtype=torch.float64, device=x_loc.device)
         nat.check(nat.lib().psb_dist_spmv(self.handle, ptr(ext), ptr(y), current_stream_ptr()),
                   'psb_dist_spmv')

@@ -52,6 +52,37 @@ def test_partition_matches_oracle(nranks):
                 assert np.array_equal(mine[q], ref[r]['send'][q])
 
 
+@pytest.mark.parametrize('nranks', [2, 3, 8])
+def test_rectangular_partition_matches_oracle(nranks):
+    """Restriction / prolongation row blocks of the row-partitioned V-cycle: halo lists, local
+    renumbering and send lists bit-identical to oracle.partition.partition_rect."""
+    from pysolvers_b200.Linear import amg_setup
+    A = -fd_laplacian_2d(0.0, 1.0, 24)
+    ops, ups, downs = amg_setup.build_hierarchy(A, num_levels=2)
+    for M in (downs[0], ups[0]):
+        M = sp.csr_matrix(M)
+        ref = opart.partition_rect(M, nranks)
+        rs, cs = pdist.row_starts(M.shape[0], nranks), pdist.row_starts(M.shape[1], nranks)
+        recvs = []
+        for r in range(nranks):
+            blk = M[int(rs[r]):int(rs[r + 1]), :]
+            loc = pdist.localize(torch.from_numpy(blk.indptr.astype(np.int64)),
+                                 torch.from_numpy(blk.indices.astype(np.int64)), int(cs[r]), int(cs[r + 1]), cs)
+            assert np.array_equal(loc['local_indices'].numpy(), ref[r]['indices'])
+            assert np.array_equal(loc['recv'].numpy(), ref[r]['recv'])
+            assert np.array_equal(loc['recv_owner'].numpy(), ref[r]['recv_owner'])
+            nrows = blk.shape[0]
+            assert 0 <= loc['r0'] <= loc['r1'] <= nrows
+            _, halo_rows = opart.interior_boundary_rows(ref[r]['indptr'], ref[r]['indices'], int(cs[r + 1] - cs[r]))
+            assert not np.any((halo_rows >= loc['r0']) & (halo_rows < loc['r1']))
+            recvs.append((loc['recv'].numpy(), loc['recv_owner'].numpy()))
+        for r in range(nranks):
+            mine = pdist.send_lists(r, int(cs[r]), recvs)
+            assert sorted(mine) == sorted(ref[r]['send'])
+            for q in mine:
+                assert np.array_equal(mine[q], ref[r]['send'][q])
+
+
 def test_interior_window_is_found_for_slabs():
     A = fd_laplacian_3d(0.0, 1.0, 16)            # 4096 rows, 256-row planes
     starts = pdist.row_starts(A.shape[0], 2)

@@ -83,7 +83,7 @@ def test_trsv_edge_cases(cuda):
 
 def _both_kernels(T, lower, unit, v):
     """Solve with the grid-wide kernel (hand-over through L2), the one-CTA kernel (hand-over through
-    the shared-memory window) and, where the analysis allows it, the 8-CTA cluster kernel (window
+    the shared-memory window) and, where the analysis allows it, the 4-CTA cluster kernel (window
     replicated through distributed shared memory): the results must be the same bits."""
     from pysolvers_b200.device import DeviceTrsv, to_device
     dT = DeviceTrsv(T, lower=lower, unit_diag=unit)

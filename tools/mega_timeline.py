@@ -1,7 +1,7 @@
 """Per-CTA phase timeline of the persistent PCG kernel (psb_debug_mega_timeline).
 
-    python tools/mega_timeline.py [--m 1448] [--iters 200] [--first 100] [--count 8] [--out PREFIX]
-    python -m torch.distributed.run --nproc-per-node N ... tools/mega_timeline.py --m 4096
+    python tools/mega_timeline.py [--gridm 1448] [--iters 200] [--first 100] [--count 8] [--out PREFIX]
+    python -m torch.distributed.run --nproc-per-node N ... tools/mega_timeline.py --gridm 4096
 
 Records %globaltimer at the five phase boundaries of iterations [first, first+count) for every
 CTA (of every rank), prints where an iteration's time goes -- phase A work, wait at the p.Ap
@@ -28,7 +28,7 @@ from pysolvers_b200.problems import device_fd_laplacian  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--m', type=int, default=1448)
+    ap.add_argument('--gridm', dest='m', type=int, default=1448)
     ap.add_argument('--dim', type=int, default=2)
     ap.add_argument('--iters', type=int, default=200)
     ap.add_argument('--first', type=int, default=100)
