@@ -237,6 +237,69 @@ gmres_multiaxpy_kernel(GmresState* st, int64_t n, const double* __restrict__ Q, 
   }
 }
 
+// CGS2, last chunk of round 1 fused with the round-2 dots OF THE SAME CHUNK: w = w - sum_c h1_c q_c
+// is final after this chunk, so q_c . w (the round-2 coefficients of these <= 8 vectors) is formed
+// from the q values already in registers -- one pass over w and the chunk's basis vectors less
+// per iteration (all of round 2's dot pass while the Krylov dimension is <= 8).
+__global__ void __launch_bounds__(kBlock, 3)
+gmres_axpy_dot_kernel(GmresState* st, int64_t n, const double* __restrict__ Q, int64_t ldq,
+                      double* __restrict__ w, const double* coef, int j0, int cnt, double* dot_out,
+                      ReduceBuf rb) {
+  __shared__ double scratch[kWarps];
+  if (ld_cg(&st->done) != 0) return;
+  double h[kCh], acc[kCh];
+#pragma unroll
+  for (int c = 0; c < kCh; ++c) { h[c] = (c < cnt) ? -ld_cg(coef + j0 + c) : 0.0; acc[c] = 0.0; }
+  const double* q0 = Q + (int64_t)j0 * ldq;
+  const int64_t n2 = n >> 1;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n2; i += (int64_t)gridDim.x * kBlock) {
+    double2 wv = ld2rw(w + 2 * i);
+    double2 q[kCh];
+#pragma unroll
+    for (int c = 0; c < kCh; ++c)
+      if (c < cnt) q[c] = ld_stream2(q0 + (int64_t)c * ldq + 2 * i);
+#pragma unroll
+    for (int c = 0; c < kCh; ++c) {
+      if (c < cnt) {
+        wv.x = wv.x + h[c] * q[c].x;
+        wv.y = wv.y + h[c] * q[c].y;
+      }
+    }
+    st_stream2(w + 2 * i, wv);
+#pragma unroll
+    for (int c = 0; c < kCh; ++c) {
+      if (c < cnt) {
+        acc[c] += q[c].x * wv.x;
+        acc[c] += q[c].y * wv.y;
+      }
+    }
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t e = n - 1;
+    double wv = w[e];
+#pragma unroll
+    for (int c = 0; c < kCh; ++c)
+      if (c < cnt) wv = wv + h[c] * q0[(int64_t)c * ldq + e];
+    w[e] = wv;
+#pragma unroll
+    for (int c = 0; c < kCh; ++c)
+      if (c < cnt) acc[c] += q0[(int64_t)c * ldq + e] * wv;
+  }
+#pragma unroll
+  for (int c = 0; c < kCh; ++c) {
+    if (c < cnt) {
+      double t = block_sum(acc[c], scratch);
+      if (threadIdx.x == 0) rb.partials[(int64_t)c * gridDim.x + blockIdx.x] = t;
+    }
+  }
+  if (last_block(rb.ticket)) {
+    for (int c = 0; c < cnt; ++c) {
+      double s = sum_partials(rb.partials + (int64_t)c * gridDim.x, gridDim.x, scratch);
+      if (threadIdx.x == 0) dot_out[j0 + c] = s;
+    }
+  }
+}
+
 // One warp: finish column k of the Hessenberg matrix, rotate, test convergence.
 __global__ void gmres_givens_kernel(GmresState* st, GmresSmall sm, double* __restrict__ hist, int cgs2) {
   if (st->done != 0) return;
@@ -436,7 +499,9 @@ static int gmres_solve_impl(psb_csr* A, psb_dist* D, psb_prec_t prec, const doub
     const int64_t need = ((n >> 1) + kBlock - 1) / kBlock;
     return (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(*cache, need), w.rb.max_grid));
   };
-  static thread_local int wave_dot = 0, wave_axpy = 0, wave_mgs = 0;
+  static thread_local int wave_dot = 0, wave_axpy = 0, wave_mgs = 0, wave_fused = 0;
+  const int grid_fused = one_wave((const void*)gmres_axpy_dot_kernel, &wave_fused);
+  static const bool fuse_cgs2 = getenv("PSB_GMRES_NOFUSE") == nullptr;
   const int grid_dot = one_wave((const void*)gmres_multidot_kernel, &wave_dot);
   const int grid_axpy = one_wave((const void*)gmres_multiaxpy_kernel, &wave_axpy);
   const int grid_mgs = one_wave((const void*)gmres_mgs_kernel, &wave_mgs);
@@ -472,9 +537,11 @@ static int gmres_solve_impl(psb_csr* A, psb_dist* D, psb_prec_t prec, const doub
         if (rc != PSB_OK) return rc;
       }
     } else {
+      const int j_last = (k / kCh) * kCh;              // first vector of the last chunk
       for (int round = 0; round < 2; ++round) {
         double* hout = round == 0 ? w.sm.hcol : w.sm.hcol2;
         for (int j0 = 0; j0 <= k; j0 += kCh) {
+          if (round == 1 && fuse_cgs2 && j0 == j_last) continue;   // formed by the fused kernel below
           const int cnt = std::min(kCh, k + 1 - j0);
           gmres_multidot_kernel<<<grid_dot, kBlock, 0, st>>>(w.st, n, w.Q, w.ldq, w.w, j0, cnt, hout, w.rb);
           PSB_LAUNCH_CHECK();
@@ -483,6 +550,13 @@ static int gmres_solve_impl(psb_csr* A, psb_dist* D, psb_prec_t prec, const doub
         if (rc != PSB_OK) return rc;
         for (int j0 = 0; j0 <= k; j0 += kCh) {
           const int cnt = std::min(kCh, k + 1 - j0);
+          if (round == 0 && fuse_cgs2 && j0 == j_last) {
+            // last axpy chunk of round 1 + the round-2 dots of the same chunk in one pass
+            gmres_axpy_dot_kernel<<<grid_fused, kBlock, 0, st>>>(w.st, n, w.Q, w.ldq, w.w, hout, j0, cnt,
+                                                                w.sm.hcol2, w.rb);
+            PSB_LAUNCH_CHECK();
+            continue;
+          }
           const int want_norm = (round == 1 && j0 + kCh > k) ? 1 : 0;
           gmres_multiaxpy_kernel<<<grid_axpy, kBlock, 0, st>>>(w.st, n, w.Q, w.ldq, w.w, hout, j0, cnt, -1.0,
                                                           0, want_norm, 1, w.rb);

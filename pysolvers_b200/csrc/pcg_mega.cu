@@ -166,6 +166,7 @@ pcg_mega_kernel(const MegaParams P) {
   ea.pp_n = P.n_push;
 #pragma unroll
   for (int k = 0; k < kMaxPush; ++k) { ea.pp_off[k] = P.push_off[k]; ea.pp_cnt[k] = P.push_cnt[k]; }
+  ea.pp_skip_lo = P.nopush_lo; ea.pp_skip_hi = P.nopush_hi;
   ea.xsol = P.x;
   bulk_cache_bounds<1, C16>(P.A, ea, pipe);
 
@@ -184,7 +185,7 @@ pcg_mega_kernel(const MegaParams P) {
     if (row_ok(lt, row)) {
       const double v = P.b[row];
       P.r[row] = v; P.x[row] = 0.0; P.pbuf[1][row] = 0.0;
-      pushed |= mega_push_r(P, row, v);
+      if (P.n_push > 0 && (row < P.nopush_lo || row >= P.nopush_hi)) pushed |= mega_push_r(P, row, v);
       acc += v * v;
     }
   }
@@ -250,7 +251,7 @@ pcg_mega_kernel(const MegaParams P) {
           if (row_ok(lt, row)) {
             const double rn = rv[u] - alpha * av[u];                               // :122
             mega_st(P.r + row, rn);
-            if (P.n_push > 0) pushed |= mega_push_r(P, row, rn);
+            if (P.n_push > 0 && (row < P.nopush_lo || row >= P.nopush_hi)) pushed |= mega_push_r(P, row, rn);
             acc += rn * rn;
           }
         }
@@ -353,6 +354,19 @@ static int mega_launch_t(MegaParams& P, psb_csr* A, cudaStream_t stream) {
     const long long t0 = (P.int_r0 + R - 1) / R;
     const long long t1 = P.int_r1 >= P.n ? tiles : P.int_r1 / R;
     if (t1 > t0) { P.rot_t0 = t0; P.rot_t1 = t1; }
+  }
+  {   // largest row interval that intersects no push range (rows inside it skip the range tests)
+    long long best_lo = 0, best_hi = 0, cur = 0;
+    long long lo[kMaxPush], hi[kMaxPush];
+    int np = 0;
+    for (int k = 0; k < P.n_push; ++k) if (P.push_cnt[k] > 0) { lo[np] = P.push_off[k]; hi[np] = P.push_off[k] + P.push_cnt[k]; ++np; }
+    for (int a = 0; a < np; ++a) for (int b = a + 1; b < np; ++b) if (lo[b] < lo[a]) { std::swap(lo[a], lo[b]); std::swap(hi[a], hi[b]); }
+    for (int k = 0; k <= np; ++k) {
+      const long long gap_hi = k < np ? lo[k] : P.n;
+      if (gap_hi - cur > best_hi - best_lo) { best_lo = cur; best_hi = gap_hi; }
+      if (k < np) cur = std::max(cur, hi[k]);
+    }
+    P.nopush_lo = (int)best_lo; P.nopush_hi = (int)best_hi;
   }
   P.timeline = g_timeline; P.tl_first = g_tl_first; P.tl_count = g_tl_count;
   { static int flags = -1; if (flags < 0) { const char* e = getenv("PSB_MEGA_FLAGS"); flags = e ? atoi(e) : 0; } P.dbg_flags = flags; }

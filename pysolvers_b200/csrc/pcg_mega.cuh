@@ -53,6 +53,7 @@ struct MegaParams {
   int cap_v, cap_c;
   unsigned long long* timeline;                  // profiling (psb_debug_mega_timeline), nullable
   int tl_first, tl_count;
+  int nopush_lo, nopush_hi;                      // rows in [nopush_lo, nopush_hi) lie in no push range (cheap per-row test)
   int dbg_flags;                                 // PSB_MEGA_FLAGS: 1 no early tile staging, 2 no phase-B loads across the barrier
 };
 

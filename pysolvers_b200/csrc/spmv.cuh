@@ -70,6 +70,7 @@ struct EpiArgs {
   int pp_n = 0;
   long long pp_off[4] = {0, 0, 0, 0}, pp_cnt[4] = {0, 0, 0, 0};
   double* pp_remote[4] = {nullptr, nullptr, nullptr, nullptr};
+  int pp_skip_lo = 0, pp_skip_hi = 0;   // rows in [pp_skip_lo, pp_skip_hi) are in no push range: two compares per row
   // ---- multi-GPU over NVLink peer memory (dist.cu) ------------------------------------
   // once the dot is final, store it (epoch-tagged, see peer_push) into this rank's slot in
   // every rank's memory

@@ -409,10 +409,12 @@ __device__ __forceinline__ void bulk_pass(const psb_csr& A, const double* x, dou
           // (PCGSolver.py:121): p_{k-1} is in a register here anyway, so the update pass never
           // has to read p -- same operands, same rounding, 8 bytes per row less traffic
           if (ea.xsol != nullptr) ea.xsol[row] = xo + ea.alpha_prev * po;
+          if (ea.pp_n > 0 && (rabs < ea.pp_skip_lo || rabs >= ea.pp_skip_hi)) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)                 // boundary rows also go to the neighbours' halo
-            if (q < ea.pp_n && row >= ea.pp_off[q] && row < ea.pp_off[q] + ea.pp_cnt[q])
-              ea.pp_remote[q][row - ea.pp_off[q]] = pn;
+            for (int q = 0; q < 4; ++q)               // boundary rows also go to the neighbours' halo
+              if (q < ea.pp_n && row >= ea.pp_off[q] && row < ea.pp_off[q] + ea.pp_cnt[q])
+                ea.pp_remote[q][row - ea.pp_off[q]] = pn;
+          }
           acc += pn * sum;
         } else {
           epi_finish<EPI>(row, sum, own, y, ea, acc);

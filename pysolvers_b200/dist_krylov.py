@@ -188,7 +188,10 @@ class DistributedGMRESSolver(IterativeLinearSolver):
             if self.precond is None or not self.precFrozen():
                 if self.precond is not None and hasattr(self.precond, 'close'):
                     self.precond.close()
-                self.precond = ptype.form(A.global_matrix() if hasattr(A, 'global_matrix') else A)
+                if not hasattr(A, 'global_matrix'):
+                    raise TypeError('forming a preconditioner needs the global matrix: pass a '
+                                    'dist_krylov.DistOperator(dist_csr, global_matrix) instead of the bare DistCSR')
+                self.precond = ptype.form(A.global_matrix())
             prec_h = self.precond.right_device_handle()
         lib = nat.lib()
         maxiter = int(self.maxiter())
@@ -217,6 +220,20 @@ class DistributedGMRESSolver(IterativeLinearSolver):
                 msg='GMRES failure: true residual %12.5g did not meet tolerance '
                     'tau=%12.5g. Recursive residual was %12.5g.' % (res.norm_r, self.tau(), res.norm_r_rec))
         return self.handleMaxiter(res.k, x, res.norm_r_rec, res.norm_b)
+
+
+class DistOperator:
+    """A row block (dist.DistCSR) together with the global matrix it is a block of (host scipy CSR,
+    or a callable returning it): what DistributedGMRESSolver needs when it has to FORM a
+    preconditioner whose setup is global (the smoothed-aggregation hierarchy)."""
+
+    def __init__(self, dist_csr, global_matrix):
+        self.dist = dist_csr
+        self._global = global_matrix
+        self.shape = (dist_csr.n, dist_csr.n_cols)
+
+    def global_matrix(self):
+        return self._global() if callable(self._global) else self._global
 
 
 class _DistJacobian:

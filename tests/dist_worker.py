@@ -83,7 +83,7 @@ def check_gmres_amg(comm, rank, world, fails):
         gd = dk.DistributedGMRES(CommonSolverArgs(**ctl), precond=dk.DistAMG(comm, numIters=5, numLevels=nlev)).makeSolver()
         blk = J[lo:hi, :]
         D = pdist.DistCSR(comm, blk.indptr, blk.indices, blk.data, lo, hi, n, p2p=False)
-        sd = quiet(gd.solve, D, b[lo:hi])
+        sd = quiet(gd.solve, dk.DistOperator(D, J), b[lo:hi])
         if sd.iters() != s1.iters() or sd.success() != s1.success():
             fails.append('%s: GMRES+AMG iters %s vs %s' % (tag, sd.iters(), s1.iters()))
         if rel(gd.last_history, g1.last_history) > 1e-9:
@@ -138,8 +138,10 @@ def check_gmres_amg(comm, rank, world, fails):
     std = quiet(nd.solve, fd, fd.initialU())
     if std.success() != st1.success() or std.iters() != st1.iters() or lind != lin1:
         fails.append('newton: iters %s lin %s vs 1 GPU iters %s lin %s' % (std.iters(), lind, st1.iters(), lin1))
-    if rel(hd, h1) > 1e-6:
-        fails.append('newton: ||F|| history rel %.2e' % rel(hd, h1))
+    # ||F|| ends at the rounding floor of evaluating F (~1e-13 ||F_0||): compare down to that floor
+    ha, hb = np.asarray(hd), np.asarray(h1)
+    if ha.shape != hb.shape or np.any(np.abs(ha - hb) > 1e-8 * hb + 1e-11 * hb[0]):
+        fails.append('newton: ||F|| history differs %s vs %s' % (ha, hb))
     lo, hi = fd.lo, fd.hi
     u1 = st1.soln().cpu().numpy() if hasattr(st1.soln(), 'cpu') else st1.soln()
     if np.linalg.norm(std.soln().cpu().numpy() - u1[lo:hi]) > 1e-8 * np.linalg.norm(u1):

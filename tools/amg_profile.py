@@ -1,0 +1,76 @@
+"""AMG preconditioner application (configs[4]: Bratu Jacobian, 5 V-cycles, 2 levels, damped
+Jacobi) timed on the device, with a profiler range around ONE application:
+
+    python tools/amg_profile.py 2048                       # timings (CUDA events)
+    ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+        --log-file gpurun_out/amg_launches.csv python tools/amg_profile.py 2048 --profile
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from pysolvers_b200 import _native as nat  # noqa: E402
+from pysolvers_b200.Linear import AMG, DampedJacobiSmoother  # noqa: E402
+from pysolvers_b200.device import to_device  # noqa: E402
+from pysolvers_b200.problems import FDBratu2D  # noqa: E402
+
+
+def time_gpu(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
+def main():
+    m = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+    profile = '--profile' in sys.argv
+    func = FDBratu2D(m=m)
+    J = func.evalJ(func.initialU())
+    F = func.evalF(func.initialU())
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        pre = AMG(numIters=5, smoother=DampedJacobiSmoother).form(J)
+    setup = time.perf_counter() - t0
+    amg = pre.device_amg()
+    v = to_device(-F)
+    z = torch.empty_like(v)
+    if profile:
+        amg.prec.apply(v, z)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        amg.prec.apply(v, z)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return 0
+    l0 = nat.launch_count()
+    amg.prec.apply(v, z)
+    launches = nat.launch_count() - l0
+    out = {'m': m, 'levels': [a.shape[0] for a in amg.A], 'amg_setup_host_s': setup,
+           'apply_5_vcycles_ms': 1e3 * time_gpu(lambda: amg.prec.apply(v, z)), 'launches_per_apply': int(launches)}
+    cv = to_device(np.ones(amg.A[0].shape[0]))
+    cz = torch.empty_like(cv)
+    out['coarse_solve_ms'] = 1e3 * time_gpu(lambda: amg.coarse.apply(cv, cz))
+    out['coarse_levels_L11_U11'] = list(amg.coarse.levels())
+    out['coarse_dense_rows'] = amg.coarse.n2
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())
