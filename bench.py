@@ -493,6 +493,10 @@ def run_single_gpu(args):
     step_bytes = 32 * n + ITERS_PER_STEP * iter_bytes
     step_ms = dev_ms / args.steps
     step_gbs = step_bytes / (step_ms * 1e-3) / 1e9
+    # what the kernel really moves: x += alpha p is deferred into the next SpMV pass, so an iteration
+    # touches 72 n (not SURVEY's 88 n) vector bytes; + the final x flush (24 n)
+    moved_bytes = 32 * n + 24 * n + ITERS_PER_STEP * (12 * nnz + 4 * (n + 1) + 72 * n)
+    moved_gbs = moved_bytes / (step_ms * 1e-3) / 1e9
     del p_d, ap_d
 
     # ---- e2e: public API with host operands ---------------------------------------
@@ -561,7 +565,11 @@ def run_single_gpu(args):
                                 'state copy-back)' % ITERS_PER_STEP,
                       'achieved': step_gbs, 'peak': peak_gbs, 'unit': 'GB/s', 'frac': step_gbs / peak_gbs,
                       'traffic': ncu_traffic('pcg_mega_kernel'),
-                      'bytes_per_launch': step_bytes, 'ms_per_launch': step_ms, 'peak_source': peak_src}
+                      'bytes_per_launch': step_bytes, 'ms_per_launch': step_ms, 'peak_source': peak_src,
+                      'note': 'achieved = ALGORITHMIC bytes (SURVEY 8d: 12 nnz + 4(n+1) + 88 n per iteration) / time, so '
+                              'frac can exceed 1: the kernel moves fewer bytes than that count (72 n of vectors per '
+                              'iteration) -- see bytes_moved_per_launch / frac_moved for the traffic actually generated',
+                      'bytes_moved_per_launch': moved_bytes, 'moved_GBps': moved_gbs, 'frac_moved': moved_gbs / peak_gbs}
                      if mega else
                      {'bound': 'hbm', 'kernel': 'spmv_bulk_kernel<EPI_DOT> (A p fused with p.Ap)',
                       'achieved': spmv_gbs, 'peak': peak_gbs, 'unit': 'GB/s',

@@ -99,68 +99,82 @@ struct BlockDiag {
   int32_t* c_hi = nullptr;
   int64_t* off = nullptr;
   double* vals = nullptr;
-  void release() { cudaFree(row0); cudaFree(c_lo); cudaFree(c_hi); cudaFree(off); cudaFree(vals); n = 0; }
+  int32_t* long_rows = nullptr;    // rows of >= kLongRow entries (warp-per-row kernel)
+  int64_t n_long = 0;
+  void release() {
+    cudaFree(row0); cudaFree(c_lo); cudaFree(c_hi); cudaFree(off); cudaFree(vals); cudaFree(long_rows);
+    row0 = c_lo = c_hi = long_rows = nullptr; off = nullptr; vals = nullptr; n = 0; n_long = 0;
+  }
 };
 
 // y = blockdiag(B) x: row r of a collapsed supernode starting at line row0[r] reads x[row0 + c] for
-// c in [c_lo, c_hi) with the weights vals[off + c - c_lo]; rows outside a supernode copy.  Short
-// rows: one thread each, sequential sum.  Rows of >= 32 entries (the large supernodes near the top
-// of the elimination tree, up to thousands of lines) are done by the whole warp, one after the
-// other: coalesced 256-byte reads of the row, four in flight per lane, fixed-order reduction --
-// with a thread per row a few rows of 2 000 uncoalesced entries held the kernel for 120 us.
+// c in [c_lo, c_hi) with the weights vals[off + c - c_lo]; rows outside a supernode copy.
+// Two kernels: a thread per row for the short rows (sequential sum), and a WARP per row for the
+// rows of >= kLongRow entries (the large supernodes near the top of the elimination tree, hundreds
+// of lines: with a thread per row a few hundred uncoalesced entries held the stage for 120 us;
+// listed at set-up time, coalesced 256-byte reads, four in flight per lane, fixed-order reduction).
+constexpr int kLongRow = 32;
+
 __global__ void __launch_bounds__(kBlock)
 blockdiag_kernel(int64_t n, const int32_t* __restrict__ row0, const int32_t* __restrict__ c_lo,
                  const int32_t* __restrict__ c_hi, const int64_t* __restrict__ off,
                  const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
                  const int* d_skip) {
   if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
+  for (int64_t r = blockIdx.x * (int64_t)kBlock + threadIdx.x; r < n; r += (int64_t)gridDim.x * kBlock) {
+    const int lo = c_lo[r], hi = c_hi[r];
+    if (hi - lo >= kLongRow) continue;                   // blockdiag_long_kernel
+    if (hi <= lo) { y[r] = x[r]; continue; }
+    const double* xv = x + row0[r];
+    const double* w = vals + off[r];
+    double acc = 0.0;
+    for (int c = lo; c < hi; ++c) acc += w[c - lo] * xv[c];
+    y[r] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+blockdiag_long_kernel(int64_t n_long, const int32_t* __restrict__ long_rows, const int32_t* __restrict__ row0,
+                      const int32_t* __restrict__ c_lo, const int32_t* __restrict__ c_hi,
+                      const int64_t* __restrict__ off, const double* __restrict__ vals,
+                      const double* __restrict__ x, double* __restrict__ y, const int* d_skip) {
+  if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * kBlock) >> 5;
-  for (int64_t base = warp * 32; base < n; base += n_warps * 32) {
-    const int64_t r = base + lane;
-    const bool valid = r < n;
-    int lo = 0, hi = 0, r0 = 0;
-    long long o = 0;
-    if (valid) { lo = c_lo[r]; hi = c_hi[r]; r0 = row0[r]; o = off[r]; }
-    const int len = hi - lo;
-    const bool is_long = valid && len >= 32;
-    double res = 0.0;
-    if (valid && !is_long) {
-      if (len <= 0) res = x[r];
-      else {
-        const double* xv = x + r0;
-        const double* w = vals + o;
-        double acc = 0.0;
-        for (int c = lo; c < hi; ++c) acc += w[c - lo] * xv[c];
-        res = acc;
-      }
+  for (int64_t i = warp; i < n_long; i += n_warps) {
+    const int r = long_rows[i];
+    const int lo = c_lo[r], hi = c_hi[r];
+    const double* w = vals + off[r] - lo;
+    const double* xv = x + row0[r];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int c = lo + lane; c < hi; c += 128) {
+      const int c1 = c + 32, c2 = c + 64, c3 = c + 96;
+      const double w0 = w[c], x0 = xv[c];
+      const double w1 = c1 < hi ? w[c1] : 0.0, x1 = c1 < hi ? xv[c1] : 0.0;
+      const double w2 = c2 < hi ? w[c2] : 0.0, x2 = c2 < hi ? xv[c2] : 0.0;
+      const double w3 = c3 < hi ? w[c3] : 0.0, x3 = c3 < hi ? xv[c3] : 0.0;
+      a0 += w0 * x0; a1 += w1 * x1; a2 += w2 * x2; a3 += w3 * x3;
     }
-    unsigned m = __ballot_sync(0xffffffffu, is_long);
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      const int lo_s = __shfl_sync(0xffffffffu, lo, src), hi_s = __shfl_sync(0xffffffffu, hi, src);
-      const int r0_s = __shfl_sync(0xffffffffu, r0, src);
-      const long long o_s = __shfl_sync(0xffffffffu, o, src);
-      const double* w = vals + o_s - lo_s;
-      const double* xv = x + r0_s;
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      for (int c = lo_s + lane; c < hi_s; c += 128) {
-        const int c1 = c + 32, c2 = c + 64, c3 = c + 96;
-        const double w0 = w[c], x0 = xv[c];
-        const double w1 = c1 < hi_s ? w[c1] : 0.0, x1 = c1 < hi_s ? xv[c1] : 0.0;
-        const double w2 = c2 < hi_s ? w[c2] : 0.0, x2 = c2 < hi_s ? xv[c2] : 0.0;
-        const double w3 = c3 < hi_s ? w[c3] : 0.0, x3 = c3 < hi_s ? xv[c3] : 0.0;
-        a0 += w0 * x0; a1 += w1 * x1; a2 += w2 * x2; a3 += w3 * x3;
-      }
-      double a = (a0 + a1) + (a2 + a3);
+    double a = (a0 + a1) + (a2 + a3);
 #pragma unroll
-      for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
-      if (lane == src) res = a;
-    }
-    if (valid) y[r] = res;
+    for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+    if (lane == 0) y[r] = a;
   }
+}
+
+static int blockdiag_apply(const BlockDiag& B, int64_t n, const double* x, double* y, const int* d_skip,
+                           cudaStream_t st) {
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + kBlock - 1) / kBlock, (int64_t)sm_count() * 8));
+  blockdiag_kernel<<<grid, kBlock, 0, st>>>(n, B.row0, B.c_lo, B.c_hi, B.off, B.vals, x, y, d_skip);
+  PSB_LAUNCH_CHECK();
+  if (B.n_long > 0) {
+    const int64_t warps = B.n_long;
+    const int g2 = (int)std::max<int64_t>(1, std::min<int64_t>((warps * 32 + kBlock - 1) / kBlock, (int64_t)sm_count() * 8));
+    blockdiag_long_kernel<<<g2, kBlock, 0, st>>>(B.n_long, B.long_rows, B.row0, B.c_lo, B.c_hi, B.off, B.vals, x, y, d_skip);
+    PSB_LAUNCH_CHECK();
+  }
+  return PSB_OK;
 }
 
 struct SplitLuPrec : psb_prec {
@@ -215,8 +229,8 @@ struct SplitLuPrec : psb_prec {
       rc = trsv_solve(L11, r, bdL.n ? tmp : y1, map_in, nullptr, nullptr, d_skip, st);
       if (rc != PSB_OK) return rc;
       if (bdL.n) {
-        blockdiag_kernel<<<grid_of(n1L), kBlock, 0, st>>>(n1L, bdL.row0, bdL.c_lo, bdL.c_hi, bdL.off, bdL.vals, tmp, y1, d_skip);
-        PSB_LAUNCH_CHECK();
+        rc = blockdiag_apply(bdL, n1L, tmp, y1, d_skip, st);
+        if (rc != PSB_OK) return rc;
       }
     }
     gather_kernel<<<grid_of(n2L), kBlock, 0, st>>>(r, map_in, n1L, n2L, w2, d_skip);
@@ -249,8 +263,8 @@ struct SplitLuPrec : psb_prec {
       if (rc != PSB_OK) return rc;
       const double* rhs1 = s1;
       if (bdU.n) {                                                         // s1' = blockdiag(D^-1) s1, then U~11
-        blockdiag_kernel<<<grid_of(n1U), kBlock, 0, st>>>(n1U, bdU.row0, bdU.c_lo, bdU.c_hi, bdU.off, bdU.vals, s1, tmp, d_skip);
-        PSB_LAUNCH_CHECK();
+        rc = blockdiag_apply(bdU, n1U, s1, tmp, d_skip, st);
+        if (rc != PSB_OK) return rc;
         rhs1 = tmp;
       }
       rc = trsv_solve(U11, rhs1, ycat, nullptr, z, map_out, d_skip, st);   // x1, scattered into z; ycat is free again
@@ -346,9 +360,16 @@ extern "C" int psb_splitlu_set_blockdiag(psb_prec_t P_, int upper, int64_t n_row
   if (e == cudaSuccess) e = cudaMemcpyAsync(B.c_hi, h_c_hi, (size_t)n_rows * 4, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(B.off, h_off, (size_t)n_rows * 8, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess && n_vals) e = cudaMemcpyAsync(B.vals, h_vals, (size_t)n_vals * 8, cudaMemcpyHostToDevice, st);
+  std::vector<int32_t> longs;
+  for (int64_t r = 0; r < n_rows; ++r) if (h_c_hi[r] - h_c_lo[r] >= kLongRow) longs.push_back((int32_t)r);
+  if (e == cudaSuccess && !longs.empty()) {
+    e = cudaMalloc((void**)&B.long_rows, longs.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(B.long_rows, longs.data(), longs.size() * 4, cudaMemcpyHostToDevice, st);
+  }
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) { B.release(); set_error("psb_splitlu_set_blockdiag: %s", cudaGetErrorString(e)); return PSB_ERR_CUDA; }
   B.n = n_rows;
+  B.n_long = (int64_t)longs.size();
   return PSB_OK;
 }
 

@@ -127,62 +127,79 @@ trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
     const int first = (is_long || !owner) ? 0 : width - T.row_cnt[item0 + lane];
     const int32_t* cp = T.cols + base + lane + (int64_t)first * 32;
     const double*  vp = T.vals + base + lane + (int64_t)first * 32;
+    // window of 4 entries: (c0,v0) is the next one to consume
     len -= first;
     if (!is_long && !owner) len = 0;
-    // Walk this lane's entries in stored (dependency-level) order, kBatch at a time: the (col, val)
-    // pairs of a batch and then all its x loads are issued together -- most dependencies belong to
-    // levels finished long ago, so the walk runs at the latency of ONE trip through L2 per batch, not
-    // per entry (the first version polled one entry, then three: 4 in flight, 331 - 440 us for the
-    // 82 wide levels of the Bratu-2048^2 coarse factors, profiles/round2_amg.md).  An entry that is
-    // not there yet is polled alone, with back-off.  Lanes are independent (the rows of a chunk
-    // belong to one level): no warp votes inside the walk.
-    constexpr int kBatch = 8;
-    bool timed_out = false;
-    for (int k = 0; k < len; k += kBatch) {
-      int c[kBatch];
-      double v[kBatch], xv[kBatch];
+    int k = 0;
+    int c0 = -1, c1 = -1, c2 = -1, c3 = -1;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    if (len > 0) { c0 = cp[0];  v0 = vp[0]; }
+    if (len > 1) { c1 = cp[32]; v1 = vp[32]; }
+    if (len > 2) { c2 = cp[64]; v2 = vp[64]; }
+    if (len > 3) { c3 = cp[96]; v3 = vp[96]; }
+    int spins = 0, idle = 0;
+    bool fed = !(c0 >= 0);            // all entries of this lane consumed (padding ends a lane's list)
+    bool done = false;
+    while (!__all_sync(0xffffffffu, done)) {
+      bool made_progress = false;
+      if (!fed) {
+        // waiting mode: one poll of the next dependency, nothing else on the path
+        double x0 = ld_relaxed(x + c0);
+        if (is_ready(x0)) {
+          made_progress = true;
+          // streaming mode: the following three entries are polled together and consumed in
+          // order as far as they are ready; new entries are fetched behind them
+          double x1 = c1 >= 0 ? ld_relaxed(x + c1) : kNotReady;
+          double x2 = c2 >= 0 ? ld_relaxed(x + c2) : kNotReady;
+          double x3 = c3 >= 0 ? ld_relaxed(x + c3) : kNotReady;
 #pragma unroll
-      for (int j = 0; j < kBatch; ++j) {
-        const bool in = k + j < len;
-        c[j] = in ? cp[(int64_t)(k + j) * 32] : -1;
-        v[j] = in ? vp[(int64_t)(k + j) * 32] : 0.0;
-      }
-#pragma unroll
-      for (int j = 0; j < kBatch; ++j) xv[j] = c[j] >= 0 ? ld_relaxed(x + c[j]) : 0.0;
-#pragma unroll
-      for (int j = 0; j < kBatch; ++j) {
-        if (c[j] >= 0) {                                    // padding (c < 0) ends a lane's list
-          int spins = 0;
-          while (!is_ready(xv[j])) {
-            if (++spins > kSpinLimit) { timed_out = true; break; }
-            if (spins > kIdleTrips) __nanosleep(spins < kIdleTrips + 8 ? 32u * (unsigned)(spins - kIdleTrips) : 256u);
-            xv[j] = ld_relaxed(x + c[j]);
+          for (int s = 0; s < 4; ++s) {
+            if (c0 >= 0 && is_ready(x0)) {
+              acc = acc - v0 * x0;                    // stored order, product rounded first
+              ++k;
+              c0 = c1; v0 = v1; x0 = x1;
+              c1 = c2; v1 = v2; x1 = x2;
+              c2 = c3; v2 = v3; x2 = x3;
+              const int nk = k + 3;
+              if (nk < len) { c3 = cp[(int64_t)nk * 32]; v3 = vp[(int64_t)nk * 32]; } else { c3 = -1; v3 = 0.0; }
+              x3 = kNotReady;
+            }
           }
-          acc = acc - v[j] * xv[j];                         // stored order, product rounded first
+          if (c0 < 0) fed = true;
+        } else if (++spins > kSpinLimit) {
+          // a dependency never became ready: raise the flag AND poison the row with an ordinary
+          // quiet NaN (not the sentinel, so consumers do not wait for it in turn) -- the
+          // failure is then visible in the result itself
+          *T.error = 1; fed = true;
+          acc = __longlong_as_double(0x7ff8000000000000ll);
         }
       }
-      if (timed_out) break;
-    }
-    if (timed_out) {
-      // a dependency never became ready: raise the flag AND poison the row with an ordinary quiet
-      // NaN (not the sentinel, so consumers do not wait for it in turn)
-      *T.error = 1;
-      acc = __longlong_as_double(0x7ff8000000000000ll);
-    }
-    __syncwarp();
-    if (is_long) {
-      double t = acc;
+      // warps whose dependencies are still levels away back off instead of hammering L2
+      if (__any_sync(0xffffffffu, made_progress)) idle = 0;
+      else if (++idle > kIdleTrips) __nanosleep(idle < kIdleTrips + 8 ? 32u * (unsigned)(idle - kIdleTrips) : 256u);
+      if (!done) {
+        if (is_long) {
+          // the row is complete when every lane has consumed its share
+          if (__all_sync(0xffffffffu, fed)) {
+            double t = acc;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) {
-        const double r = T.unit_diag ? t : t * d;           // d = 1 / diagonal
-        st_relaxed(x + row, r);
-        if (out2 != nullptr) out2[out_map[row]] = r;
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) {
+              const double r = T.unit_diag ? t : t * d;       // d = 1 / diagonal
+              st_relaxed(x + row, r);
+              if (out2 != nullptr) out2[out_map[row]] = r;
+            }
+            done = true;
+          }
+        } else if (fed) {
+          if (owner) {
+            const double r = T.unit_diag ? acc : acc * d;   // times the reciprocal of the diagonal, last
+            st_relaxed(x + row, r);
+            if (out2 != nullptr) out2[out_map[row]] = r;
+          }
+          done = true;
+        }
       }
-    } else if (owner) {
-      const double r = T.unit_diag ? acc : acc * d;         // times the reciprocal of the diagonal, last
-      st_relaxed(x + row, r);
-      if (out2 != nullptr) out2[out_map[row]] = r;
     }
   }
 }
@@ -221,7 +238,8 @@ int trsv_solve(const psb_trsv* T, const double* rhs, double* x, const int32_t* r
   }
   // Only the warps working a few dozen levels ahead of the wavefront do useful work; the rest
   // would just poll.  Size the grid for `kLookahead` levels of average width.
-  constexpr int64_t kLookahead = 48;
+  int64_t kLookahead = 48;
+  { const char* e = getenv("PSB_TRSV_LOOKAHEAD"); if (e) kLookahead = std::max(1, atoi(e)); }
   const int64_t chunks_per_level = T->n_groups / std::max(T->n_levels, 1) + 1;
   int64_t warps_needed = std::min<int64_t>(T->n_groups, chunks_per_level * kLookahead);
   int64_t grid = std::min<int64_t>((int64_t)per_sm * sm_count(), (warps_needed + kWarps - 1) / kWarps);

@@ -66,6 +66,10 @@ def main():
     cv = to_device(np.ones(amg.A[0].shape[0]))
     cz = torch.empty_like(cv)
     out['coarse_solve_ms'] = 1e3 * time_gpu(lambda: amg.coarse.apply(cv, cz))
+    for la in os.environ.get('PSB_SWEEP_LOOKAHEAD', '').split():
+        os.environ['PSB_TRSV_LOOKAHEAD'] = la
+        out['coarse_solve_ms_lookahead_' + la] = 1e3 * time_gpu(lambda: amg.coarse.apply(cv, cz))
+    os.environ.pop('PSB_TRSV_LOOKAHEAD', None)
     out['coarse_levels_L11_U11'] = list(amg.coarse.levels())
     out['coarse_dense_rows'] = amg.coarse.n2
     print(json.dumps(out))
