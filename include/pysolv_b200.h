@@ -54,6 +54,10 @@ long long   psb_launch_count(void);
 #define PSB_SPMV_VECTOR      2  /* sub-warp per row, shuffle reduction               */
 #define PSB_SPMV_STREAM_LSU  3  /* first-generation STREAM: coalesced LDG.128 of the
                                   tile, products parked in shared memory            */
+#define PSB_SPMV_MERGE       4  /* merge-path: the n_rows + nnz work items are split evenly
+                                  over CTAs and threads wherever the row boundaries fall
+                                  (a few very long rows among short ones); deterministic,
+                                  equal to scipy to rounding (not bit for bit)        */
 #define PSB_SPMV_TILE512    16  /* OR-ed into a STREAM kind for psb_csr_set_kind:
                                   512-row tiles instead of 256                       */
 

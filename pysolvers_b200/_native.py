@@ -16,7 +16,7 @@ PSB_OK = 0
 CONVERGED, MAXITER, BREAKDOWN_UR, BREAKDOWN_PAP, TRIVIAL, GMRES_FALSE_CONV = range(6)
 ORTH_CGS2, ORTH_MGS = 1, 2
 SMOOTH_JACOBI, SMOOTH_GS = 0, 1
-SPMV_STREAM, SPMV_VECTOR, SPMV_STREAM_LSU, SPMV_TILE512 = 1, 2, 3, 16
+SPMV_STREAM, SPMV_VECTOR, SPMV_STREAM_LSU, SPMV_MERGE, SPMV_TILE512 = 1, 2, 3, 4, 16
 
 
 class NativeError(RuntimeError):

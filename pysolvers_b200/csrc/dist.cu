@@ -248,11 +248,11 @@ dist_direction_kernel(DistState* st, int64_t n, int it, const double* __restrict
 // Layout of the exported region: [slots: kRing x 32 ranks x 2 words][flags: 32 x u64]
 // [p buffer 0][p buffer 1].
 // ---------------------------------------------------------------------------------------
-constexpr int64_t kSlotsBytes = 4096;    // kRing * kMaxRanks * 16 B = 2048
+constexpr int64_t kSlotsBytes = (int64_t)kRing * kMaxRanks * kSlotWords * 8;    // a 128-byte line per slot
 constexpr int64_t kFlagsBytes = 4096;
 
 struct P2PView {
-  const unsigned long long* my_slots;          // local: slot(e, q) at ((e % kRing) * kMaxRanks + q) * 2
+  const unsigned long long* my_slots;          // local: slot(e, q) at ((e % kRing) * kMaxRanks + q) * kSlotWords
   unsigned long long* const* slot_ptrs;        // device [kRing * nranks]: my slot in rank q's memory
   int nranks, my_rank;
   int n_push;
@@ -269,7 +269,7 @@ __device__ __forceinline__ double p2p_reduce(const P2PView& c, unsigned int epoc
     double s = 0.0;
     for (int q = 0; q < c.nranks; ++q) {
       double v;
-      if (!peer_wait(c.my_slots + ((size_t)(epoch % kRing) * kMaxRanks + q) * 2, epoch, &v)) *c.error = 1;
+      if (!peer_wait(c.my_slots + ((size_t)(epoch % kRing) * kMaxRanks + q) * kSlotWords, epoch, &v)) *c.error = 1;
       s += v;
     }
     s_sum = s;
@@ -599,7 +599,7 @@ extern "C" int psb_dist_p2p_open(psb_dist_t D, const void* h_handles, int32_t n_
   std::vector<unsigned long long*> sp((size_t)kRing * nr);
   for (int e = 0; e < kRing; ++e)
     for (int q = 0; q < nr; ++q)
-      sp[(size_t)e * nr + q] = (unsigned long long*)D->peer_shm[q] + ((size_t)e * kMaxRanks + me) * 2;
+      sp[(size_t)e * nr + q] = (unsigned long long*)D->peer_shm[q] + ((size_t)e * kMaxRanks + me) * kSlotWords;
   PSB_CUDA(cudaMalloc((void**)&D->d_slot_ptrs, sp.size() * sizeof(void*)));
   PSB_CUDA(cudaMemcpy(D->d_slot_ptrs, sp.data(), sp.size() * sizeof(void*), cudaMemcpyHostToDevice));
   D->pushes.clear();
@@ -880,7 +880,7 @@ static int dist_pcg_p2p(psb_dist_t D, const double* d_b, double* d_x, void* d_wo
       P.st = (MegaState*)(base + 2048);
       P.ticket = rb.ticket; P.partials = rb.partials;
       P.my_slots = (const unsigned long long*)D->shm; P.slot_ptrs = D->d_slot_ptrs;
-      P.nranks = c.nranks; P.epoch0 = e;
+      P.nranks = c.nranks; P.epoch0 = e; P.ring_words = kMaxRanks * kSlotWords;
       P.n_push = c.n_push;
       for (int k = 0; k < c.n_push; ++k) {
         P.push_off[k] = D->pushes[k].send_off; P.push_cnt[k] = D->pushes[k].cnt;

@@ -300,6 +300,80 @@ gmres_axpy_dot_kernel(GmresState* st, int64_t n, const double* __restrict__ Q, i
   }
 }
 
+// CGS2 with up to kFusedMax basis vectors: round 1's axpy over ALL vectors fused with ALL of round 2's
+// dots.  w1[i] = w[i] - sum_j h1_j q_j[i] depends on element i only, so a CTA finishes a tile of w1
+// (256 x 2 elements, in registers) from the q tiles and then walks the same q tiles again -- now in
+// L1 / L2 -- for q_j . w1: the basis is read from HBM once for both steps instead of twice
+// (3 instead of 4 passes over the basis per iteration).  Accumulators: one shared-memory slot per
+// (vector, thread) -- 32 doubles per thread in registers spilled at 128 registers.
+constexpr int kFusedMax = 32;
+
+__global__ void __launch_bounds__(kBlock, 2)
+gmres_cgs2_fused_kernel(GmresState* st, int64_t n, const double* Q, int64_t ldq, double* __restrict__ w,
+                        const double* coef, int cnt, double* dot_out, ReduceBuf rb) {
+  __shared__ double scratch[kWarps];
+  __shared__ double sh[kFusedMax];
+  if (ld_cg(&st->done) != 0) return;
+  extern __shared__ double sacc[];                       // [cnt][kBlock]
+  if (threadIdx.x < kFusedMax) sh[threadIdx.x] = (int)threadIdx.x < cnt ? -ld_cg(coef + threadIdx.x) : 0.0;
+  for (int j = 0; j < cnt; ++j) sacc[j * kBlock + threadIdx.x] = 0.0;
+  __syncthreads();
+  double* const acc = sacc + threadIdx.x;                // acc[j * kBlock]
+  const int64_t n2 = n >> 1;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n2; i += (int64_t)gridDim.x * kBlock) {
+    double2 wv = ld2rw(w + 2 * i);
+#pragma unroll
+    for (int j0 = 0; j0 < kFusedMax; j0 += 8) {
+      if (j0 < cnt) {                                   // uniform
+        double2 q[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (j0 + c < cnt) {                           // L1-allocating: read again below
+            const double2* p = reinterpret_cast<const double2*>(Q + (int64_t)(j0 + c) * ldq + 2 * i);
+            q[c] = *p;
+          }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (j0 + c < cnt) { wv.x = wv.x + sh[j0 + c] * q[c].x; wv.y = wv.y + sh[j0 + c] * q[c].y; }
+      }
+    }
+    st_stream2(w + 2 * i, wv);
+#pragma unroll
+    for (int j0 = 0; j0 < kFusedMax; j0 += 8) {
+      if (j0 < cnt) {
+        double2 q[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (j0 + c < cnt) q[c] = *reinterpret_cast<const double2*>(Q + (int64_t)(j0 + c) * ldq + 2 * i);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (j0 + c < cnt) {
+            double a = acc[(j0 + c) * kBlock];
+            a += q[c].x * wv.x; a += q[c].y * wv.y;
+            acc[(j0 + c) * kBlock] = a;
+          }
+      }
+    }
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t e = n - 1;
+    double wv = w[e];
+    for (int j = 0; j < cnt; ++j) wv = wv + sh[j] * Q[(int64_t)j * ldq + e];
+    w[e] = wv;
+    for (int j = 0; j < cnt; ++j) acc[j * kBlock] += Q[(int64_t)j * ldq + e] * wv;
+  }
+  for (int j = 0; j < cnt; ++j) {
+    const double t = block_sum(acc[j * kBlock], scratch);
+    if (threadIdx.x == 0) rb.partials[(int64_t)j * gridDim.x + blockIdx.x] = t;
+  }
+  if (last_block(rb.ticket)) {
+    for (int j = 0; j < cnt; ++j) {
+      const double t = sum_partials(rb.partials + (int64_t)j * gridDim.x, gridDim.x, scratch);
+      if (threadIdx.x == 0) dot_out[j] = t;
+    }
+  }
+}
+
 // One warp: finish column k of the Hessenberg matrix, rotate, test convergence.
 __global__ void gmres_givens_kernel(GmresState* st, GmresSmall sm, double* __restrict__ hist, int cgs2) {
   if (st->done != 0) return;
@@ -400,7 +474,7 @@ struct GmresWork {
 static int64_t small_bytes(int64_t m) {
   return align_up(((m + 2) * 2 + m * (m + 1) + 2 * m + (m + 1) + m) * (int64_t)sizeof(double), 256);
 }
-static int64_t reduce_bytes() { return align_up((int64_t)sm_count() * 16 * kCh * sizeof(double), 256); }
+static int64_t reduce_bytes() { return align_up((int64_t)sm_count() * 16 * 32 * sizeof(double), 256); }   // 32 = kFusedMax partial rows
 
 static GmresWork carve(void* d_work, int64_t n, int64_t m) {
   char* base = (char*)d_work;
@@ -501,6 +575,17 @@ static int gmres_solve_impl(psb_csr* A, psb_dist* D, psb_prec_t prec, const doub
   };
   static thread_local int wave_dot = 0, wave_axpy = 0, wave_mgs = 0, wave_fused = 0;
   const int grid_fused = one_wave((const void*)gmres_axpy_dot_kernel, &wave_fused);
+  // dynamic shared memory of the fully fused CGS2 kernel: kFusedMax x kBlock accumulators
+  static thread_local int wave_cgs2 = 0;
+  constexpr size_t kFusedSmem = (size_t)kFusedMax * kBlock * sizeof(double);
+  if (wave_cgs2 == 0) {
+    PSB_CUDA(cudaFuncSetAttribute(gmres_cgs2_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gmres_cgs2_fused_kernel, kBlock, kFusedSmem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    wave_cgs2 = per_sm * sm_count();
+  }
+  const int grid_cgs2 = one_wave((const void*)gmres_cgs2_fused_kernel, &wave_cgs2);
+  static const bool fuse_all = getenv("PSB_GMRES_NOFUSE_ALL") == nullptr;
   static const bool fuse_cgs2 = getenv("PSB_GMRES_NOFUSE") == nullptr;
   const int grid_dot = one_wave((const void*)gmres_multidot_kernel, &wave_dot);
   const int grid_axpy = one_wave((const void*)gmres_multiaxpy_kernel, &wave_axpy);
@@ -538,7 +623,29 @@ static int gmres_solve_impl(psb_csr* A, psb_dist* D, psb_prec_t prec, const doub
       }
     } else {
       const int j_last = (k / kCh) * kCh;              // first vector of the last chunk
-      for (int round = 0; round < 2; ++round) {
+      const bool all_fused = fuse_cgs2 && fuse_all && k + 1 <= kFusedMax;
+      if (all_fused) {
+        // round-1 dots | all-reduce | [round-1 axpy over all vectors + all round-2 dots] | all-reduce |
+        // round-2 axpy (+ ||w||^2): the basis is streamed from HBM three times, not four
+        for (int j0 = 0; j0 <= k; j0 += kCh) {
+          const int cnt = std::min(kCh, k + 1 - j0);
+          gmres_multidot_kernel<<<grid_dot, kBlock, 0, st>>>(w.st, n, w.Q, w.ldq, w.w, j0, cnt, w.sm.hcol, w.rb);
+          PSB_LAUNCH_CHECK();
+        }
+        rc = allreduce(w.sm.hcol, k + 1);
+        if (rc != PSB_OK) return rc;
+        gmres_cgs2_fused_kernel<<<grid_cgs2, kBlock, kFusedSmem, st>>>(w.st, n, w.Q, w.ldq, w.w, w.sm.hcol, k + 1, w.sm.hcol2, w.rb);
+        PSB_LAUNCH_CHECK();
+        rc = allreduce(w.sm.hcol2, k + 1);
+        if (rc != PSB_OK) return rc;
+        for (int j0 = 0; j0 <= k; j0 += kCh) {
+          const int cnt = std::min(kCh, k + 1 - j0);
+          gmres_multiaxpy_kernel<<<grid_axpy, kBlock, 0, st>>>(w.st, n, w.Q, w.ldq, w.w, w.sm.hcol2, j0, cnt, -1.0,
+                                                          0, j0 + kCh > k ? 1 : 0, 1, w.rb);
+          PSB_LAUNCH_CHECK();
+        }
+      }
+      for (int round = 0; round < 2 && !all_fused; ++round) {
         double* hout = round == 0 ? w.sm.hcol : w.sm.hcol2;
         for (int j0 = 0; j0 <= k; j0 += kCh) {
           if (round == 1 && fuse_cgs2 && j0 == j_last) continue;   // formed by the fused kernel below

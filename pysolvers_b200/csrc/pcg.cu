@@ -362,10 +362,10 @@ extern "C" int psb_pcg_solve(psb_csr_t A, psb_prec_t prec, const double* d_b, do
       unsigned long long* slots = (unsigned long long*)(base + 2048);
       unsigned long long** d_ptrs = (unsigned long long**)(base + 1536);
       unsigned long long* h_ptrs[kRing];
-      for (int e = 0; e < kRing; ++e) h_ptrs[e] = slots + (size_t)e * kMaxRanks * 2;
+      for (int e = 0; e < kRing; ++e) h_ptrs[e] = slots + (size_t)e * kSlotWords;   // one rank: a line per ring entry
       PSB_CUDA(cudaMemcpyAsync(d_ptrs, h_ptrs, sizeof(h_ptrs), cudaMemcpyHostToDevice, st));
       PSB_CUDA(cudaStreamSynchronize(st));                  // h_ptrs is on the stack
-      P.my_slots = slots; P.slot_ptrs = d_ptrs; P.nranks = 1; P.epoch0 = 1;
+      P.my_slots = slots; P.slot_ptrs = d_ptrs; P.nranks = 1; P.epoch0 = 1; P.ring_words = kSlotWords;
       P.n_push = 0; P.n_wait = 0; P.halo_epoch0 = 1;
       P.int_r0 = P.int_r1 = 0;
       P.maxiter = maxiter; P.tau = tau; P.fail_on_maxiter = fail_on_maxiter;

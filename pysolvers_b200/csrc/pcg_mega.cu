@@ -48,6 +48,7 @@ __device__ __forceinline__ unsigned long long mega_now() {
 }
 
 __device__ __forceinline__ double mega_sum_partials(const double* partials, int count, double* scratch);
+constexpr unsigned long long kMegaFailBits = 0x7ff4dead00000001ull;   // signalling NaN: "a peer never answered"
 
 // Grid-wide (and rank-wide) sum of `v`.  Every thread of every CTA calls it; all return the same
 // bits.  `pushed`: this thread stored halo data into a neighbour's memory since the last raise
@@ -63,20 +64,56 @@ __device__ __forceinline__ double mega_allreduce(const MegaParams& P, double v, 
   __shared__ int s_ok;
   const double t = block_sum(v, scratch);
   if (threadIdx.x == 0) P.partials[blockIdx.x] = t;
-  if (pushed) __threadfence_system();
-  const size_t ring = (size_t)(epoch % kRing) * kMaxRanks * 2;
+  // Halo stores into the neighbours' memory are published by ONE system-scope fence of the last CTA
+  // (below), not by a fence in every pushing thread: the pushing thread's stores happen before its
+  // gpu-scope fence and ticket (last_block), the last CTA observes every ticket, and its
+  // fence.sys is cumulative over everything it has observed (PTX memory model; the same pattern as
+  // "bar.sync, then one thread fences and raises the flag" inside a CTA).  With the system fence in
+  // the pushing threads the r.r reduce took 13 - 15 us at 8 GPUs against 6.5 us for p.Ap
+  // (profiles/round2_mega_timeline.md); PSB_MEGA_FLAGS=4 restores it for A/B runs.
+  if (pushed && (P.dbg_flags & 4)) __threadfence_system();
+  const size_t ring = (size_t)(epoch % kRing) * (size_t)P.ring_words;
   const bool last = last_block(P.ticket);
+  // Two-stage release for more than two ranks: only the LAST CTA of each rank polls the ranks' slots
+  // (8 lanes instead of 8 lanes x every CTA: with all of them polling, a poll trip through L2 took
+  // several microseconds and the reduce 9 - 14 us at 8 GPUs), adds them in rank order and stores the
+  // total into a local broadcast slot; every other CTA polls that one slot.
+  const bool two_stage = P.nranks > 2;
+  const size_t bcast = ring + (size_t)(kMaxRanks - 1) * kSlotWords;
   if (last) {
     const double s = mega_sum_partials(P.partials, gridDim.x, scratch);
     if ((int)threadIdx.x < P.nranks) peer_push(push_base + ring, s, epoch);
+    if (two_stage && threadIdx.x < 32) {
+      double mine = 0.0;
+      bool good = true;
+      if ((int)threadIdx.x < P.nranks) good = peer_wait(P.my_slots + ring + threadIdx.x * kSlotWords, epoch, &mine);
+      double tot = 0.0;
+      for (int q = 0; q < P.nranks; ++q) tot += __shfl_sync(0xffffffffu, mine, q);
+      const bool all_good = __all_sync(0xffffffffu, good);
+      if (threadIdx.x == 0) {
+        if (!all_good) *P.error = 1;
+        // a time-out still releases the other CTAs, with a payload no arithmetic produces
+        peer_push(const_cast<unsigned long long*>(P.my_slots) + bcast,
+                  all_good ? tot : __longlong_as_double((long long)kMegaFailBits), epoch);
+      }
+    }
   }
   if (threadIdx.x < 32) {                       // one lane per rank polls, then a fixed-order sum
-    double mine = 0.0;
-    bool good = true;
-    if ((int)threadIdx.x < P.nranks) good = peer_wait(P.my_slots + ring + threadIdx.x * 2, epoch, &mine);
     double s = 0.0;
-    for (int q = 0; q < P.nranks; ++q) s += __shfl_sync(0xffffffffu, mine, q);
-    const bool all_good = __all_sync(0xffffffffu, good);
+    bool all_good = true;
+    if (two_stage) {
+      double tot = 0.0;
+      bool good = true;
+      if (threadIdx.x == 0) good = peer_wait(P.my_slots + bcast, epoch, &tot);
+      s = __shfl_sync(0xffffffffu, tot, 0);
+      all_good = __all_sync(0xffffffffu, good) && (unsigned long long)__double_as_longlong(s) != kMegaFailBits;
+    } else {
+      double mine = 0.0;
+      bool good = true;
+      if ((int)threadIdx.x < P.nranks) good = peer_wait(P.my_slots + ring + threadIdx.x * kSlotWords, epoch, &mine);
+      for (int q = 0; q < P.nranks; ++q) s += __shfl_sync(0xffffffffu, mine, q);
+      all_good = __all_sync(0xffffffffu, good);
+    }
     if (threadIdx.x == 0) { s_sum = s; s_ok = all_good ? 1 : 0; if (!all_good) *P.error = 1; }
   }
   // The halo flags are raised AFTER the poll: the neighbour needs them only when it reaches its
@@ -157,7 +194,7 @@ pcg_mega_kernel(const MegaParams P) {
   unsigned int e = P.epoch0;
   const unsigned long long h0 = P.halo_epoch0;
   unsigned long long* push_base = nullptr;
-  if (tid < P.nranks) push_base = P.slot_ptrs[tid];          // ring 0; ring k is kMaxRanks * 2 words further
+  if (tid < P.nranks) push_base = P.slot_ptrs[tid];          // ring 0; ring k is k * ring_words further
 
   // constant part of the SpMV arguments; the bounds of the first two tiles are cached
   EpiArgs ea;

@@ -7,6 +7,11 @@ namespace psb {
 constexpr int kRing = 4;         // reduction slots are reused every kRing epochs
 constexpr int kMaxRanks = 32;
 constexpr int kMaxPush = 4;
+// One all-reduce slot (two 8-byte epoch-tagged words) per 128-byte line: every CTA of a rank polls
+// the slots of all ranks, and with the slots of 8 ranks in ONE line ~4 700 lanes hammered a single L2
+// slice -- the peers' incoming stores queued behind them (reduce latency 4.5 us at 2 GPUs, 9 - 14 us at
+// 8, profiles/round2_mega_timeline.md).  Spread over lines, i.e. L2 slices, each sees one lane per CTA.
+constexpr int kSlotWords = 16;
 
 struct MegaState {
   double norm_b, norm_r;
@@ -29,8 +34,9 @@ struct MegaParams {
   double* partials;
   unsigned int* ticket;
   // all-reduce slots (epoch-tagged, see common.cuh peer_push / peer_wait)
-  const unsigned long long* my_slots;            // local ring: slot(e, q) at ((e % kRing) * kMaxRanks + q) * 2
+  const unsigned long long* my_slots;            // local ring: slot(e, q) at (e % kRing) * ring_words + q * kSlotWords
   unsigned long long* const* slot_ptrs;          // device [kRing * nranks]: my slot in rank q's memory
+  int ring_words;                                // words between ring entries (kMaxRanks * kSlotWords; kSlotWords on one GPU)
   int nranks;
   unsigned int epoch0;
   // halo pushes to the neighbours (row-partitioned runs)

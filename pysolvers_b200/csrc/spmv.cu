@@ -365,10 +365,171 @@ static int launch_vector(const psb_csr* A, const double* x, double* y, const Epi
   return PSB_OK;
 }
 
+// ---------------------------------------------------------------------------
+// MERGE kernel (merge-path SpMV, Merrill & Garland): skewed row-length histograms
+// ---------------------------------------------------------------------------
+// A few very long rows among short ones defeat both layouts above: a thread (or sub-warp) per row
+// serialises on the long rows, and a STREAM tile that contains one does not fit shared memory.  Here
+// the WORK is split evenly instead of the rows: the n_rows row-ends and the nnz entries are merged
+// into one list of n_rows + nnz items, every CTA takes kMergeTile consecutive items and every thread
+// kMergeItems of them, wherever the row boundaries fall (two binary searches per CTA, one per thread).
+// A thread adds the products of its segment in stored order; the pieces of a row that spans threads
+// are combined by a segmented scan in thread order, the pieces of a row that spans CTAs by a second
+// small kernel in CTA order: deterministic, but associated differently from the sequential sum, so
+// this kind agrees with scipy to rounding, not bit for bit (like VECTOR).  The epilogue runs as a
+// separate pass over the rows (the sums are complete only after the cross-CTA fix-up).
+constexpr int kMergeItems = 7;
+constexpr int kMergeTile = kBlock * kMergeItems;
+
+// first coordinate (row, nz) on diagonal d of the merge of row_end[0..n_rows) with 0..nnz)
+__device__ __forceinline__ void merge_search(int64_t d, const int* __restrict__ row_end, int64_t n_rows, int64_t nnz,
+                                             int64_t& row, int64_t& nz) {
+  int64_t lo = d > nnz ? d - nnz : 0, hi = d < n_rows ? d : n_rows;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)row_end[mid] <= d - mid - 1) lo = mid + 1; else hi = mid;
+  }
+  row = lo; nz = d - lo;
+}
+
+__global__ void __launch_bounds__(kBlock)
+spmv_merge_kernel(const psb_csr A, const double* x, double* __restrict__ ysum, int* __restrict__ carry_row,
+                  double* __restrict__ carry_val, const int* __restrict__ d_skip) {
+  __shared__ int s_end[kMergeTile + 2];
+  __shared__ double s_acc[kMergeTile + 2];
+  __shared__ long long s_coord[4];
+  __shared__ int s_key[kBlock];
+  __shared__ double s_val[kBlock];
+  if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
+  const int tid = threadIdx.x;
+  const int* row_end = A.rowptr + 1;
+  const int64_t total = A.n_rows + A.nnz;
+  const int64_t n_tiles = (total + kMergeTile - 1) / kMergeTile;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t d0 = tile * kMergeTile, d1 = min(d0 + (int64_t)kMergeTile, total);
+    if (tid < 2) {
+      int64_t r, k;
+      merge_search(tid == 0 ? d0 : d1, row_end, A.n_rows, A.nnz, r, k);
+      s_coord[2 * tid] = r; s_coord[2 * tid + 1] = k;
+    }
+    __syncthreads();
+    const int64_t r0 = s_coord[0], r1 = s_coord[2];
+    const int n_tr = (int)(r1 - r0) + 1;                      // rows touched; the last one may be partial
+    for (int i = tid; i < n_tr; i += kBlock) {
+      s_end[i] = r0 + i < A.n_rows ? row_end[r0 + i] : INT32_MAX;
+      s_acc[i] = 0.0;
+    }
+    __syncthreads();
+    // this thread's segment
+    const int64_t d = min(d0 + (int64_t)tid * kMergeItems, d1);
+    const int64_t de = min(d + (int64_t)kMergeItems, d1);
+    int64_t lo = max(d - A.nnz, r0), hi = min(d, r1);       // search restricted to the tile's rows
+    lo = max(lo, (int64_t)0);
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if ((int64_t)s_end[mid - r0] <= d - mid - 1) lo = mid + 1; else hi = mid;
+    }
+    int64_t r = lo, k = d - lo;
+    double acc = 0.0;
+    for (int64_t it = d; it < de; ++it) {
+      if (k < (int64_t)s_end[r - r0]) {
+        acc += A.vals[k] * ld_ca(x + A.colind[k]);            // stored order inside the segment
+        ++k;
+      } else {
+        s_acc[r - r0] = acc;                                   // the row ends here: its tail part
+        acc = 0.0;
+        ++r;
+      }
+    }
+    s_key[tid] = (int)(r - r0);
+    s_val[tid] = acc;                                          // carry: head part of row r
+    __syncthreads();
+    // carries of consecutive threads with the same row are one run: segmented scan per 32, runs
+    // added into the row's slot in thread order (warp 0, eight rounds: deterministic)
+    if (tid < 32) {
+      for (int c = 0; c < kBlock; c += 32) {
+        const int key = s_key[c + tid];
+        double v = s_val[c + tid];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double up = __shfl_up_sync(0xffffffffu, v, o);
+          const int kup = __shfl_up_sync(0xffffffffu, key, o);
+          if (tid >= o && kup == key) v = up + v;
+        }
+        const int knext = __shfl_down_sync(0xffffffffu, key, 1);
+        if (tid == 31 || knext != key) s_acc[key] = s_acc[key] + v;   // run tail; later rounds add behind it
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < n_tr - 1; i += kBlock) ysum[r0 + i] = s_acc[i];   // rows that END in this tile
+    if (tid == 0) {
+      const bool open = r1 < A.n_rows;                         // the last row continues in the next tile
+      carry_row[tile] = open ? (int)r1 : -1;
+      carry_val[tile] = open ? s_acc[n_tr - 1] : 0.0;
+    }
+    __syncthreads();
+  }
+}
+
+// adds the head parts that earlier CTAs computed to the row's tail part, in CTA order
+__global__ void __launch_bounds__(kBlock)
+spmv_merge_fixup_kernel(int64_t n_tiles, const int* __restrict__ carry_row, const double* __restrict__ carry_val,
+                        double* __restrict__ ysum, const int* __restrict__ d_skip) {
+  if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
+  for (int64_t t = blockIdx.x * (int64_t)kBlock + threadIdx.x; t < n_tiles; t += (int64_t)gridDim.x * kBlock) {
+    const int row = carry_row[t];
+    if (row < 0 || (t > 0 && carry_row[t - 1] == row)) continue;   // not the first CTA of this row's run
+    double sum = 0.0;
+    for (int64_t u = t; u < n_tiles && carry_row[u] == row; ++u) sum += carry_val[u];
+    ysum[row] = sum + ysum[row];
+  }
+}
+
+// the epilogue of a merge-path product: one thread per row on the finished sums
+template <int EPI>
+__global__ void __launch_bounds__(kBlock)
+spmv_merge_epi_kernel(const psb_csr A, const double* __restrict__ ysum, const double* x, double* y,
+                      const EpiArgs ea, const int* __restrict__ d_skip) {
+  __shared__ double scratch[kWarps];
+  if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < A.n_rows; i += (int64_t)gridDim.x * kBlock)
+    epilogue<EPI>(A.row_off + i, ysum[i], x, y, ea, acc);
+  finish_dot<EPI>(acc, A, ea, scratch);
+}
+
+template <int EPI>
+static int launch_merge(const psb_csr* A, const double* x, double* y, const EpiArgs& ea, const int* d_skip,
+                        cudaStream_t st) {
+  const int64_t total = A->n_rows + A->nnz;
+  const int64_t n_tiles = (total + kMergeTile - 1) / kMergeTile;
+  if (A->merge_ysum == nullptr || n_tiles > A->merge_tiles) {
+    set_error("spmv_launch: the matrix has no merge-path workspace (psb_csr_set_kind(PSB_SPMV_MERGE) allocates it)");
+    return PSB_ERR_ARG;
+  }
+  static thread_local int per_sm = 0;
+  if (per_sm == 0) {
+    int rc = occupancy_per_sm(spmv_merge_kernel, 0, &per_sm);
+    if (rc != PSB_OK) return rc;
+  }
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)per_sm * sm_count(), n_tiles));
+  spmv_merge_kernel<<<grid, kBlock, 0, st>>>(*A, x, A->merge_ysum, A->merge_carry_row, A->merge_carry_val, d_skip);
+  PSB_LAUNCH_CHECK();
+  const int g2 = (int)std::max<int64_t>(1, std::min<int64_t>((n_tiles + kBlock - 1) / kBlock, (int64_t)sm_count() * 4));
+  spmv_merge_fixup_kernel<<<g2, kBlock, 0, st>>>(n_tiles, A->merge_carry_row, A->merge_carry_val, A->merge_ysum, d_skip);
+  PSB_LAUNCH_CHECK();
+  const int g3 = grid_for(8, (A->n_rows + kBlock - 1) / kBlock, A->max_grid);
+  spmv_merge_epi_kernel<EPI><<<g3, kBlock, 0, st>>>(*A, A->merge_ysum, x, y, ea, d_skip);
+  PSB_LAUNCH_CHECK();
+  return PSB_OK;
+}
+
 template <int EPI>
 static int launch_epi(const psb_csr* A, const double* x, double* y, const EpiArgs& ea,
                       const int* d_skip, cudaStream_t st) {
   if (A->n_rows == 0) return PSB_OK;
+  if (A->kind == PSB_SPMV_MERGE) return launch_merge<EPI>(A, x, y, ea, d_skip, st);
   if (A->kind == PSB_SPMV_STREAM) {
     return A->rpt == 2 ? launch_bulk<EPI, 2>(A, x, y, ea, d_skip, st)
                        : launch_bulk<EPI, 1>(A, x, y, ea, d_skip, st);
@@ -459,12 +620,31 @@ static size_t lsu_smem(const psb_csr* A, int rpt) {
   return (size_t)((A->max_tile_nnz[rpt - 1] + 1) & ~1) * 8 + (size_t)(kBlock * rpt + 1) * 4;
 }
 
+// workspace of the merge-path kind: row sums + one carry per CTA tile
+static int merge_alloc(psb_csr* A) {
+  const int64_t tiles = (A->n_rows + A->nnz + kMergeTile - 1) / kMergeTile + 1;
+  if (A->merge_ysum != nullptr && A->merge_tiles >= tiles) return PSB_OK;
+  cudaFree(A->merge_ysum); cudaFree(A->merge_carry_row); cudaFree(A->merge_carry_val);
+  A->merge_ysum = nullptr; A->merge_carry_row = nullptr; A->merge_carry_val = nullptr; A->merge_tiles = 0;
+  PSB_CUDA(cudaMalloc((void**)&A->merge_ysum, (size_t)std::max<int64_t>(A->n_rows, 1) * sizeof(double)));
+  PSB_CUDA(cudaMalloc((void**)&A->merge_carry_row, (size_t)tiles * sizeof(int)));
+  PSB_CUDA(cudaMalloc((void**)&A->merge_carry_val, (size_t)tiles * sizeof(double)));
+  A->merge_tiles = tiles;
+  return PSB_OK;
+}
+
 static void choose_kernel(psb_csr* A) {
   const double mean = A->n_rows ? (double)A->nnz / (double)A->n_rows : 0.0;
   int w = 2;
   while (w < 32 && w < mean) w <<= 1;
   A->vec_width = w;
   A->kind = PSB_SPMV_VECTOR; A->rpt = 1;
+  // skewed histogram: a few rows far longer than the rest (>= 512 entries and >= 16 x the mean) would
+  // serialise a thread-per-row or sub-warp-per-row kernel -> split the work, not the rows
+  if (A->max_row >= 512 && (double)A->max_row >= 16.0 * std::max(mean, 2.0) && merge_alloc(A) == PSB_OK) {
+    A->kind = PSB_SPMV_MERGE;
+    return;
+  }
   if (mean > 32.0) return;
   if (A->vec_loads) {                                  // bulk copies need 16-byte alignment
     int cv, cc; size_t smem;
@@ -498,6 +678,7 @@ extern "C" int psb_csr_create(int64_t n_rows, int64_t n_cols, int64_t nnz,
   A->max_grid = sm_count() * 16;
   A->partials = nullptr; A->ticket = nullptr; A->colind16 = nullptr;
   A->mega_grid = 0; A->mega_tile_rows = 0; A->mega_tile_nnz = 0;
+  A->merge_ysum = nullptr; A->merge_carry_row = nullptr; A->merge_carry_val = nullptr; A->merge_tiles = 0;
   int h_stats[4] = {0, 0, 0, 0};        // longest row, fullest 256- / 512-row tile, "a column delta does not fit 16 bits"
   int* d_stats = nullptr;
   cudaError_t e = cudaMalloc(&A->partials, sizeof(double) * A->max_grid);
@@ -565,6 +746,7 @@ extern "C" int psb_csr_destroy(psb_csr_t A) {
   if (A->partials) cudaFree(A->partials);
   if (A->ticket) cudaFree(A->ticket);
   if (A->colind16) cudaFree((void*)A->colind16);
+  cudaFree(A->merge_ysum); cudaFree(A->merge_carry_row); cudaFree(A->merge_carry_val);
   delete A;
   return PSB_OK;
 }
@@ -587,6 +769,12 @@ extern "C" int psb_csr_set_kind(psb_csr_t A, int kind) {
   const int base = kind & 15;
   const int rpt = (kind & PSB_SPMV_TILE512) ? 2 : 1;
   if (base == PSB_SPMV_VECTOR) { A->kind = base; return PSB_OK; }
+  if (base == PSB_SPMV_MERGE) {
+    int rc = merge_alloc(A);
+    if (rc != PSB_OK) return rc;
+    A->kind = base;
+    return PSB_OK;
+  }
   if (base == PSB_SPMV_STREAM) {
     PSB_REQUIRE(A->vec_loads, PSB_ERR_UNSUPP, "psb_csr_set_kind: arrays are not 16-byte aligned");
     int cv, cc; size_t smem;

@@ -19,6 +19,11 @@ struct psb_csr {
   double*       partials;   // per-CTA partial sums of the fused dot
   unsigned int* ticket;     // last-CTA ticket
   int  max_grid;        // CTAs the partial buffer can hold
+  // merge-path kind: per-row sums before the epilogue and the per-CTA carries (owned, lazily allocated)
+  double* merge_ysum;
+  int*    merge_carry_row;
+  double* merge_carry_val;
+  int64_t merge_tiles;
   // persistent PCG kernel: tile plan cached per (grid) -- rows per tile and the fullest such tile
   int  mega_grid, mega_tile_rows, mega_tile_nnz;
 };

@@ -1,4 +1,3 @@
-python -m pytest tests/test_gpu_amg.py tests/test_gpu_trsv.py -x -q > gpurun_out/r2h_tests.log 2>&1; tail -3 gpurun_out/r2h_tests.log
-PSB_SWEEP_LOOKAHEAD="2 4 8 16 32 48 96" python tools/amg_profile.py 2048 2> gpurun_out/r2h_amg2048.err | tee gpurun_out/r2h_amg2048.json
-PSB_SWEEP_LOOKAHEAD="2 4 8 16 32 48 96" python tools/amg_profile.py 512 2> gpurun_out/r2h_amg512.err | tee gpurun_out/r2h_amg512.json
-ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2h_amg2048_launches.csv python tools/amg_profile.py 2048 --profile > gpurun_out/r2h_ncu_amg.log 2>&1; tail -2 gpurun_out/r2h_ncu_amg.log
+python -m pytest tests -m gpu -x -q > gpurun_out/r2j_tests.log 2>&1; tail -6 gpurun_out/r2j_tests.log | cut -c1-400
+python tools/dist_bratu.py --gridm 2048 2> gpurun_out/r2j_bratu_n1.err | grep -E "^\{" | tee gpurun_out/r2j_bratu_n1.json | cut -c1-1200
+python tools/mega_timeline.py --gridm 1448 --out gpurun_out/tl1c_m1448 2>&1 | grep -E "^rank|iter_us"
