@@ -289,6 +289,9 @@ int psb_amg_create(int32_t n_levels, const psb_csr_t* A, const psb_csr_t* P,
                    double tau, psb_prec_t* out);
 /* AMGVCycleSolver.solve (VCycleSolver.py:52-95): up to maxiter cycles, d_hist[k] =
  * ||b - A x_k||; status PSB_CONVERGED / PSB_MAXITER / PSB_TRIVIAL.  Synchronises. */
+/* x += dx (ClassicSmoothers.py:34: the update of the Gauss-Seidel smoother when it is used as a
+ * stand-alone plug-in object; inside the V-cycle the same kernel runs from psb_amg_create's handle) */
+int psb_vec_add(int64_t n, const double* d_dx, double* d_x, void* stream);
 int psb_amg_solve(psb_prec_t amg, const double* d_b, double* d_x, int32_t maxiter,
                   double tau, double* d_hist, psb_solve_result* result, void* stream);
 

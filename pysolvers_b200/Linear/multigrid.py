@@ -90,7 +90,8 @@ class GaussSeidelSmoother(_DeviceSmoother):
         for _ in range(nu):
             nat.check(nat.lib().psb_spmv_residual(dA.handle, ptr(xd), ptr(fd), ptr(r),
                                                   current_stream_ptr()), 'psb_spmv_residual')
-            xd = xd + dU.solve(r)
+            dx = dU.solve(r)
+            nat.check(nat.lib().psb_vec_add(xd.numel(), ptr(dx), ptr(xd), current_stream_ptr()), 'psb_vec_add')
         dU.check()
         return xd.cpu().numpy()
 

@@ -73,6 +73,7 @@ SIGNATURES = {
     'psb_prec_destroy': (C.c_int, [_vp]),
     'psb_amg_create': (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dbl, _i32, _i32, _i32, _dbl,
                                  C.POINTER(_vp)]),
+    'psb_vec_add': (C.c_int, [_i64, _vp, _vp, _vp]),
     'psb_amg_solve': (C.c_int, [_vp, _vp, _vp, _i32, _dbl, _vp, C.POINTER(SolveResult), _vp]),
     'psb_pcg_workspace_bytes': (_i64, [_i64, C.c_int]),
     'psb_pcg_solve': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _dbl, _i32, _vp,

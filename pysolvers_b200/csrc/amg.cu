@@ -428,6 +428,15 @@ extern "C" int psb_dist_amg_create(psb_comm_t comm, int32_t n_levels, const psb_
   return amg_finish_create(M, out);
 }
 
+// x += dx on the device (ClassicSmoothers.py:34, the Gauss-Seidel plug-in smoother's update)
+extern "C" int psb_vec_add(int64_t n, const double* d_dx, double* d_x, void* stream) {
+  PSB_REQUIRE(n >= 0 && (n == 0 || (d_dx && d_x)), PSB_ERR_ARG, "psb_vec_add: bad argument");
+  if (n == 0) return PSB_OK;
+  amg_add_kernel<<<stream_grid(n, sm_count() * 16), kBlock, 0, (cudaStream_t)stream>>>(d_x, d_dx, n, nullptr);
+  PSB_LAUNCH_CHECK();
+  return PSB_OK;
+}
+
 // AMGVCycleSolver.solve: up to maxiter V-cycles from x0 = b; d_hist (maxiter doubles) receives
 // ||b - A x|| after every cycle.  Synchronises.
 extern "C" int psb_amg_solve(psb_prec_t amg, const double* d_b, double* d_x, int32_t maxiter, double tau,
