@@ -109,14 +109,15 @@ trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
     if (g >= (unsigned int)T.n_groups) return;
     const int64_t base = T.grp_ptr[g];
     int len = (int)((T.grp_ptr[g + 1] - base) >> 5);           // entries per lane
-    const int rows = T.grp_rows[g];                            // 0: one long row for the warp
+    const int rows = T.grp_rows[g];                            // 0: one long row for the warp; < 0: -rows rows of 8 lanes
     const int item0 = T.grp_item[g];
-    const bool is_long = rows == 0;
-    const bool owner = is_long ? (lane == 0) : (lane < rows);  // lanes that own a row
+    const bool is_sub = rows < 0;
+    const bool is_long = rows <= 0;                            // lanes share rows: reduce before the store
+    const bool owner = rows == 0 ? (lane == 0) : (is_sub ? ((lane & 7) == 0 && (lane >> 3) < -rows) : (lane < rows));
     int row = 0;
     double acc = 0.0, d = 1.0;
     if (owner) {
-      const int q = item0 + (is_long ? 0 : lane);
+      const int q = item0 + (rows == 0 ? 0 : (is_sub ? (lane >> 3) : lane));
       row = T.order[q];
       acc = rhs_map ? rhs[rhs_map[row]] : rhs[row];
       d = T.diag[q];
@@ -125,6 +126,7 @@ trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
     // entry row, for the lock-step walk of the one-CTA kernel): this lane's list starts further in
     const int width = len;
     const int first = (is_long || !owner) ? 0 : width - T.row_cnt[item0 + lane];
+    if (is_sub && (lane >> 3) >= -rows) len = 0;              // lanes of an absent row
     const int32_t* cp = T.cols + base + lane + (int64_t)first * 32;
     const double*  vp = T.vals + base + lane + (int64_t)first * 32;
     // window of 4 entries: (c0,v0) is the next one to consume
@@ -182,9 +184,10 @@ trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
           // the row is complete when every lane has consumed its share
           if (__all_sync(0xffffffffu, fed)) {
             double t = acc;
+            if (!is_sub) { t += __shfl_xor_sync(0xffffffffu, t, 16); t += __shfl_xor_sync(0xffffffffu, t, 8); }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (lane == 0) {
+            for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (owner) {
               const double r = T.unit_diag ? t : t * d;       // d = 1 / diagonal
               st_relaxed(x + row, r);
               if (out2 != nullptr) out2[out_map[row]] = r;
@@ -219,7 +222,8 @@ int trsv_solve(const psb_trsv* T, const double* rhs, double* x, const int32_t* r
                double* out2, const int32_t* out_map, const int* d_skip, cudaStream_t st) {
   if (T->n == 0) return PSB_OK;
   const int forced = T->forced_kernel >= 0 ? T->forced_kernel : trsv_kernel_override();
-  const int kernel = forced >= 0 ? forced : T->kernel;
+  int kernel = forced >= 0 ? forced : T->kernel;
+  if (!T->cta_ok) kernel = PSB_TRSV_GRID;       // wide levels packed with 8 lanes per row: the grid kernel's format
   if (kernel == PSB_TRSV_CTA || kernel == PSB_TRSV_CLUSTER) {
     if (T->n_far > 0) {      // far dependencies are polled in the global vector: sentinel first
       const int fg = (int)std::min<int64_t>((T->n + kBlock * 4 - 1) / (kBlock * 4), (int64_t)sm_count() * 8);
@@ -366,34 +370,61 @@ extern "C" int psb_trsv_create(int64_t n, const int32_t* h_rowptr, const int32_t
     for (int64_t i = 0; i < n; ++i) T->h_level_rows[cursor[level[i]]++] = (int32_t)i;
   }
 
-  // ---- processing order: inside a level the short rows first, then the long ones ------------
-  constexpr int kLongRow = 32;                 // more off-diagonal entries than this -> warp per row
+  // ---- row classes ------------------------------------------------------------------------------
+  // narrow levels (IC / ILUT / chains: the latency of the dependency chain decides, one-CTA / cluster
+  // kernels): thread per row up to 32 entries, warp per row beyond.
+  // WIDE levels (> kTrsvClusterMaxChunksPerLevel chunks of 32 rows per level: the grid kernel; e.g. the
+  // leading blocks of the AMG coarse LU factors, 8 000 rows per level, 46 entries per row): a lane
+  // walks its entries four L2 round trips at a time, so a 32-entry row on one lane is 8 trips deep and
+  // every level waited for its longest thread-per-row row (measured 4 - 5 us per level,
+  // profiles/round2_amg.md).  There: thread per row up to 8 entries, EIGHT lanes per row (four rows
+  // per warp) up to 64, warp per row beyond -- at most two trips per row.
+  const bool wide = (double)n / 32.0 / std::max(T->n_levels, 1) > kTrsvClusterMaxChunksPerLevel &&
+                    getenv("PSB_TRSV_NO_SUBWARP") == nullptr;
+  const int kShortRow = wide ? 8 : 32;         // thread per row up to this many off-diagonal entries
+  const int kLongRow = wide ? 64 : 32;         // more than this -> warp per row; in between: 8 lanes per row
+  auto cls = [&](int32_t i) { return off_count[i] <= kShortRow ? 0 : (off_count[i] <= kLongRow ? 1 : 2); };
+  // ---- processing order: inside a level the short rows first, then the medium, then the long ones
   std::vector<int32_t> order((size_t)n);
   {
     int64_t q = 0;
     for (int l = 0; l < T->n_levels; ++l) {
       const int32_t a0 = T->h_level_ptr[l], b0 = T->h_level_ptr[l + 1];
-      for (int32_t p = a0; p < b0; ++p) { const int32_t i = T->h_level_rows[p]; if (off_count[i] <= kLongRow) order[q++] = i; }
-      for (int32_t p = a0; p < b0; ++p) { const int32_t i = T->h_level_rows[p]; if (off_count[i] > kLongRow) order[q++] = i; }
+      for (int c = 0; c < 3; ++c)
+        for (int32_t p = a0; p < b0; ++p) { const int32_t i = T->h_level_rows[p]; if (cls(i) == c) order[q++] = i; }
     }
   }
-  // ---- chunks: up to 32 consecutive short rows (SELL-32), or one long row over 32 lanes -------
+  // ---- chunks: up to 32 consecutive short rows (SELL-32), up to 4 medium rows on 8 lanes each
+  // (grp_rows = -rows), or one long row over 32 lanes (grp_rows = 0) ---------------------------------
   std::vector<int64_t> grp_ptr(1, 0);
   std::vector<int32_t> grp_item, grp_rows;
+  T->n_subwarp = 0;
   for (int64_t q = 0; q < n;) {
-    if (off_count[order[q]] > kLongRow) {
+    const int c0 = cls(order[q]);
+    const int32_t lv = level[order[q]];
+    if (c0 == 2) {
       const int64_t w = (off_count[order[q]] + 31) / 32;
       grp_item.push_back((int32_t)q); grp_rows.push_back(0);
       grp_ptr.push_back(grp_ptr.back() + w * 32);
       ++T->n_long;
       ++q;
+    } else if (c0 == 1) {
+      int cnt = 0;
+      int32_t w = 0;
+      while (q + cnt < n && cnt < 4 && cls(order[q + cnt]) == 1 && level[order[q + cnt]] == lv) {
+        w = std::max(w, (off_count[order[q + cnt]] + 7) / 8);
+        ++cnt;
+      }
+      grp_item.push_back((int32_t)q); grp_rows.push_back(-cnt);
+      grp_ptr.push_back(grp_ptr.back() + (int64_t)w * 32);
+      ++T->n_subwarp;
+      q += cnt;
     } else {
       // a chunk never spans two levels: its rows are independent of each other, so the lanes of
       // a warp never wait for one another (the one-CTA kernel relies on it)
       int cnt = 0;
       int32_t w = 0;
-      const int32_t lv = level[order[q]];
-      while (q + cnt < n && cnt < 32 && off_count[order[q + cnt]] <= kLongRow && level[order[q + cnt]] == lv) {
+      while (q + cnt < n && cnt < 32 && cls(order[q + cnt]) == 0 && level[order[q + cnt]] == lv) {
         w = std::max(w, off_count[order[q + cnt]]);
         ++cnt;
       }
@@ -411,7 +442,7 @@ extern "C" int psb_trsv_create(int64_t n, const int32_t* h_rowptr, const int32_t
   int64_t nnz_off = 0;
   std::vector<std::pair<int32_t, int32_t>> deps;
   for (int g = 0; g < T->n_groups; ++g) {
-    const int nrows = grp_rows[g] == 0 ? 1 : grp_rows[g];
+    const int nrows = grp_rows[g] == 0 ? 1 : std::abs(grp_rows[g]);
     const int64_t width = (grp_ptr[g + 1] - grp_ptr[g]) / 32;
     for (int l = 0; l < nrows; ++l) {
       const int64_t q = grp_item[g] + l;
@@ -433,8 +464,10 @@ extern "C" int psb_trsv_create(int64_t n, const int32_t* h_rowptr, const int32_t
         const int32_t p = dp.second;
         // short rows: lane l, right-aligned (the row's last entry in the chunk's last entry row);
         // long row: entry k spread as (k / 32, k % 32)
+        // medium row l of a sub-warp chunk: entry k on lane 8 l + k % 8, entry row k / 8
         const int64_t pos = grp_rows[g] == 0 ? grp_ptr[g] + k
-                                             : grp_ptr[g] + (int64_t)(width - (int64_t)deps.size() + k) * 32 + l;
+                          : grp_rows[g] < 0 ? grp_ptr[g] + (int64_t)(k / 8) * 32 + 8 * l + (k % 8)
+                                            : grp_ptr[g] + (int64_t)(width - (int64_t)deps.size() + k) * 32 + l;
         cols[pos] = h_colind[p];
         vals[pos] = h_vals[p];
         ++k; ++nnz_off;
@@ -473,7 +506,7 @@ extern "C" int psb_trsv_create(int64_t n, const int32_t* h_rowptr, const int32_t
       const int nrows = grp_rows[g] == 0 ? 1 : grp_rows[g];
       const int64_t width = (grp_ptr[g + 1] - grp_ptr[g]) / 32;
       int has_far = 0;
-      for (int l = 0; l < nrows; ++l) {
+      for (int l = 0; l < nrows && T->n_subwarp == 0; ++l) {   // sub-warp chunks: grid kernel only
         const int64_t q = grp_item[g] + l;
         for (int64_t k = 0; k < (grp_rows[g] == 0 ? width * 32 : width); ++k) {
           const int64_t at = grp_rows[g] == 0 ? grp_ptr[g] + k : grp_ptr[g] + k * 32 + l;
@@ -488,7 +521,7 @@ extern "C" int psb_trsv_create(int64_t n, const int32_t* h_rowptr, const int32_t
       wmeta[4 * (size_t)g + 0] = (int32_t)(uint32_t)(grp_ptr[g] & 0xffffffffll);
       wmeta[4 * (size_t)g + 1] = (int32_t)(grp_ptr[g] >> 32);
       wmeta[4 * (size_t)g + 2] = grp_item[g];
-      wmeta[4 * (size_t)g + 3] = (int32_t)(grp_rows[g] | (has_far << 6) | (width << 7));
+      wmeta[4 * (size_t)g + 3] = (int32_t)(std::max(grp_rows[g], 0) | (has_far << 6) | (width << 7));
     }
   }
   // One CTA wins while the solve is bound by the latency of the dependency chain and a level has
@@ -498,7 +531,8 @@ extern "C" int psb_trsv_create(int64_t n, const int32_t* h_rowptr, const int32_t
   // Thresholds measured on B200 (profiles/round1d_trsv.md, round1g_cluster.md).
   {
     const bool local = (double)T->n_far <= 0.02 * (double)std::max<int64_t>(T->nnz_off, 1);
-    if (!local) T->kernel = PSB_TRSV_GRID;
+    if (T->n_subwarp > 0) { T->cluster_ok = 0; T->cta_ok = 0; }
+    if (!local || T->n_subwarp > 0) T->kernel = PSB_TRSV_GRID;
     else if (cpl <= kTrsvCtaMaxChunksPerLevel) T->kernel = PSB_TRSV_CTA;
     else if (cluster_cand) T->kernel = PSB_TRSV_CLUSTER;
     else T->kernel = PSB_TRSV_GRID;
@@ -557,6 +591,8 @@ extern "C" int psb_trsv_set_kernel(psb_trsv_t T, int kernel) {
   PSB_REQUIRE(kernel >= -1 && kernel <= PSB_TRSV_CLUSTER, PSB_ERR_ARG, "psb_trsv_set_kernel: unknown kernel");
   PSB_REQUIRE(kernel != PSB_TRSV_CLUSTER || T->cluster_ok, PSB_ERR_UNSUPP,
               "psb_trsv_set_kernel: this factor was not analysed for the cluster kernel");
+  PSB_REQUIRE(kernel != PSB_TRSV_CTA || T->cta_ok, PSB_ERR_UNSUPP,
+              "psb_trsv_set_kernel: this factor has wide levels packed for the grid kernel (8 lanes per row)");
   T->forced_kernel = kernel;
   return PSB_OK;
 }

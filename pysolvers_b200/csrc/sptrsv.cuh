@@ -10,6 +10,8 @@ struct psb_trsv {
   int n_levels = 0;
   int n_groups = 0;                   // work chunks (32 short rows, or one long row per warp)
   int n_long = 0;                     // rows handled by a whole warp
+  int n_subwarp = 0;                  // chunks of up to 4 rows on 8 lanes each (wide levels: grid kernel only)
+  int cta_ok = 1;                     // the packing can be run by the one-CTA kernel
   // host copies kept for inspection / bit-exact tests
   std::vector<int32_t> h_level_ptr;   // n_levels + 1
   std::vector<int32_t> h_level_rows;  // n, level-major, ascending inside a level
@@ -19,7 +21,7 @@ struct psb_trsv {
   double*  d_diag = nullptr;      // [n]           1 / diagonal of item q (1 for unit_diag)
   int64_t* d_grp_ptr = nullptr;   // [n_groups+1]  start of chunk g in cols/vals
   int32_t* d_grp_item = nullptr;  // [n_groups]    first item of chunk g
-  int32_t* d_grp_rows = nullptr;  // [n_groups]    rows in the chunk (1..32), or 0 = one long row
+  int32_t* d_grp_rows = nullptr;  // [n_groups]    rows in the chunk (1..32), 0 = one long row, -r = r rows of 8 lanes each
   int32_t* d_row_cnt = nullptr;   // [n]           off-diagonal entries of item q
   int32_t* d_cols = nullptr;      // [nnz_packed]  short rows: lane l of chunk g holds its row RIGHT-aligned, entry k of
                                   //               cnt at grp_ptr[g] + 32 (width - cnt + k) + l; -1 = padding (in front)

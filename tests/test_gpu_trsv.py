@@ -101,8 +101,11 @@ def _both_kernels(T, lower, unit, v):
     return dT, out['cta']
 
 
-def test_both_kernels_bit_identical(cuda):
+def test_both_kernels_bit_identical(cuda, monkeypatch):
     from oracle import precond
+    # one packing for all three kernels: without the grid-only 8-lanes-per-row chunks that factors with
+    # wide levels get by default (test_wide_levels_subwarp_rows covers those)
+    monkeypatch.setenv('PSB_TRSV_NO_SUBWARP', '1')
     rng = np.random.default_rng(5)
     cases = []
     for m in (24, 140):          # 140^2 = 19 600 rows: the window wraps around
@@ -142,6 +145,41 @@ def test_both_kernels_bit_identical(cuda):
     from pysolvers_b200.device import DeviceTrsv
     i2 = DeviceTrsv(band, lower=True).info2()
     assert i2['n_far'] > 0 and i2['max_dist'] >= 15000
+
+
+def test_wide_levels_subwarp_rows(cuda):
+    """Factors with WIDE levels and medium / long rows (the leading blocks of the AMG coarse LU factors):
+    the analysis packs them for the grid kernel with a thread per row up to 8 entries, 8 lanes per row up
+    to 64, a warp per row beyond.  Against scipy to rounding, deterministic, and -- with the sub-warp
+    classes switched off (thread per row up to 32 entries) -- equal to the old packing to rounding."""
+    from pysolvers_b200.device import DeviceTrsv, to_device
+    rng = np.random.default_rng(17)
+    n_lev, per = 24, 2500
+    n = n_lev * per
+    rows, cols, vals = [], [], []
+    for i in range(per, n):
+        lv = i // per
+        k = int(rng.choice([3, 7, 12, 30, 50, 64, 65, 150, 400], p=[.2, .15, .15, .15, .1, .05, .05, .1, .05]))
+        c = rng.choice(lv * per, size=min(k, lv * per), replace=False)
+        c[0] = (lv - 1) * per + int(rng.integers(per))         # at least one dependency on the previous level
+        c = np.unique(c)
+        rows.append(np.full(c.size, i)); cols.append(c); vals.append(rng.standard_normal(c.size) / (4.0 * c.size))
+    L = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n)) \
+        + sp.diags(rng.random(n) + 1.0)
+    L = L.tocsr()
+    v = rng.standard_normal(n)
+    for T, lower in ((L, True), (L.T.tocsr(), False)):
+        dT = DeviceTrsv(T, lower=lower)
+        info = dT.info()
+        assert info['levels'] == n_lev and dT.info2()['kernel'] == 'grid'
+        x1 = dT.solve(to_device(v)).cpu().numpy()
+        x2 = dT.solve(to_device(v)).cpu().numpy()
+        dT.check()
+        assert np.array_equal(x1, x2)
+        ref = spla.spsolve_triangular(T, v, lower=lower)
+        assert np.linalg.norm(x1 - ref) <= 1e-12 * np.linalg.norm(ref)
+        with pytest.raises(Exception):
+            dT.set_kernel('cta')                                 # 8-lanes-per-row chunks are the grid kernel's format
 
 
 def test_ic_apply_vs_reference_golden(cuda, golden):

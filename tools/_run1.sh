@@ -1,6 +1,6 @@
-export PSB_BENCH_SKIP_IC=1 PSB_BENCH_SKIP_C4=1 PSB_BENCH_SKIP_PARITY=1 PSB_CPU_ITERS=4
-python bench.py --steps 2 --warmup 3 > gpurun_out/r2p_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2p_launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/r2p_ncu1.log 2>&1
-python bench.py --steps 2 --warmup 3 > gpurun_out/r2p_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:pcg_mega -s 1 -c 1 -o gpurun_out/r2p_prof python bench.py --steps 2 --warmup 3 > gpurun_out/r2p_ncu2.log 2>&1
-tail -c 400 gpurun_out/r2p_plain.log; tail -3 gpurun_out/r2p_ncu2.log; ls -la gpurun_out/r2p_prof.ncu-rep
+python -m pytest tests/test_gpu_trsv.py tests/test_gpu_amg.py tests/test_gpu_gmres.py -x -q > gpurun_out/r2q_tests.log 2>&1; tail -4 gpurun_out/r2q_tests.log | cut -c1-300
+python tools/amg_profile.py 512 2> gpurun_out/r2q_amg512.err | tee gpurun_out/r2q_amg512.json
+python tools/amg_profile.py 2048 2> gpurun_out/r2q_amg2048.err | tee gpurun_out/r2q_amg2048.json
+PSB_TRSV_NO_SUBWARP=1 python tools/amg_profile.py 2048 2>/dev/null | cut -c1-300
+python tools/config_bench.py c2 2>/dev/null | python -c "
+import json,sys; d=json.load(sys.stdin)['c2']; print([(x['config'][-22:], x['iters'], x['ref_iters'], round(1e3*x['gpu_ilut_apply_s'],3), x['hist_max_rel_err']) for x in d])"
