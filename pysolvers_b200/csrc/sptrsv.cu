@@ -378,11 +378,16 @@ extern "C" int psb_trsv_create(int64_t n, const int32_t* h_rowptr, const int32_t
   // walks its entries four L2 round trips at a time, so a 32-entry row on one lane is 8 trips deep and
   // every level waited for its longest thread-per-row row (measured 4 - 5 us per level,
   // profiles/round2_amg.md).  There: thread per row up to 8 entries, EIGHT lanes per row (four rows
-  // per warp) up to 64, warp per row beyond -- at most two trips per row.
+  // per warp) up to 128, warp per row beyond (thresholds swept on the Bratu-2048^2 coarse factors:
+  // (8, 128) 0.89 ms per coarse solve, (8, 64) 0.92, (4, 32) 1.02, thread per row up to 32: 1.02).
   const bool wide = (double)n / 32.0 / std::max(T->n_levels, 1) > kTrsvClusterMaxChunksPerLevel &&
                     getenv("PSB_TRSV_NO_SUBWARP") == nullptr;
-  const int kShortRow = wide ? 8 : 32;         // thread per row up to this many off-diagonal entries
-  const int kLongRow = wide ? 64 : 32;         // more than this -> warp per row; in between: 8 lanes per row
+  int kShortRow = wide ? 8 : 32;               // thread per row up to this many off-diagonal entries
+  int kLongRow = wide ? 128 : 32;              // more than this -> warp per row; in between: 8 lanes per row
+  if (wide) {                                  // A/B measurements
+    if (const char* e = getenv("PSB_TRSV_SHORT")) kShortRow = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("PSB_TRSV_LONG")) kLongRow = std::max(kShortRow, atoi(e));
+  }
   auto cls = [&](int32_t i) { return off_count[i] <= kShortRow ? 0 : (off_count[i] <= kLongRow ? 1 : 2); };
   // ---- processing order: inside a level the short rows first, then the medium, then the long ones
   std::vector<int32_t> order((size_t)n);

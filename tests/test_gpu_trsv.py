@@ -150,7 +150,7 @@ def test_both_kernels_bit_identical(cuda, monkeypatch):
 def test_wide_levels_subwarp_rows(cuda):
     """Factors with WIDE levels and medium / long rows (the leading blocks of the AMG coarse LU factors):
     the analysis packs them for the grid kernel with a thread per row up to 8 entries, 8 lanes per row up
-    to 64, a warp per row beyond.  Against scipy to rounding, deterministic, and -- with the sub-warp
+    to 128, a warp per row beyond.  Against scipy to rounding, deterministic, and -- with the sub-warp
     classes switched off (thread per row up to 32 entries) -- equal to the old packing to rounding."""
     from pysolvers_b200.device import DeviceTrsv, to_device
     rng = np.random.default_rng(17)

@@ -37,9 +37,33 @@ def time_gpu(fn, reps=5, warm=2):
     return e0.elapsed_time(e1) / reps * 1e-3
 
 
+def pack_sweep(m):
+    """coarse LU solve with different row-class thresholds of the wide-level packing (A/B)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from pysolvers_b200.Linear import amg_setup
+    from pysolvers_b200.device import DeviceSplitLU
+    func = FDBratu2D(m=m)
+    J = sp.csr_matrix(func.evalJ(func.initialU()))
+    ops, _, _ = amg_setup.build_hierarchy(J, 2)
+    lu = spla.splu(sp.csc_matrix(ops[0]), permc_spec='MMD_AT_PLUS_A')
+    cv = to_device(np.ones(ops[0].shape[0]))
+    cz = torch.empty_like(cv)
+    out = {}
+    for short, long_ in ((8, 64), (4, 32), (8, 32), (4, 64), (8, 128), (16, 64), (2, 32)):
+        os.environ['PSB_TRSV_SHORT'], os.environ['PSB_TRSV_LONG'] = str(short), str(long_)
+        c = DeviceSplitLU(lu)
+        out['short%d_long%d' % (short, long_)] = round(1e3 * time_gpu(lambda: c.apply(cv, cz)), 4)
+        del c
+    print(json.dumps(out))
+    return 0
+
+
 def main():
     m = int(sys.argv[1]) if len(sys.argv) > 1 else 512
     profile = '--profile' in sys.argv
+    if '--pack-sweep' in sys.argv:
+        return pack_sweep(m)
     func = FDBratu2D(m=m)
     J = func.evalJ(func.initialU())
     F = func.evalF(func.initialU())
