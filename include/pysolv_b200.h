@@ -152,7 +152,9 @@ int psb_trsv_set_kernel(psb_trsv_t T, int kernel);
 /* Debugging aid of the one-CTA kernel: when d_trace (device, 12 * groups int64) is not NULL every
  * chunk records clock64 at its start, at its first missing dependency, after sleeping, at its
  * last batch of entries, when its last dependency arrived and after its store, plus the entry
- * index of the first miss and the entries per lane. */
+ * index of the first miss and the entries per lane.  With the grid kernel the buffer needs
+ * 3 * groups int64 and every chunk records {%globaltimer when claimed, when done, first item}
+ * (items are level-major: psb_trsv_get_levels gives the level boundaries). */
 int psb_trsv_set_trace(psb_trsv_t T, long long* d_trace);
 /* Copies out the level sets (host arrays of levels+1 and n int32): level of a row
  * = 1 + max level of its dependencies; rows level-major, ascending in a level. */

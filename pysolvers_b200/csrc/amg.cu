@@ -196,7 +196,8 @@ struct AmgPrec : psb_prec {
 
   // V-cycle from level l: x (in/out) may end up in either of the two buffers; `x`/`spare`
   // are updated so that x names the result
-  int run_level(int l, const double* f, double*& x, double*& spare, cudaStream_t s) {
+  // `pre_done`: sweeps of the pre-smoothing that the caller has already applied to x
+  int run_level(int l, const double* f, double*& x, double*& spare, cudaStream_t s, int pre_done = 0) {
     const int* skip = &st->skip;
     AmgLevel& L = lev[l];
     if (l == 0) {                                                             // VCycleManager.py:34-37
@@ -206,7 +207,7 @@ struct AmgPrec : psb_prec {
       }
       return coarse->apply(f, x, skip, s);
     }
-    int rc = smooth(l, f, x, spare, nu_pre, s);                               // :42
+    int rc = smooth(l, f, x, spare, nu_pre - pre_done, s);                    // :42
     if (rc != PSB_OK) return rc;
     EpiArgs ea; ea.f = f;
     rc = L.A.launch(EPI_RESID, x, L.r, ea, skip, s);                          // :45
@@ -253,9 +254,14 @@ struct AmgPrec : psb_prec {
       PSB_LAUNCH_CHECK();
     }
     const int* skip = &st->skip;
+    // The residual that ends cycle k and the first Jacobi sweep of cycle k + 1 need the same
+    // r = b - A x: the residual kernel forms that sweep as well (into the second buffer) and the next
+    // cycle starts one sweep in -- a pass over the fine matrix less per cycle, same arithmetic.
+    const bool fuse_sweep = top > 0 && smoother == PSB_SMOOTH_JACOBI && nu_pre >= 1;
+    bool presmoothed = false;
     for (int k = 0; k < maxiter; ++k) {
-      double* x = home;
-      double* spare = F.x2;
+      double* x = presmoothed ? F.x2 : home;
+      double* spare = presmoothed ? home : F.x2;
       int rc;
       if (top == 0) {
         // single level: the "cycle" is the direct solve
@@ -263,9 +269,10 @@ struct AmgPrec : psb_prec {
         if (rc != PSB_OK) return rc;
         x = F.x2; spare = home;
       } else {
-        rc = run_level(top, b, x, spare, s);
+        rc = run_level(top, b, x, spare, s, presmoothed ? 1 : 0);
         if (rc != PSB_OK) return rc;
       }
+      presmoothed = false;
       if (x != home) {                        // odd number of ping-pong sweeps: bring x home
         amg_copy_kernel<<<grid, kBlock, 0, s>>>(home, x, F.n, skip);
         PSB_LAUNCH_CHECK();
@@ -274,6 +281,10 @@ struct AmgPrec : psb_prec {
       // r = b - A x with ||r||, the history entry and the strict '<' test done by the kernel's
       // last CTA (VCycleSolver.py:84-91): no separate pass over r
       EpiArgs ea; ea.f = b;
+      if (fuse_sweep && k + 1 < maxiter) {
+        ea.jac_out = F.x2; ea.dinv = F.dinv; ea.omega = omega;
+        presmoothed = true;
+      }
       if (dist) {
         ea.dot = &st->rr;                     // this rank's part; finished after the all-reduce
         rc = F.A.launch(EPI_RESID_NORM, home, F.r, ea, skip, s);

@@ -397,6 +397,7 @@ spmv_merge_kernel(const psb_csr A, const double* x, double* __restrict__ ysum, i
                   double* __restrict__ carry_val, const int* __restrict__ d_skip) {
   __shared__ int s_end[kMergeTile + 2];
   __shared__ double s_acc[kMergeTile + 2];
+  __shared__ double s_prod[kMergeTile];                      // the tile's products, staged with coalesced loads
   __shared__ long long s_coord[4];
   __shared__ int s_key[kBlock];
   __shared__ double s_val[kBlock];
@@ -414,11 +415,17 @@ spmv_merge_kernel(const psb_csr A, const double* x, double* __restrict__ ysum, i
     }
     __syncthreads();
     const int64_t r0 = s_coord[0], r1 = s_coord[2];
+    const int64_t k0 = s_coord[1];
+    const int n_tk = (int)(s_coord[3] - k0);                  // entries of the tile
     const int n_tr = (int)(r1 - r0) + 1;                      // rows touched; the last one may be partial
     for (int i = tid; i < n_tr; i += kBlock) {
       s_end[i] = r0 + i < A.n_rows ? row_end[r0 + i] : INT32_MAX;
       s_acc[i] = 0.0;
     }
+    // a thread's segment is kMergeItems CONSECUTIVE entries: read straight from global memory that is
+    // a 56-byte stride between lanes (measured 1 TB/s); staged here, consecutive lanes read
+    // consecutive entries
+    for (int i = tid; i < n_tk; i += kBlock) s_prod[i] = A.vals[k0 + i] * ld_ca(x + A.colind[k0 + i]);
     __syncthreads();
     // this thread's segment
     const int64_t d = min(d0 + (int64_t)tid * kMergeItems, d1);
@@ -433,7 +440,7 @@ spmv_merge_kernel(const psb_csr A, const double* x, double* __restrict__ ysum, i
     double acc = 0.0;
     for (int64_t it = d; it < de; ++it) {
       if (k < (int64_t)s_end[r - r0]) {
-        acc += A.vals[k] * ld_ca(x + A.colind[k]);            // stored order inside the segment
+        acc += s_prod[k - k0];                                 // stored order inside the segment
         ++k;
       } else {
         s_acc[r - r0] = acc;                                   // the row ends here: its tail part
@@ -640,8 +647,13 @@ static void choose_kernel(psb_csr* A) {
   A->vec_width = w;
   A->kind = PSB_SPMV_VECTOR; A->rpt = 1;
   // skewed histogram: a few rows far longer than the rest (>= 512 entries and >= 16 x the mean) would
-  // serialise a thread-per-row or sub-warp-per-row kernel -> split the work, not the rows
-  if (A->max_row >= 512 && (double)A->max_row >= 16.0 * std::max(mean, 2.0) && merge_alloc(A) == PSB_OK) {
+  // serialise a thread-per-row or sub-warp-per-row kernel -> split the work, not the rows.  Only when
+  // the longest row is a visible share of the matrix (>= nnz / 512): the sub-warp kernel walks a row at
+  // ~0.1 us per 16 entries, so shorter rows hide behind the streaming of the rest, and the merge
+  // kernels run at ~40 % of its bandwidth (U12 block of the Bratu-2048^2 coarse LU, 691 200 x 8 192,
+  // 10.9 M entries: VECTOR 63 us, MERGE 114 us)
+  if (A->max_row >= 512 && (double)A->max_row >= 16.0 * std::max(mean, 2.0) &&
+      (int64_t)A->max_row * 512 >= A->nnz && merge_alloc(A) == PSB_OK) {
     A->kind = PSB_SPMV_MERGE;
     return;
   }

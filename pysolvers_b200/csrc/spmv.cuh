@@ -67,6 +67,10 @@ struct EpiArgs {
   // RESID_NORM: the last CTA ends the V-cycle -- ||r||, history, strict '<' test (VCycleSolver.py:87-91)
   AmgState*     amg_state = nullptr;
   double*       amg_hist = nullptr;
+  // RESID_NORM: when not null, the first Jacobi sweep of the NEXT cycle is formed from the residual
+  // just computed, jac_out = x + omega * dinv .* r (the arithmetic of EPI_JACOBI, which would
+  // recompute the same r = f - A x with another pass over the matrix)
+  double*       jac_out = nullptr;
   // DOT_PUP, persistent PCG: deferred solution update xsol += alpha_prev * pold on the tile's own rows
   double*       xsol = nullptr;
   double        alpha_prev = 0.0;

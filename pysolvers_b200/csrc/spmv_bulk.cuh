@@ -50,8 +50,11 @@ __device__ __forceinline__ EpiRow epi_preload(int64_t row, const double* x, cons
   o.a = 0.0; o.b = 0.0; o.c = 0.0;
   if (EPI == EPI_DOT) {
     o.a = __ldg(x + row);
-  } else if (EPI == EPI_RESID || EPI == EPI_RESID_NORM) {
+  } else if (EPI == EPI_RESID) {
     o.a = ea.f[row];
+  } else if (EPI == EPI_RESID_NORM) {
+    o.a = ea.f[row];
+    if (ea.jac_out != nullptr) { o.b = ea.dinv[row]; o.c = __ldg(x + row); }
   } else if (EPI == EPI_ADD) {
     o.a = y[row];
   } else if (EPI == EPI_JACOBI) {
@@ -74,6 +77,11 @@ __device__ __forceinline__ void epi_finish(int64_t row, double sum, const EpiRow
     const double r = o.a - sum;
     y[row] = r;
     acc += r * r;
+    if (ea.jac_out != nullptr) {                 // next cycle's first Jacobi sweep, as EPI_JACOBI
+      double d = o.b * r;
+      if (ea.omega != 1.0) d = ea.omega * d;
+      ea.jac_out[row] = o.c + d;
+    }
   } else if (EPI == EPI_ADD) {
     y[row] = o.a + sum;
   } else if (EPI == EPI_JACOBI) {

@@ -84,7 +84,14 @@ struct TrsvView {
   unsigned int* counter;
   int* error;
   int unit_diag;
+  long long* trace;          // debugging (psb_trsv_set_trace): per chunk {claimed, done, first item}, null: off
 };
+
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ double ld_relaxed(const double* p) {
   double v;
@@ -95,6 +102,8 @@ __device__ __forceinline__ void st_relaxed(double* p, double v) {
   asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
 }
 
+// kTrace: %globaltimer stamps per chunk (tools/trsv_levels.py)
+template <bool kTrace>
 __global__ void __launch_bounds__(kBlock)
 trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
                   const int32_t* __restrict__ rhs_map, double* out2,
@@ -111,6 +120,7 @@ trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
     int len = (int)((T.grp_ptr[g + 1] - base) >> 5);           // entries per lane
     const int rows = T.grp_rows[g];                            // 0: one long row for the warp; < 0: -rows rows of 8 lanes
     const int item0 = T.grp_item[g];
+    if (kTrace && lane == 0) { T.trace[3 * (int64_t)g] = global_ns(); T.trace[3 * (int64_t)g + 2] = item0; }
     const bool is_sub = rows < 0;
     const bool is_long = rows <= 0;                            // lanes share rows: reduce before the store
     const bool owner = rows == 0 ? (lane == 0) : (is_sub ? ((lane & 7) == 0 && (lane >> 3) < -rows) : (lane < rows));
@@ -204,6 +214,7 @@ trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
         }
       }
     }
+    if (kTrace && lane == 0) T.trace[3 * (int64_t)g + 1] = global_ns();
   }
 }
 
@@ -237,7 +248,7 @@ int trsv_solve(const psb_trsv* T, const double* rhs, double* x, const int32_t* r
   PSB_LAUNCH_CHECK();
   static thread_local int per_sm = 0;
   if (per_sm == 0) {
-    PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_solve_kernel, kBlock, 0));
+    PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_solve_kernel<false>, kBlock, 0));
     if (per_sm < 1) per_sm = 1;
   }
   // Only the warps working a few dozen levels ahead of the wavefront do useful work; the rest
@@ -248,8 +259,9 @@ int trsv_solve(const psb_trsv* T, const double* rhs, double* x, const int32_t* r
   int64_t warps_needed = std::min<int64_t>(T->n_groups, chunks_per_level * kLookahead);
   int64_t grid = std::min<int64_t>((int64_t)per_sm * sm_count(), (warps_needed + kWarps - 1) / kWarps);
   TrsvView V{T->n, T->n_groups, T->d_order, T->d_diag, T->d_grp_ptr, T->d_grp_item, T->d_grp_rows,
-             T->d_cols, T->d_vals, T->d_row_cnt, T->d_counter, T->d_error, T->unit_diag};
-  trsv_solve_kernel<<<(int)std::max<int64_t>(grid, 1), kBlock, 0, st>>>(V, rhs, x, rhs_map, out2, out_map, d_skip);
+             T->d_cols, T->d_vals, T->d_row_cnt, T->d_counter, T->d_error, T->unit_diag, T->d_trace};
+  auto kern = T->d_trace != nullptr ? trsv_solve_kernel<true> : trsv_solve_kernel<false>;
+  kern<<<(int)std::max<int64_t>(grid, 1), kBlock, 0, st>>>(V, rhs, x, rhs_map, out2, out_map, d_skip);
   PSB_LAUNCH_CHECK();
   return PSB_OK;
 }

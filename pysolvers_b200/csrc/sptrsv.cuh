@@ -37,7 +37,7 @@ struct psb_trsv {
   int64_t max_dist = 0;           // largest position distance of a dependency
   int cluster_ok = 0;             // the window data respect the (larger) reuse slack of the cluster kernel
   int kernel = 0;                 // PSB_TRSV_GRID / PSB_TRSV_CTA / PSB_TRSV_CLUSTER chosen by the analysis
-  long long* d_trace = nullptr;   // not owned: psb_trsv_set_trace (debugging the one-CTA kernel)
+  long long* d_trace = nullptr;   // not owned: psb_trsv_set_trace (debugging: per-chunk time stamps)
   int forced_kernel = -1;         // psb_trsv_set_kernel: >= 0 overrides the analysis
 };
 

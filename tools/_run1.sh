@@ -1,4 +1,4 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/r2s_tests.log 2>&1; tail -3 gpurun_out/r2s_tests.log | cut -c1-300
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-python bench.py > gpurun_out/r2s_bench.json 2> gpurun_out/r2s_bench.err; tail -c 300 gpurun_out/r2s_bench.json; echo; tail -2 gpurun_out/r2s_bench.err
-python bench.py --impl reference > gpurun_out/r2s_bench_ref.json 2> gpurun_out/r2s_bench_ref.err; cut -c1-400 gpurun_out/r2s_bench_ref.json
+#!/bin/bash
+timeout 900 python -m pytest tests/test_gpu_amg.py tests/test_gpu_spmv.py tests/test_gpu_trsv.py -x -q -m gpu 2>&1 | tail -3
+timeout 600 python tools/amg_profile.py 2048 > gpurun_out/amg2048_c.json 2>gpurun_out/amg2048_c.err; cat gpurun_out/amg2048_c.json
+timeout 600 python tools/amg_profile.py 512 2>/dev/null
