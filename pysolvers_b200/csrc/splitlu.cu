@@ -130,21 +130,50 @@ struct BlockDiag {
 
 // y = blockdiag(B) x: row r of a collapsed supernode starting at line row0[r] reads x[row0 + c] for
 // c in [c_lo, c_hi) with the weights vals[off + c - c_lo]; rows outside a supernode copy.
-// Two kernels: a thread per row for the short rows (sequential sum), and a WARP per row for the
+// Two row classes: a thread per row for the short rows (sequential sum), and a WARP per row for the
 // rows of >= kLongRow entries (the large supernodes near the top of the elimination tree, hundreds
 // of lines: with a thread per row a few hundred uncoalesced entries held the stage for 120 us;
 // listed at set-up time, coalesced 256-byte reads, four in flight per lane, fixed-order reduction).
 constexpr int kLongRow = 32;
 
+// One launch: the first `g_long` CTAs take the listed long rows (a warp each), the others the short
+// rows (a thread each) -- the two parts are independent and overlap.
 __global__ void __launch_bounds__(kBlock)
-blockdiag_kernel(int64_t n, const int32_t* __restrict__ row0, const int32_t* __restrict__ c_lo,
+blockdiag_kernel(int64_t n, int g_long, int64_t n_long, const int32_t* __restrict__ long_rows,
+                 const int32_t* __restrict__ row0, const int32_t* __restrict__ c_lo,
                  const int32_t* __restrict__ c_hi, const int64_t* __restrict__ off,
                  const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
                  const int* d_skip) {
   if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
-  for (int64_t r = blockIdx.x * (int64_t)kBlock + threadIdx.x; r < n; r += (int64_t)gridDim.x * kBlock) {
+  if ((int)blockIdx.x < g_long) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)g_long * kBlock) >> 5;
+    for (int64_t i = warp; i < n_long; i += n_warps) {
+      const int r = long_rows[i];
+      const int lo = c_lo[r], hi = c_hi[r];
+      const double* w = vals + off[r] - lo;
+      const double* xv = x + row0[r];
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      for (int c = lo + lane; c < hi; c += 128) {
+        const int c1 = c + 32, c2 = c + 64, c3 = c + 96;
+        const double w0 = w[c], x0 = xv[c];
+        const double w1 = c1 < hi ? w[c1] : 0.0, x1 = c1 < hi ? xv[c1] : 0.0;
+        const double w2 = c2 < hi ? w[c2] : 0.0, x2 = c2 < hi ? xv[c2] : 0.0;
+        const double w3 = c3 < hi ? w[c3] : 0.0, x3 = c3 < hi ? xv[c3] : 0.0;
+        a0 += w0 * x0; a1 += w1 * x1; a2 += w2 * x2; a3 += w3 * x3;
+      }
+      double a = (a0 + a1) + (a2 + a3);
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+      if (lane == 0) y[r] = a;
+    }
+    return;
+  }
+  const int64_t g_short = (int64_t)gridDim.x - g_long;
+  for (int64_t r = (blockIdx.x - g_long) * (int64_t)kBlock + threadIdx.x; r < n; r += g_short * kBlock) {
     const int lo = c_lo[r], hi = c_hi[r];
-    if (hi - lo >= kLongRow) continue;                   // blockdiag_long_kernel
+    if (hi - lo >= kLongRow) continue;                   // a listed long row
     if (hi <= lo) { y[r] = x[r]; continue; }
     const double* xv = x + row0[r];
     const double* w = vals + off[r];
@@ -154,47 +183,14 @@ blockdiag_kernel(int64_t n, const int32_t* __restrict__ row0, const int32_t* __r
   }
 }
 
-__global__ void __launch_bounds__(kBlock)
-blockdiag_long_kernel(int64_t n_long, const int32_t* __restrict__ long_rows, const int32_t* __restrict__ row0,
-                      const int32_t* __restrict__ c_lo, const int32_t* __restrict__ c_hi,
-                      const int64_t* __restrict__ off, const double* __restrict__ vals,
-                      const double* __restrict__ x, double* __restrict__ y, const int* d_skip) {
-  if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * kBlock) >> 5;
-  for (int64_t i = warp; i < n_long; i += n_warps) {
-    const int r = long_rows[i];
-    const int lo = c_lo[r], hi = c_hi[r];
-    const double* w = vals + off[r] - lo;
-    const double* xv = x + row0[r];
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    for (int c = lo + lane; c < hi; c += 128) {
-      const int c1 = c + 32, c2 = c + 64, c3 = c + 96;
-      const double w0 = w[c], x0 = xv[c];
-      const double w1 = c1 < hi ? w[c1] : 0.0, x1 = c1 < hi ? xv[c1] : 0.0;
-      const double w2 = c2 < hi ? w[c2] : 0.0, x2 = c2 < hi ? xv[c2] : 0.0;
-      const double w3 = c3 < hi ? w[c3] : 0.0, x3 = c3 < hi ? xv[c3] : 0.0;
-      a0 += w0 * x0; a1 += w1 * x1; a2 += w2 * x2; a3 += w3 * x3;
-    }
-    double a = (a0 + a1) + (a2 + a3);
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
-    if (lane == 0) y[r] = a;
-  }
-}
-
 static int blockdiag_apply(const BlockDiag& B, int64_t n, const double* x, double* y, const int* d_skip,
                            cudaStream_t st) {
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + kBlock - 1) / kBlock, (int64_t)sm_count() * 8));
-  blockdiag_kernel<<<grid, kBlock, 0, st>>>(n, B.row0, B.c_lo, B.c_hi, B.off, B.vals, x, y, d_skip);
+  const int g_short = (int)std::max<int64_t>(1, std::min<int64_t>((n + kBlock - 1) / kBlock, (int64_t)sm_count() * 6));
+  const int g_long = B.n_long > 0
+      ? (int)std::max<int64_t>(1, std::min<int64_t>((B.n_long * 32 + kBlock - 1) / kBlock, (int64_t)sm_count() * 2)) : 0;
+  blockdiag_kernel<<<g_long + g_short, kBlock, 0, st>>>(n, g_long, B.n_long, B.long_rows, B.row0, B.c_lo, B.c_hi,
+                                                       B.off, B.vals, x, y, d_skip);
   PSB_LAUNCH_CHECK();
-  if (B.n_long > 0) {
-    const int64_t warps = B.n_long;
-    const int g2 = (int)std::max<int64_t>(1, std::min<int64_t>((warps * 32 + kBlock - 1) / kBlock, (int64_t)sm_count() * 8));
-    blockdiag_long_kernel<<<g2, kBlock, 0, st>>>(B.n_long, B.long_rows, B.row0, B.c_lo, B.c_hi, B.off, B.vals, x, y, d_skip);
-    PSB_LAUNCH_CHECK();
-  }
   return PSB_OK;
 }
 

@@ -82,6 +82,22 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return 0
+    if '--ops' in sys.argv:
+        # every operator of the hierarchy under each SpMV kind it supports (plain y = M x)
+        for name, M in (('A_fine', amg.A[-1]), ('R', amg.R[-1]), ('P', amg.P[-1])):
+            xin = torch.rand(M.shape[1], dtype=torch.float64, device='cuda')
+            yout = torch.empty(M.shape[0], dtype=torch.float64, device='cuda')
+            info = M.info()
+            r = dict(op=name, shape=list(M.shape), nnz=M.nnz, auto_kind=info['kind'], max_row=info['max_row'],
+                     MB=round((12 * M.nnz + 4 * M.shape[0] + 8 * M.shape[0] + 8 * M.shape[1]) / 1e6, 1))
+            for kind, kn in ((1, 'bulk'), (3, 'lsu'), (3 | 16, 'lsu512'), (2, 'vector'), (4, 'merge')):
+                try:
+                    M.set_kind(kind)
+                    r[kn + '_us'] = round(1e6 * time_gpu(lambda: M.matvec(xin, yout), reps=20), 1)
+                except Exception as e:
+                    r[kn + '_us'] = None
+            M.set_kind(info['kind'])
+            print(json.dumps(r), flush=True)
     l0 = nat.launch_count()
     amg.prec.apply(v, z)
     launches = nat.launch_count() - l0
