@@ -90,6 +90,12 @@ def main():
         out['tail%d' % tail] = dict(coarse_solve_ms=round(ms, 4), levels=list(c.levels()), dense_rows=[c.n2, c.n2U],
                                     rel_err_vs_superlu=err, cond=[float(v) for v in c.cond_dense])
         print(json.dumps({('tail%d' % tail): out['tail%d' % tail]}), flush=True)
+        if '--profile' in sys.argv:              # one coarse solve inside a profiler range (ncu --profile-from-start off)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            c.apply(cv, cz)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         if '--spmv' in sys.argv:
             b = torch.ones(c.n1, dtype=torch.float64, device='cuda')
             xo = torch.empty_like(b)
