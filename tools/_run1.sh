@@ -1,5 +1,5 @@
 #!/bin/bash
-PSB_TRSV_STAGE=1 timeout 900 python -m pytest tests/test_gpu_trsv.py tests/test_gpu_amg.py -x -q -m gpu 2>&1 | tail -2
-PSB_TRSV_STAGE=1 PSB_TRSV_KERNEL=grid timeout 900 python -m pytest tests/test_gpu_trsv.py -x -q -m gpu 2>&1 | tail -2
-timeout 600 python tools/trsv_levels.py 2048 --stage-ab > gpurun_out/trsv_stage2_2048.txt 2>&1
-grep '^{' gpurun_out/trsv_stage2_2048.txt | cut -c1-250
+python tools/amg_profile.py 2048 --profile > gpurun_out/plain_amg.log 2>&1 &&
+ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file gpurun_out/round2b_amg2048_launches.csv python tools/amg_profile.py 2048 --profile > gpurun_out/ncu_amg.log 2>&1
+tail -2 gpurun_out/ncu_amg.log; wc -l gpurun_out/round2b_amg2048_launches.csv
