@@ -1,5 +1,3 @@
 #!/bin/bash
-python tools/amg_profile.py 2048 --profile > gpurun_out/plain_amg.log 2>&1 &&
-ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
-    --log-file gpurun_out/round2b_amg2048_launches.csv python tools/amg_profile.py 2048 --profile > gpurun_out/ncu_amg.log 2>&1
-tail -2 gpurun_out/ncu_amg.log; wc -l gpurun_out/round2b_amg2048_launches.csv
+PSB_TRSV_STAGE=1 timeout 600 python tools/trsv_levels.py 2048 > gpurun_out/trsv_levels_2048_stage3.txt 2>&1
+grep -E "^(L11|U11)|^\{" gpurun_out/trsv_levels_2048_stage3.txt | cut -c1-200
