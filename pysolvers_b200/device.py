@@ -267,7 +267,8 @@ class DevicePrec:
 # coarse LU: 16 384 rows -> 65 levels, 1.30 ms per solve; 8 192 rows -> 82 levels, 1.16 ms).
 DENSE_TAIL = 8192
 COLLAPSE_MIN_LEVELS = 150     # collapse the supernodes of a sparse leading block only if it has this many levels
-COLLAPSE_MIN_ROWS = 8         # ... and only supernodes of at least this many rows (host cost against levels)
+COLLAPSE_MIN_ROWS = 4         # ... and only supernodes of at least this many rows (Bratu 2048^2 coarse LU: 8 -> 82
+                              # levels, 0.785 ms per solve; 4 -> 58 levels, 0.767 ms; 2 -> 56 levels, 0.767 ms; same host time)
 DENSE_TAIL_LARGE = int(os.environ.get('PSB_DENSE_TAIL_LARGE', '8192'))     # n >= DENSE_TAIL_LARGE_N
 DENSE_TAIL_LARGE_N = 300000
 # Guard of the explicitly inverted dense blocks: applying inv(T22) as a GEMV instead of a triangular

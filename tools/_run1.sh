@@ -1,3 +1,3 @@
 #!/bin/bash
-PSB_TRSV_STAGE=1 timeout 600 python tools/trsv_levels.py 2048 > gpurun_out/trsv_levels_2048_stage3.txt 2>&1
-grep -E "^(L11|U11)|^\{" gpurun_out/trsv_levels_2048_stage3.txt | cut -c1-200
+timeout 800 python tools/trsv_levels.py 2048 --smin 8,4,2 > gpurun_out/trsv_smin_2048.txt 2>&1
+grep -E "^(L11|U11)|^\{" gpurun_out/trsv_smin_2048.txt | cut -c1-260

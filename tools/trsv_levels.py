@@ -80,16 +80,22 @@ def main():
     cz = torch.empty_like(cv)
     ref = None
     out = {}
-    for tail in tails:
+    smins = [None]
+    if '--smin' in sys.argv:                     # smallest supernode that is collapsed (device.COLLAPSE_MIN_ROWS)
+        smins = [int(v) for v in sys.argv[sys.argv.index('--smin') + 1].split(',')]
+    import pysolvers_b200.device as dev
+    for tail, smin in [(t, sm) for t in tails for sm in smins]:
+        if smin is not None:
+            dev.COLLAPSE_MIN_ROWS = smin
         c = DeviceSplitLU(lu, tail=tail)
         ms = 1e3 * time_gpu(lambda: c.apply(cv, cz))
         z = cz.cpu().numpy()
         if ref is None:
             ref = lu.solve(np.ones(ops[0].shape[0]))
         err = float(np.abs(z - ref).max() / np.abs(ref).max())
-        out['tail%d' % tail] = dict(coarse_solve_ms=round(ms, 4), levels=list(c.levels()), dense_rows=[c.n2, c.n2U],
+        out['tail%d_smin%s' % (tail, smin)] = dict(coarse_solve_ms=round(ms, 4), levels=list(c.levels()), dense_rows=[c.n2, c.n2U],
                                     rel_err_vs_superlu=err, cond=[float(v) for v in c.cond_dense])
-        print(json.dumps({('tail%d' % tail): out['tail%d' % tail]}), flush=True)
+        print(json.dumps({('tail%d_smin%s' % (tail, smin)): out['tail%d_smin%s' % (tail, smin)]}), flush=True)
         if '--profile' in sys.argv:              # one coarse solve inside a profiler range (ncu --profile-from-start off)
             torch.cuda.synchronize()
             torch.cuda.profiler.start()
@@ -119,7 +125,7 @@ def main():
                 c.U12.set_kind(kind)
                 print(json.dumps({'U12_kind': kind, 'coarse_solve_ms': round(1e3 * time_gpu(lambda: c.apply(cv, cz)), 4)}), flush=True)
             c.U12.set_kind(auto)
-        if tail == tails[0] and '--no-table' not in sys.argv:
+        if tail == tails[0] and smin == smins[-1] and '--no-table' not in sys.argv:
             level_table(c.L11, 'L11', lambda: c.apply(cv, cz))
             level_table(c.U11, 'U11', lambda: c.apply(cv, cz))
         del c
