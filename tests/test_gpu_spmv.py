@@ -108,6 +108,36 @@ def test_merge_path_long_rows_and_epilogues(cuda):
     assert np.max(np.abs(out.cpu().numpy() - wantj) / (np.abs(wantj) + scale)) < 1e-13
 
 
+def test_kernel_choice_long_rows_in_a_large_matrix(cuda):
+    """The merge-path kind is for matrices in which the longest row is a visible share of the work
+    (>= nnz / 512).  A large block with rows of up to ~600 entries among short and empty ones (the U12
+    block of a coarse LU factor) stays on the sub-warp kernel, which is twice as fast there; both kinds
+    agree with scipy to rounding."""
+    from pysolvers_b200 import _native as nat
+    from pysolvers_b200.device import DeviceCSR, to_device
+    rng = np.random.default_rng(23)
+    n_rows, n_cols = 60000, 2048
+    lens = np.zeros(n_rows, dtype=np.int64)
+    busy = rng.random(n_rows) < 0.2                               # 80 % of the rows are empty
+    lens[busy] = rng.choice([4, 25, 120, 600], size=int(busy.sum()), p=[.4, .35, .2, .05])
+    indptr = np.concatenate([[0], np.cumsum(lens)])
+    indices = np.concatenate([np.sort(rng.choice(n_cols, size=k, replace=False)) for k in lens if k])
+    A = sp.csr_matrix((rng.standard_normal(indices.size), indices, indptr), shape=(n_rows, n_cols))
+    assert lens.max() >= 512 and lens.max() >= 16 * A.nnz / n_rows and lens.max() * 512 < A.nnz
+    dA = DeviceCSR(A)
+    assert dA.info()['kind'] != nat.SPMV_MERGE
+    x = rng.standard_normal(n_cols)
+    scale = np.abs(A) @ np.abs(x) + 1e-300
+    xd = to_device(x)
+    y_auto = dA.matvec(xd).cpu().numpy()
+    dA.set_kind(nat.SPMV_VECTOR)
+    y_vec = dA.matvec(xd).cpu().numpy()
+    dA.set_kind(nat.SPMV_MERGE)
+    y_merge = dA.matvec(xd).cpu().numpy()
+    for y in (y_auto, y_vec, y_merge):
+        assert np.max(np.abs(y - A @ x) / scale) < 1e-14
+
+
 def test_spmv_epilogues(cuda):
     import torch
     from pysolvers_b200 import _native as nat

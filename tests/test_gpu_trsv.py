@@ -180,6 +180,30 @@ def test_wide_levels_subwarp_rows(cuda):
         assert np.linalg.norm(x1 - ref) <= 1e-12 * np.linalg.norm(ref)
         with pytest.raises(Exception):
             dT.set_kernel('cta')                                 # 8-lanes-per-row chunks are the grid kernel's format
+        # per-chunk time stamps of the grid kernel (psb_trsv_set_trace, tools/trsv_levels.py): every chunk
+        # claimed before it is done, its first item inside the level-major order, no level done before
+        # the chunks it depends on were claimed; the traced solve gives the same bits
+        import ctypes as C
+        import torch
+        from pysolvers_b200 import _native as nat
+        from pysolvers_b200.device import ptr
+        g = info['groups']
+        buf = torch.zeros(3 * g, dtype=torch.int64, device='cuda')
+        nat.check(nat.lib().psb_trsv_set_trace(dT.handle, ptr(buf)), 'psb_trsv_set_trace')
+        x3 = dT.solve(to_device(v)).cpu().numpy()
+        nat.check(nat.lib().psb_trsv_set_trace(dT.handle, None), 'psb_trsv_set_trace')
+        assert np.array_equal(x3, x1)
+        t = buf.cpu().numpy().reshape(g, 3)
+        assert np.all(t[:, 0] > 0) and np.all(t[:, 1] >= t[:, 0])
+        lp = np.zeros(n_lev + 1, dtype=np.int32)
+        lr = np.zeros(n, dtype=np.int32)
+        nat.check(nat.lib().psb_trsv_get_levels(dT.handle, lp.ctypes.data_as(C.c_void_p), lr.ctypes.data_as(C.c_void_p)), 'levels')
+        lev = np.searchsorted(lp, t[:, 2], side='right') - 1
+        assert lev.min() == 0 and lev.max() == n_lev - 1 and np.all(np.diff(lev) >= 0)     # chunks are level-major
+        done = np.array([t[lev == l, 1].max() for l in range(n_lev)])
+        first = np.array([t[lev == l, 1].min() for l in range(n_lev)])
+        assert np.all(first[1:] >= first[:-1])                  # every row needs a row of the level before:
+        assert np.all(done[1:] >= first[:-1])                   # nothing of a level is done before that level began to finish
 
 
 def test_ic_apply_vs_reference_golden(cuda, golden):
