@@ -403,13 +403,23 @@ __device__ __forceinline__ void merge_search(int64_t d, const int* __restrict__ 
   row = lo; nz = d - lo;
 }
 
+// row coordinate of the merge path at the start of every tile (and at its end)
+__global__ void __launch_bounds__(kBlock)
+merge_coords_kernel(const int* __restrict__ rowptr, int64_t n_rows, int64_t nnz, int64_t n_tiles, int* __restrict__ tile_row) {
+  const int64_t total = n_rows + nnz;
+  for (int64_t t = blockIdx.x * (int64_t)kBlock + threadIdx.x; t <= n_tiles; t += (int64_t)gridDim.x * kBlock) {
+    int64_t r, k;
+    merge_search(min(t * kMergeTile, total), rowptr + 1, n_rows, nnz, r, k);
+    tile_row[t] = (int)r;
+  }
+}
+
 __global__ void __launch_bounds__(kBlock)
 spmv_merge_kernel(const psb_csr A, const double* x, double* __restrict__ ysum, int* __restrict__ carry_row,
                   double* __restrict__ carry_val, const int* __restrict__ d_skip) {
   __shared__ int s_end[kMergeTile + 2];
   __shared__ double s_acc[kMergeTile + 2];
   __shared__ double s_prod[kMergeTile];                      // the tile's products, staged with coalesced loads
-  __shared__ long long s_coord[4];
   __shared__ int s_key[kBlock];
   __shared__ double s_val[kBlock];
   if (d_skip != nullptr && ld_cg(d_skip) != 0) return;
@@ -419,24 +429,41 @@ spmv_merge_kernel(const psb_csr A, const double* x, double* __restrict__ ysum, i
   const int64_t n_tiles = (total + kMergeTile - 1) / kMergeTile;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t d0 = tile * kMergeTile, d1 = min(d0 + (int64_t)kMergeTile, total);
-    if (tid < 2) {
-      int64_t r, k;
-      merge_search(tid == 0 ? d0 : d1, row_end, A.n_rows, A.nnz, r, k);
-      s_coord[2 * tid] = r; s_coord[2 * tid + 1] = k;
-    }
-    __syncthreads();
-    const int64_t r0 = s_coord[0], r1 = s_coord[2];
-    const int64_t k0 = s_coord[1];
-    const int n_tk = (int)(s_coord[3] - k0);                  // entries of the tile
+    // tile boundaries on the merge path depend on the structure only: searched once when the kind is
+    // set (a binary search in global memory here cost ~20 dependent loads per tile, the whole CTA waiting)
+    const int64_t r0 = A.merge_tile_row[tile], r1 = A.merge_tile_row[tile + 1];
+    const int64_t k0 = d0 - r0;
+    const int n_tk = (int)((d1 - r1) - k0);                   // entries of the tile
     const int n_tr = (int)(r1 - r0) + 1;                      // rows touched; the last one may be partial
-    for (int i = tid; i < n_tr; i += kBlock) {
-      s_end[i] = r0 + i < A.n_rows ? row_end[r0 + i] : INT32_MAX;
-      s_acc[i] = 0.0;
+#pragma unroll
+    for (int u = 0; u <= kMergeItems; ++u) {                 // n_tr <= kMergeTile + 1: independent loads, unrolled
+      const int i = tid + u * kBlock;
+      if (i < n_tr) {
+        s_end[i] = r0 + i < A.n_rows ? row_end[r0 + i] : INT32_MAX;
+        s_acc[i] = 0.0;
+      }
     }
     // a thread's segment is kMergeItems CONSECUTIVE entries: read straight from global memory that is
     // a 56-byte stride between lanes (measured 1 TB/s); staged here, consecutive lanes read
     // consecutive entries
-    for (int i = tid; i < n_tk; i += kBlock) s_prod[i] = A.vals[k0 + i] * ld_ca(x + A.colind[k0 + i]);
+    {
+      // all of a thread's (up to kMergeItems) entries in flight: columns and values, then the gathers
+      int cc[kMergeItems];
+      double vv[kMergeItems], xx[kMergeItems];
+#pragma unroll
+      for (int u = 0; u < kMergeItems; ++u) {
+        const int i = tid + u * kBlock;
+        cc[u] = i < n_tk ? A.colind[k0 + i] : 0;
+        vv[u] = i < n_tk ? A.vals[k0 + i] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kMergeItems; ++u) xx[u] = (tid + u * kBlock) < n_tk ? ld_ca(x + cc[u]) : 0.0;
+#pragma unroll
+      for (int u = 0; u < kMergeItems; ++u) {
+        const int i = tid + u * kBlock;
+        if (i < n_tk) s_prod[i] = vv[u] * xx[u];
+      }
+    }
     __syncthreads();
     // this thread's segment
     const int64_t d = min(d0 + (int64_t)tid * kMergeItems, d1);
@@ -585,6 +612,9 @@ psb_csr csr_row_view(const psb_csr* A, int64_t r0, int64_t r1) {
     }
   }
   v.mega_grid = 0; v.mega_tile_rows = 0; v.mega_tile_nnz = 0;
+  // the merge path (tile coordinates, carries) belongs to the whole matrix: a row range of it runs
+  // on the sub-warp kernel
+  if (v.kind == PSB_SPMV_MERGE && (r0 != 0 || r1 != A->n_rows)) v.kind = PSB_SPMV_VECTOR;
   return v;
 }
 
@@ -644,11 +674,20 @@ static size_t lsu_smem(const psb_csr* A, int rpt) {
 static int merge_alloc(psb_csr* A) {
   const int64_t tiles = (A->n_rows + A->nnz + kMergeTile - 1) / kMergeTile + 1;
   if (A->merge_ysum != nullptr && A->merge_tiles >= tiles) return PSB_OK;
-  cudaFree(A->merge_ysum); cudaFree(A->merge_carry_row); cudaFree(A->merge_carry_val);
-  A->merge_ysum = nullptr; A->merge_carry_row = nullptr; A->merge_carry_val = nullptr; A->merge_tiles = 0;
+  cudaFree(A->merge_ysum); cudaFree(A->merge_carry_row); cudaFree(A->merge_carry_val); cudaFree(A->merge_tile_row);
+  A->merge_ysum = nullptr; A->merge_carry_row = nullptr; A->merge_carry_val = nullptr; A->merge_tile_row = nullptr;
+  A->merge_tiles = 0;
   PSB_CUDA(cudaMalloc((void**)&A->merge_ysum, (size_t)std::max<int64_t>(A->n_rows, 1) * sizeof(double)));
   PSB_CUDA(cudaMalloc((void**)&A->merge_carry_row, (size_t)tiles * sizeof(int)));
   PSB_CUDA(cudaMalloc((void**)&A->merge_carry_val, (size_t)tiles * sizeof(double)));
+  PSB_CUDA(cudaMalloc((void**)&A->merge_tile_row, (size_t)(tiles + 1) * sizeof(int)));
+  // set-up time: the legacy default stream orders this after the uploads of the caller's streams
+  const int64_t n_tiles = (A->n_rows + A->nnz + kMergeTile - 1) / kMergeTile;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_tiles + kBlock) / kBlock, (int64_t)sm_count() * 4));
+  PSB_CUDA(cudaDeviceSynchronize());
+  merge_coords_kernel<<<grid, kBlock>>>(A->rowptr, A->n_rows, A->nnz, n_tiles, A->merge_tile_row);
+  PSB_LAUNCH_CHECK();
+  PSB_CUDA(cudaDeviceSynchronize());
   A->merge_tiles = tiles;
   return PSB_OK;
 }
@@ -663,8 +702,8 @@ static void choose_kernel(psb_csr* A) {
   // serialise a thread-per-row or sub-warp-per-row kernel -> split the work, not the rows.  Only when
   // the longest row is a visible share of the matrix (>= nnz / 512): the sub-warp kernel walks a row at
   // ~0.1 us per 16 entries, so shorter rows hide behind the streaming of the rest, and the merge
-  // kernels run at ~40 % of its bandwidth (U12 block of the Bratu-2048^2 coarse LU, 691 200 x 8 192,
-  // 10.9 M entries: VECTOR 63 us, MERGE 114 us)
+  // kernels run at ~70 % of its bandwidth (U12 block of the Bratu-2048^2 coarse LU, 691 200 x 8 192,
+  // 10.9 M entries: VECTOR 52 us, MERGE 75 us)
   if (A->max_row >= 512 && (double)A->max_row >= 16.0 * std::max(mean, 2.0) &&
       (int64_t)A->max_row * 512 >= A->nnz && merge_alloc(A) == PSB_OK) {
     A->kind = PSB_SPMV_MERGE;
@@ -704,6 +743,7 @@ extern "C" int psb_csr_create(int64_t n_rows, int64_t n_cols, int64_t nnz,
   A->partials = nullptr; A->ticket = nullptr; A->colind16 = nullptr;
   A->mega_grid = 0; A->mega_tile_rows = 0; A->mega_tile_nnz = 0;
   A->merge_ysum = nullptr; A->merge_carry_row = nullptr; A->merge_carry_val = nullptr; A->merge_tiles = 0;
+  A->merge_tile_row = nullptr;
   int h_stats[4] = {0, 0, 0, 0};        // longest row, fullest 256- / 512-row tile, "a column delta does not fit 16 bits"
   int* d_stats = nullptr;
   cudaError_t e = cudaMalloc(&A->partials, sizeof(double) * A->max_grid);
@@ -771,7 +811,7 @@ extern "C" int psb_csr_destroy(psb_csr_t A) {
   if (A->partials) cudaFree(A->partials);
   if (A->ticket) cudaFree(A->ticket);
   if (A->colind16) cudaFree((void*)A->colind16);
-  cudaFree(A->merge_ysum); cudaFree(A->merge_carry_row); cudaFree(A->merge_carry_val);
+  cudaFree(A->merge_ysum); cudaFree(A->merge_carry_row); cudaFree(A->merge_carry_val); cudaFree(A->merge_tile_row);
   delete A;
   return PSB_OK;
 }

@@ -24,6 +24,7 @@ struct psb_csr {
   int*    merge_carry_row;
   double* merge_carry_val;
   int64_t merge_tiles;
+  int*    merge_tile_row;      // [tiles + 1] row coordinate of every tile boundary on the merge path (structure only)
   // persistent PCG kernel: tile plan cached per (grid) -- rows per tile and the fullest such tile
   int  mega_grid, mega_tile_rows, mega_tile_nnz;
 };
