@@ -509,8 +509,18 @@ int trsv_solve_cta(const psb_trsv* T, int cluster, const double* rhs, double* x,
   // each on a warp scheduler of its own (warp = chunk mod 16, scheduler = warp mod 4), and the
   // critical warp has the fourth to itself; a fourth spinner shares its scheduler and costs a
   // factor 2.  A pause inside the spin loop (nanosleep 20 - 50 ns) oversleeps and is worse.
-  const int near_chunks = (int)(2.0 * cpl + 1.5);
-  const int ns_q4 = std::max(1, (int)(16.0 * 64.0 / cpl));
+  // Swept again in round 2 on IC factors of 256^2 / 512^2 / 1024^2 (1.0 / 1.8 / 3.4 chunks per level,
+  // tools/trsv_probe.py with PSB_PROBE_SWEEP=1): the one-CTA kernel wants 2.5 levels of spinners once a
+  // level has more than one chunk, and a sleep of 64 ns per CHUNK of distance, not per level
+  // (IC 1024^2: 0.76 / 0.90 -> 0.66 / 0.68 us per level; IC 512^2: 0.56 -> 0.52 / 0.55; IC 256^2
+  // unchanged at 0.38).  The cluster kernel keeps the round-1 constants it was measured with.
+  // PSB_TRSV_NEAR_LEVELS / PSB_TRSV_SLEEP_NS (ns per level of distance): A/B knobs.
+  double near_levels = (kc == 1 && cpl >= 1.5) ? 2.5 : 2.0;
+  double sleep_ns = kc == 1 ? 64.0 * cpl : 64.0;
+  if (const char* e = getenv("PSB_TRSV_NEAR_LEVELS")) near_levels = atof(e);
+  if (const char* e = getenv("PSB_TRSV_SLEEP_NS")) sleep_ns = atof(e);
+  const int near_chunks = (int)(near_levels * cpl + 1.5);
+  const int ns_q4 = std::max(1, (int)(16.0 * sleep_ns / cpl));
   CtaView V{T->n, T->n_groups, T->wslots, T->n > T->wslots ? 1 : 0, T->stage_len, T->d_order, T->d_diag,
             reinterpret_cast<const int4*>(T->d_wmeta), T->d_wcols, T->d_vals, T->d_error,
             near_chunks, ns_q4, T->d_trace};

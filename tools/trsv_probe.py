@@ -8,7 +8,36 @@ from oracle import precond
 from pysolvers_b200.problems import fd_laplacian_2d, load_dh_matrix
 
 
+def sweep(T, lower, name):
+    """one-CTA kernel under different spin policies (PSB_TRSV_NEAR_LEVELS: levels that spin instead
+    of sleeping; PSB_TRSV_SLEEP_NS: sleep per level of distance)"""
+    dT = DeviceTrsv(T, lower=lower)
+    v = to_device(np.ones(T.shape[0]))
+    out = torch.empty_like(v)
+    dT.set_kernel('cta')
+    lv = dT.info()['levels']
+    row = []
+    nears = os.environ.get('PSB_PROBE_NEARS', '0.5 1.0 1.5 2.0 3.0 4.0').split()
+    sleeps = os.environ.get('PSB_PROBE_SLEEPS', '32 64 128').split()
+    for near in nears:
+        for ns in sleeps:
+            os.environ['PSB_TRSV_NEAR_LEVELS'], os.environ['PSB_TRSV_SLEEP_NS'] = near, ns
+            dT.solve(v, out)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                dT.solve(v, out)
+            e1.record()
+            torch.cuda.synchronize()
+            row.append('%s/%s: %.3f' % (near, ns, 1e3 * e0.elapsed_time(e1) / 10 / lv))
+    os.environ.pop('PSB_TRSV_NEAR_LEVELS'); os.environ.pop('PSB_TRSV_SLEEP_NS')
+    print('%-10s cta us/level by (levels that spin / sleep ns per level): %s' % (name, '  '.join(row)), flush=True)
+
+
 def bench(T, lower, name, unit=False, reps=5):
+    if os.environ.get('PSB_PROBE_SWEEP'):
+        return sweep(T, lower, name)
     dT = DeviceTrsv(T, lower=lower, unit_diag=unit)
     v = to_device(np.ones(T.shape[0]))
     out = torch.empty_like(v)
