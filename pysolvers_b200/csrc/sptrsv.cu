@@ -548,9 +548,15 @@ extern "C" int psb_trsv_create(int64_t n, const int32_t* h_rowptr, const int32_t
   // Thresholds measured on B200 (profiles/round1d_trsv.md, round1g_cluster.md).
   {
     const bool local = (double)T->n_far <= 0.02 * (double)std::max<int64_t>(T->nnz_off, 1);
+    // The cluster pays off for SHORT rows (Gauss-Seidel triangles, 2 entries per row: 0.77 - 0.87 us per
+    // level against 0.93 - 1.7 on one CTA at 4.5 - 8.5 chunks per level).  With the rows of an IC factor
+    // (~17 entries) one CTA stays ahead further up: IC 1536^2, 4.3 chunks per level, 0.87 against 1.15 us
+    // per level; IC 2048^2, 6.4 chunks per level, 1.22 against 1.30 (profiles/round2_amg.md).
+    const bool short_rows = (double)T->nnz_off <= 6.0 * (double)std::max<int64_t>(n, 1);
     if (T->n_subwarp > 0) { T->cluster_ok = 0; T->cta_ok = 0; }
     if (!local || T->n_subwarp > 0) T->kernel = PSB_TRSV_GRID;
     else if (cpl <= kTrsvCtaMaxChunksPerLevel) T->kernel = PSB_TRSV_CTA;
+    else if (cluster_cand && !short_rows && cpl <= 8.0) T->kernel = PSB_TRSV_CTA;
     else if (cluster_cand) T->kernel = PSB_TRSV_CLUSTER;
     else T->kernel = PSB_TRSV_GRID;
   }
