@@ -513,13 +513,16 @@ int trsv_solve_cta(const psb_trsv* T, int cluster, const double* rhs, double* x,
   // tools/trsv_probe.py with PSB_PROBE_SWEEP=1): the one-CTA kernel wants 2.5 levels of spinners once a
   // level has more than one chunk, and a sleep of 64 ns per CHUNK of distance, not per level
   // (IC 1024^2: 0.76 / 0.90 -> 0.66 / 0.68 us per level; IC 512^2: 0.56 -> 0.52 / 0.55; IC 256^2
-  // unchanged at 0.38).  The cluster kernel keeps the round-1 constants it was measured with.
+  // unchanged at 0.38).  The cluster of 4 (64 warps, 16 schedulers) wants FOUR levels of spinners, up to
+  // about half its warps, and 128 ns per level: Gauss-Seidel triangles of 256^2 / 384^2 / 512^2 grids
+  // 0.79 / 0.82 / 0.88 -> 0.60 / 0.63 / 0.66 us per level (PSB_PROBE_KERNEL=cluster).
   // PSB_TRSV_NEAR_LEVELS / PSB_TRSV_SLEEP_NS (ns per level of distance): A/B knobs.
-  double near_levels = (kc == 1 && cpl >= 1.5) ? 2.5 : 2.0;
-  double sleep_ns = kc == 1 ? 64.0 * cpl : 64.0;
+  double near_levels = kc == 1 ? (cpl >= 1.5 ? 2.5 : 2.0) : 4.0;
+  double sleep_ns = kc == 1 ? 64.0 * cpl : 128.0;
   if (const char* e = getenv("PSB_TRSV_NEAR_LEVELS")) near_levels = atof(e);
   if (const char* e = getenv("PSB_TRSV_SLEEP_NS")) sleep_ns = atof(e);
-  const int near_chunks = (int)(near_levels * cpl + 1.5);
+  int near_chunks = (int)(near_levels * cpl + 1.5);
+  if (kc > 1) near_chunks = std::min(near_chunks, 36);
   const int ns_q4 = std::max(1, (int)(16.0 * sleep_ns / cpl));
   CtaView V{T->n, T->n_groups, T->wslots, T->n > T->wslots ? 1 : 0, T->stage_len, T->d_order, T->d_diag,
             reinterpret_cast<const int4*>(T->d_wmeta), T->d_wcols, T->d_vals, T->d_error,

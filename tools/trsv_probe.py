@@ -14,7 +14,8 @@ def sweep(T, lower, name):
     dT = DeviceTrsv(T, lower=lower)
     v = to_device(np.ones(T.shape[0]))
     out = torch.empty_like(v)
-    dT.set_kernel('cta')
+    kern = os.environ.get('PSB_PROBE_KERNEL', 'cta')
+    dT.set_kernel(kern)
     lv = dT.info()['levels']
     row = []
     nears = os.environ.get('PSB_PROBE_NEARS', '0.5 1.0 1.5 2.0 3.0 4.0').split()
@@ -32,7 +33,7 @@ def sweep(T, lower, name):
             torch.cuda.synchronize()
             row.append('%s/%s: %.3f' % (near, ns, 1e3 * e0.elapsed_time(e1) / 10 / lv))
     os.environ.pop('PSB_TRSV_NEAR_LEVELS'); os.environ.pop('PSB_TRSV_SLEEP_NS')
-    print('%-10s cta us/level by (levels that spin / sleep ns per level): %s' % (name, '  '.join(row)), flush=True)
+    print('%-10s %s us/level by (levels that spin / sleep ns per level): %s' % (name, kern, '  '.join(row)), flush=True)
 
 
 def bench(T, lower, name, unit=False, reps=5):
