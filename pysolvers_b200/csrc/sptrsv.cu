@@ -85,6 +85,8 @@ struct TrsvView {
   int* error;
   int unit_diag;
   long long* trace;          // debugging (psb_trsv_set_trace): per chunk {claimed, done, first item}, null: off
+  int idle_trips;            // polls without progress before a warp starts to sleep between polls
+  unsigned int sleep_cap;    // longest sleep between two polls (ns)
 };
 
 __device__ __forceinline__ long long global_ns() {
@@ -188,7 +190,7 @@ trsv_solve_kernel(const TrsvView T, const double* __restrict__ rhs, double* x,
       }
       // warps whose dependencies are still levels away back off instead of hammering L2
       if (__any_sync(0xffffffffu, made_progress)) idle = 0;
-      else if (++idle > kIdleTrips) __nanosleep(idle < kIdleTrips + 8 ? 32u * (unsigned)(idle - kIdleTrips) : 256u);
+      else if (++idle > T.idle_trips) __nanosleep(min(32u * (unsigned)(idle - T.idle_trips), T.sleep_cap));
       if (!done) {
         if (is_long) {
           // the row is complete when every lane has consumed its share
@@ -259,7 +261,11 @@ int trsv_solve(const psb_trsv* T, const double* rhs, double* x, const int32_t* r
   int64_t warps_needed = std::min<int64_t>(T->n_groups, chunks_per_level * kLookahead);
   int64_t grid = std::min<int64_t>((int64_t)per_sm * sm_count(), (warps_needed + kWarps - 1) / kWarps);
   TrsvView V{T->n, T->n_groups, T->d_order, T->d_diag, T->d_grp_ptr, T->d_grp_item, T->d_grp_rows,
-             T->d_cols, T->d_vals, T->d_row_cnt, T->d_counter, T->d_error, T->unit_diag, T->d_trace};
+             T->d_cols, T->d_vals, T->d_row_cnt, T->d_counter, T->d_error, T->unit_diag, T->d_trace,
+             kIdleTrips, 256u};
+  // A/B knobs of the back-off (defaults above)
+  if (const char* e = getenv("PSB_TRSV_IDLE_TRIPS")) V.idle_trips = std::max(0, atoi(e));
+  if (const char* e = getenv("PSB_TRSV_SLEEP_CAP")) V.sleep_cap = (unsigned int)std::max(32, atoi(e));
   auto kern = T->d_trace != nullptr ? trsv_solve_kernel<true> : trsv_solve_kernel<false>;
   kern<<<(int)std::max<int64_t>(grid, 1), kBlock, 0, st>>>(V, rhs, x, rhs_map, out2, out_map, d_skip);
   PSB_LAUNCH_CHECK();

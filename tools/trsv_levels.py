@@ -102,6 +102,20 @@ def main():
             c.apply(cv, cz)
             torch.cuda.synchronize()
             torch.cuda.profiler.stop()
+        if '--backoff' in sys.argv:                  # back-off of waiting warps in the grid kernel
+            b1 = torch.ones(c.n1, dtype=torch.float64, device='cuda')
+            o1 = torch.empty_like(b1)
+            b2 = torch.ones(c.n1U, dtype=torch.float64, device='cuda')
+            o2 = torch.empty_like(b2)
+            for idle in (2, 5, 10, 20, 40):
+                for cap in (128, 256, 512, 1024, 2048, 4096):
+                    os.environ['PSB_TRSV_IDLE_TRIPS'], os.environ['PSB_TRSV_SLEEP_CAP'] = str(idle), str(cap)
+                    r = dict(idle_trips=idle, sleep_cap=cap,
+                             coarse_solve_ms=round(1e3 * time_gpu(lambda: c.apply(cv, cz)), 4),
+                             L11_us=round(1e6 * time_gpu(lambda: c.L11.solve(b1, o1)), 1),
+                             U11_us=round(1e6 * time_gpu(lambda: c.U11.solve(b2, o2)), 1))
+                    print(json.dumps(r), flush=True)
+            os.environ.pop('PSB_TRSV_IDLE_TRIPS'); os.environ.pop('PSB_TRSV_SLEEP_CAP')
         if '--spmv' in sys.argv:
             b = torch.ones(c.n1, dtype=torch.float64, device='cuda')
             xo = torch.empty_like(b)
